@@ -1,0 +1,327 @@
+// 3x3x3 stride-1 pad-1 Conv3d as an implicit GEMM on tcgen05 (sm_100a).
+//
+//   out[v, co] = sum_{tap, ci} in[v + off(tap), ci] * Wp[tap][co][ci]          (NDHWC bf16, fp32 accumulate)
+//
+// fprop and dgrad are the same kernel: dgrad feeds dY as `in` and a flipped/transposed weight pack.
+//
+// Mapping: M = 128 voxels arranged as a (bw x bh x bd) box, N = BN output channels, K = 27 taps x Cin.
+// Per (tap, 64-channel chunk) one TMA 5-D box load brings the shifted 128-voxel x KC-channel A tile
+// (out-of-volume voxels are zero-filled by TMA = the conv's zero padding) and one 2-D load brings the
+// BN x KC weight tile; both land 128B-swizzled, K-major, and feed tcgen05.mma (128 x BN x 16) with the
+// accumulator in TMEM (double-buffered so the epilogue of tile i overlaps the main loop of tile i+1).
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-5 epilogue.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b2 {
+
+struct IgemmParams {
+  int N, D, H, W;
+  int Cin, Cout;
+  int bw, bh, bd;
+  int tiles_w, tiles_h, tiles_d;
+  int n_tiles_n, BN;
+  int KC, n_chunks;
+  int stages;
+  int a_bytes, b_bytes;
+  int relu;
+  int ldy, y_coff;
+  __nv_bfloat16* y;
+  float* y32;          // optional fp32 output (same indexing, ld = ldy) instead of bf16
+  long long total_tiles;
+};
+
+static constexpr int kThreads = 192;
+static constexpr int kAccStride = 256;  // TMEM columns between the two accumulators
+
+__device__ __forceinline__ bool tap_active(int tap, int w0, int h0, int d0, const IgemmParams& p) {
+  const int dd = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
+  if (d0 + dd + p.bd <= 0 || d0 + dd >= p.D) return false;
+  if (h0 + dh + p.bh <= 0 || h0 + dh >= p.H) return false;
+  if (w0 + dw + p.bw <= 0 || w0 + dw >= p.W) return false;
+  return true;
+}
+
+__device__ __forceinline__ void decode_tile(long long tile, const IgemmParams& p, int& n, int& d0, int& h0,
+                                            int& w0, int& n0) {
+  const int nt = (int)(tile % p.n_tiles_n);
+  long long mt = tile / p.n_tiles_n;
+  const int tw = (int)(mt % p.tiles_w);
+  mt /= p.tiles_w;
+  const int th = (int)(mt % p.tiles_h);
+  mt /= p.tiles_h;
+  const int td = (int)(mt % p.tiles_d);
+  n = (int)(mt / p.tiles_d);
+  w0 = tw * p.bw;
+  h0 = th * p.bh;
+  d0 = td * p.bd;
+  n0 = nt * p.BN;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)p.stages * p.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * p.b_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.stages;
+  uint64_t* tmem_full = bars + 2 * p.stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int n, d0, h0, w0, n0;
+        decode_tile(tile, p, n, d0, h0, w0, n0);
+        for (int tap = 0; tap < 27; ++tap) {
+          if (!tap_active(tap, w0, h0, d0, p)) continue;
+          const int dd = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
+          for (int ch = 0; ch < p.n_chunks; ++ch) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_bytes + p.b_bytes));
+            tma_load_5d(smem_a + (size_t)stage * p.a_bytes, &tmap_a, &full[stage], ch * p.KC, w0 + dw, h0 + dh,
+                        d0 + dd, n);
+            tma_load_2d(smem_b + (size_t)stage * p.b_bytes, &tmap_b, &full[stage], ch * p.KC, tap * p.Cout + n0);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN, 0, 0);
+      const uint32_t layout = (p.KC == 64) ? SWZ_128B : SWZ_64B;
+      const uint32_t sbo = 8u * (uint32_t)p.KC * 2u;
+      const int ksteps = p.KC / 16;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        int n, d0, h0, w0, n0;
+        decode_tile(tile, p, n, d0, h0, w0, n0);
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        uint32_t accumulate = 0;
+        for (int tap = 0; tap < 27; ++tap) {
+          if (!tap_active(tap, w0, h0, d0, p)) continue;
+          for (int ch = 0; ch < p.n_chunks; ++ch) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(smem_a + (size_t)stage * p.a_bytes);
+            const uint32_t b_base = smem_u32(smem_b + (size_t)stage * p.b_bytes);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = make_smem_desc(a_base + k * 32, 16, sbo, layout);
+              const uint64_t bdesc = make_smem_desc(b_base + k * 32, 16, sbo, layout);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;     // accumulator row == voxel within the box
+    const int lw = row % p.bw;
+    const int lh = (row / p.bw) % p.bh;
+    const int ld = row / (p.bw * p.bh);
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      int n, d0, h0, w0, n0;
+      decode_tile(tile, p, n, d0, h0, w0, n0);
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int w = w0 + lw, h = h0 + lh, d = d0 + ld;
+      const bool valid = (w < p.W) && (h < p.H) && (d < p.D);
+      const size_t vox = (((size_t)n * p.D + d) * p.H + h) * p.W + w;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          if (p.y32 != nullptr) {
+            float4* dst = reinterpret_cast<float4*>(p.y32 + vox * p.ldy + p.y_coff + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o;
+              o.x = __uint_as_float(v[4 * j + 0]);
+              o.y = __uint_as_float(v[4 * j + 1]);
+              o.z = __uint_as_float(v[4 * j + 2]);
+              o.w = __uint_as_float(v[4 * j + 3]);
+              if (p.relu) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              }
+              dst[j] = o;
+            }
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(p.y + vox * p.ldy + p.y_coff + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                f[e] = __uint_as_float(v[8 * j + e]);
+                if (p.relu) f[e] = fmaxf(f[e], 0.f);
+              }
+              uint4 o;
+              o.x = pack_bf16x2(f[0], f[1]);
+              o.y = pack_bf16x2(f[2], f[3]);
+              o.z = pack_bf16x2(f[4], f[5]);
+              o.w = pack_bf16x2(f[6], f[7]);
+              dst[j] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// choose the (bw, bh, bd) box with bw*bh*bd == 128 that wastes the fewest padded voxels
+static void choose_box(int W, int H, int D, int& bw, int& bh, int& bd) {
+  long long best = -1;
+  for (int lw = 0; lw <= 7; ++lw)
+    for (int lh = 0; lw + lh <= 7; ++lh) {
+      const int ld = 7 - lw - lh;
+      const int cw = 1 << lw, chh = 1 << lh, cd = 1 << ld;
+      const long long cost = (long long)ceil_div(W, cw) * cw * (long long)ceil_div(H, chh) * chh *
+                             (long long)ceil_div(D, cd) * cd;
+      // tie-break: longer contiguous W runs, then H
+      const long long score = cost * 1024 - cw * 8 - chh;
+      if (best < 0 || score < best) {
+        best = score;
+        bw = cw;
+        bh = chh;
+        bd = cd;
+      }
+    }
+}
+
+int make_act_tmap(CUtensorMap* map, const void* base, int N, int D, int H, int W, int C, int ld, int coff,
+                  int box_c, int bw, int bh, int bd) {
+  const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+  const uint64_t e = 2;
+  const uint64_t strides[4] = {(uint64_t)ld * e, (uint64_t)W * ld * e, (uint64_t)H * W * ld * e,
+                               (uint64_t)D * H * W * ld * e};
+  const uint32_t box[5] = {(uint32_t)box_c, (uint32_t)bw, (uint32_t)bh, (uint32_t)bd, 1};
+  const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(base) + coff;
+  return encode_tmap_bf16(map, b, 5, dims, strides, box, box_c * 2);
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+// See include/unetsulc_b200.h for the contract.
+extern "C" int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff,
+                               int y_is_fp32, int N, int D, int H, int W, int Cin, int Cout, int relu,
+                               cudaStream_t stream) {
+  B2_REQUIRE(x && wpack && y, "b2_conv3d_igemm: null pointer");
+  B2_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "b2_conv3d_igemm: bad shape %dx%dx%dx%d", N, D, H, W);
+  B2_REQUIRE(Cin % 32 == 0 && Cin >= 32, "b2_conv3d_igemm: Cin=%d must be a multiple of 32", Cin);
+  B2_REQUIRE(Cout % 32 == 0 && Cout >= 32, "b2_conv3d_igemm: Cout=%d must be a multiple of 32", Cout);
+  B2_REQUIRE(ldx % 8 == 0 && x_coff % 8 == 0 && ldy % 8 == 0 && y_coff % 8 == 0,
+             "b2_conv3d_igemm: channel strides/offsets must be multiples of 8");
+  B2_REQUIRE(x_coff + Cin <= ldx && y_coff + Cout <= ldy, "b2_conv3d_igemm: channel window out of range");
+
+  IgemmParams p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  choose_box(W, H, D, p.bw, p.bh, p.bd);
+  p.tiles_w = ceil_div(W, p.bw);
+  p.tiles_h = ceil_div(H, p.bh);
+  p.tiles_d = ceil_div(D, p.bd);
+  // N tile: largest divisor of Cout that is a multiple of 32 and <= 256
+  int BN = 0;
+  for (int c = 256; c >= 32; c -= 32)
+    if (Cout % c == 0) { BN = c; break; }
+  B2_REQUIRE(BN > 0, "b2_conv3d_igemm: no N tile for Cout=%d", Cout);
+  p.BN = BN;
+  p.n_tiles_n = Cout / BN;
+  p.KC = (Cin % 64 == 0) ? 64 : 32;
+  p.n_chunks = Cin / p.KC;
+  p.a_bytes = 128 * p.KC * 2;
+  p.b_bytes = BN * p.KC * 2;
+  const int smem_budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
+  p.stages = smem_budget / (p.a_bytes + p.b_bytes);
+  if (p.stages > 12) p.stages = 12;
+  B2_REQUIRE(p.stages >= 2, "b2_conv3d_igemm: tile does not fit shared memory");
+  p.relu = relu;
+  p.ldy = ldy; p.y_coff = y_coff;
+  p.y = y_is_fp32 ? nullptr : reinterpret_cast<__nv_bfloat16*>(y);
+  p.y32 = y_is_fp32 ? reinterpret_cast<float*>(y) : nullptr;
+  p.total_tiles = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles_n;
+
+  CUtensorMap ta, tb;
+  int rc = make_act_tmap(&ta, x, N, D, H, W, Cin, ldx, x_coff, p.KC, p.bw, p.bh, p.bd);
+  if (rc) return rc;
+  {
+    const uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)27 * Cout};
+    const uint64_t strides[1] = {(uint64_t)Cin * 2};
+    const uint32_t box[2] = {(uint32_t)p.KC, (uint32_t)BN};
+    rc = encode_tmap_bf16(&tb, wpack, 2, dims, strides, box, p.KC * 2);
+    if (rc) return rc;
+  }
+  const size_t smem_bytes = (size_t)p.stages * (p.a_bytes + p.b_bytes) + 1024 + 512;
+  B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  conv3d_igemm_kernel<<<(unsigned)grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+  B2_CHECK_CUDA(cudaGetLastError());
+  return B2_OK;
+}

@@ -1,0 +1,290 @@
+// Weight gradient of the 3x3x3 stride-1 pad-1 Conv3d on tcgen05 (sm_100a).
+//
+//   dW[co][ci][tap] = sum_v dY[v, co] * X[v + off(tap), ci]                       (NDHWC bf16, fp32 accumulate)
+//
+// GEMM view: the reduction (K) runs over voxels, so both operands sit in shared memory "MN-major":
+// a TMA box load of 128 voxels x 64 channels lands as [voxel row][128 B of channels], 128B-swizzled, which is
+// exactly the canonical MN-major UMMA layout (64-element atoms along M/N at stride LBO, 8-voxel groups along K
+// at stride SBO).  A = shifted X tiles ("slots" = (tap, 64-channel chunk); 128/SWC slots stacked along M),
+// B = the un-shifted dY tile (N = BN output channels, loaded once per 128-voxel K-step and reused by every
+// slot group).  Each CTA owns up to 512/BN accumulators (slot groups) in TMEM and a contiguous range of
+// K-steps; partial results go to a fp32 workspace [split][tap][ci][co] and a second kernel reduces the splits
+// deterministically into PyTorch's [co][ci][kd][kh][kw] layout.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b2 {
+
+int make_act_tmap(CUtensorMap* map, const void* base, int N, int D, int H, int W, int C, int ld, int coff,
+                  int box_c, int bw, int bh, int bd);
+
+struct WgradParams {
+  int N, D, H, W;
+  int Cin, Cout;
+  int bw, bh, bd;
+  int tiles_w, tiles_h, tiles_d;
+  int SWC, n_cchunks, total_slots, SPG;  // slot width (channels), chunks per tap, slots, slots per group
+  int G, gpc, n_gchunks;                 // groups, groups per CTA chunk, number of chunks
+  int BN, n_cout_tiles;
+  int splits;
+  long long ksteps_total;
+  int stages_a;
+  int a_bytes, b_bytes, slot_bytes;
+  float* ws;
+};
+
+static constexpr int kWgThreads = 192;
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                    const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem;                                   // 2 x dY tile
+  uint8_t* smem_a = smem + 2 * (size_t)p.b_bytes;           // stages_a x slot group
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages_a * p.a_bytes);
+  uint64_t* full_a = bars;
+  uint64_t* empty_a = bars + p.stages_a;
+  uint64_t* full_b = bars + 2 * p.stages_a;
+  uint64_t* empty_b = full_b + 2;
+  uint64_t* acc_full = empty_b + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int gchunk = blockIdx.x % p.n_gchunks;
+  const int nt = blockIdx.x / p.n_gchunks;
+  const int split = blockIdx.y;
+  const int g_begin = gchunk * p.gpc;
+  const int g_end = min(g_begin + p.gpc, p.G);
+  const int n0 = nt * p.BN;
+  const long long t_begin = p.ksteps_total * split / p.splits;
+  const long long t_end = p.ksteps_total * (split + 1) / p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_dy);
+    for (int s = 0; s < p.stages_a; ++s) {
+      mbar_init(&full_a[s], 1);
+      mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full_b[s], 1);
+      mbar_init(&empty_b[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (long long t = t_begin; t < t_end; ++t) {
+        long long mt = t;
+        const int w0 = (int)(mt % p.tiles_w) * p.bw;
+        mt /= p.tiles_w;
+        const int h0 = (int)(mt % p.tiles_h) * p.bh;
+        mt /= p.tiles_h;
+        const int d0 = (int)(mt % p.tiles_d) * p.bd;
+        const int n = (int)(mt / p.tiles_d);
+        // dY tile (B operand): BN/64 column blocks of [128 voxels][64 channels]
+        mbar_wait(&empty_b[sb], pb ^ 1);
+        mbar_arrive_expect_tx(&full_b[sb], (uint32_t)p.b_bytes);
+        for (int j = 0; j < p.BN / 64; ++j)
+          tma_load_5d(smem_b + (size_t)sb * p.b_bytes + (size_t)j * 16384, &tmap_dy, &full_b[sb], n0 + j * 64, w0,
+                      h0, d0, n);
+        if (++sb == 2) { sb = 0; pb ^= 1; }
+        for (int g = g_begin; g < g_end; ++g) {
+          mbar_wait(&empty_a[sa], pa ^ 1);
+          mbar_arrive_expect_tx(&full_a[sa], (uint32_t)p.a_bytes);
+          for (int j = 0; j < p.SPG; ++j) {
+            int s = g * p.SPG + j;
+            if (s >= p.total_slots) s = p.total_slots - 1;  // padding slot: result discarded
+            const int tap = s / p.n_cchunks, cc = s % p.n_cchunks;
+            const int dd = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
+            tma_load_5d(smem_a + (size_t)sa * p.a_bytes + (size_t)j * p.slot_bytes, &tmap_x, &full_a[sa],
+                        cc * p.SWC, w0 + dw, h0 + dh, d0 + dd, n);
+          }
+          if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN, 1, 1);
+      const uint32_t layout_a = (p.SWC == 64) ? SWZ_128B : SWZ_64B;
+      const uint32_t row_a = (uint32_t)p.SWC * 2u;
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (long long t = t_begin; t < t_end; ++t) {
+        mbar_wait(&full_b[sb], pb);
+        tc_fence_after();
+        const uint32_t b_base = smem_u32(smem_b + (size_t)sb * p.b_bytes);
+        for (int g = g_begin; g < g_end; ++g) {
+          mbar_wait(&full_a[sa], pa);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem_a + (size_t)sa * p.a_bytes);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(g - g_begin) * p.BN;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // 128 voxels = 8 x K16
+            const uint64_t adesc = make_smem_desc(a_base + k * 16 * row_a, (uint32_t)p.slot_bytes, 8 * row_a, layout_a);
+            const uint64_t bdesc = make_smem_desc(b_base + k * 16 * 128, 16384, 1024, SWZ_128B);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (t != t_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_a[sa]);
+          if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(&empty_b[sb]);
+        if (++sb == 2) { sb = 0; pb ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    for (int g = g_begin; g < g_end; ++g) {
+      const int s = g * p.SPG + row / p.SWC;
+      const bool valid = (s < p.total_slots) && (t_end > t_begin);
+      const int tap = s / p.n_cchunks;
+      const int ci = (s % p.n_cchunks) * p.SWC + row % p.SWC;
+      float* dst = p.ws + (((size_t)split * 27 + tap) * p.Cin + ci) * p.Cout + n0;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g - g_begin) * p.BN;
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          float4* d4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dW[co][ci][tap] = sum_s ws[s][tap][ci][co]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int Cin,
+                                    int Cout) {
+  const long long total = 27LL * Cin * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(long long)s * total + i];
+    const int co = (int)(i % Cout);
+    const long long r = i / Cout;
+    const int ci = (int)(r % Cin);
+    const int tap = (int)(r / Cin);
+    dw[((long long)co * Cin + ci) * 27 + tap] = acc;
+  }
+}
+
+static void choose_box_w(int W, int H, int D, int& bw, int& bh, int& bd) {
+  long long best = -1;
+  for (int lw = 0; lw <= 7; ++lw)
+    for (int lh = 0; lw + lh <= 7; ++lh) {
+      const int ld = 7 - lw - lh;
+      const int cw = 1 << lw, chh = 1 << lh, cd = 1 << ld;
+      const long long cost = (long long)ceil_div(W, cw) * cw * (long long)ceil_div(H, chh) * chh *
+                             (long long)ceil_div(D, cd) * cd;
+      const long long score = cost * 1024 - cw * 8 - chh;
+      if (best < 0 || score < best) { best = score; bw = cw; bh = chh; bd = cd; }
+    }
+}
+
+static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int Cout) {
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  choose_box_w(W, H, D, p.bw, p.bh, p.bd);
+  p.tiles_w = ceil_div(W, p.bw);
+  p.tiles_h = ceil_div(H, p.bh);
+  p.tiles_d = ceil_div(D, p.bd);
+  p.SWC = (Cin % 64 == 0) ? 64 : 32;
+  p.n_cchunks = Cin / p.SWC;
+  p.total_slots = 27 * p.n_cchunks;
+  p.SPG = 128 / p.SWC;
+  p.G = ceil_div(p.total_slots, p.SPG);
+  p.BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  p.n_cout_tiles = Cout / p.BN;
+  const int P = 512 / p.BN;
+  p.n_gchunks = ceil_div(p.G, P);
+  p.gpc = ceil_div(p.G, p.n_gchunks);
+  p.n_gchunks = ceil_div(p.G, p.gpc);
+  p.ksteps_total = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
+  const int base_ctas = p.n_gchunks * p.n_cout_tiles;
+  int splits = num_sms() / base_ctas;
+  if (splits < 1) splits = 1;
+  if ((long long)splits > p.ksteps_total) splits = (int)p.ksteps_total;
+  p.splits = splits;
+  p.slot_bytes = 128 * p.SWC * 2;
+  p.a_bytes = 128 * 128 * 2;
+  p.b_bytes = 128 * p.BN * 2;
+  const int budget = 227 * 1024 - 1024 - 512;
+  p.stages_a = (budget - 2 * p.b_bytes) / p.a_bytes;
+  if (p.stages_a > 5) p.stages_a = 5;
+  return p.stages_a >= 2 ? 0 : -1;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" long long b2_conv3d_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout) {
+  if (Cin % 32 != 0 || Cout % 64 != 0 || N <= 0 || D <= 0 || H <= 0 || W <= 0) return -1;
+  WgradParams p;
+  if (plan_wgrad(p, N, D, H, W, Cin, Cout) != 0) return -1;
+  return (long long)p.splits * 27 * Cin * Cout * (long long)sizeof(float);
+}
+
+extern "C" int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* dy, int ldy, int y_coff, float* dw,
+                               void* workspace, long long workspace_bytes, int N, int D, int H, int W, int Cin,
+                               int Cout, cudaStream_t stream) {
+  B2_REQUIRE(x && dy && dw && workspace, "b2_conv3d_wgrad: null pointer");
+  B2_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "b2_conv3d_wgrad: bad shape");
+  B2_REQUIRE(Cin % 32 == 0 && Cin >= 32, "b2_conv3d_wgrad: Cin=%d must be a multiple of 32", Cin);
+  B2_REQUIRE(Cout % 64 == 0 && Cout >= 64, "b2_conv3d_wgrad: Cout=%d must be a multiple of 64", Cout);
+  B2_REQUIRE(ldx % 8 == 0 && x_coff % 8 == 0 && ldy % 8 == 0 && y_coff % 8 == 0,
+             "b2_conv3d_wgrad: channel strides/offsets must be multiples of 8");
+  WgradParams p;
+  B2_REQUIRE(plan_wgrad(p, N, D, H, W, Cin, Cout) == 0, "b2_conv3d_wgrad: tile does not fit shared memory");
+  const long long need = (long long)p.splits * 27 * Cin * Cout * (long long)sizeof(float);
+  B2_REQUIRE(workspace_bytes >= need, "b2_conv3d_wgrad: workspace %lld < %lld bytes", workspace_bytes, need);
+  p.ws = reinterpret_cast<float*>(workspace);
+
+  CUtensorMap tx, ty;
+  int rc = make_act_tmap(&tx, x, N, D, H, W, Cin, ldx, x_coff, p.SWC, p.bw, p.bh, p.bd);
+  if (rc) return rc;
+  rc = make_act_tmap(&ty, dy, N, D, H, W, Cout, ldy, y_coff, 64, p.bw, p.bh, p.bd);
+  if (rc) return rc;
+
+  const size_t smem_bytes = 2 * (size_t)p.b_bytes + (size_t)p.stages_a * p.a_bytes + 1024 + 512;
+  B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  dim3 grid((unsigned)(p.n_gchunks * p.n_cout_tiles), (unsigned)p.splits);
+  conv3d_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tx, ty, p);
+  B2_CHECK_CUDA(cudaGetLastError());
+  const long long total = 27LL * Cin * Cout;
+  int rblocks = (int)((total + 255) / 256);
+  if (rblocks > num_sms() * 8) rblocks = num_sms() * 8;
+  wgrad_reduce_kernel<<<rblocks, 256, 0, stream>>>(p.ws, dw, p.splits, Cin, Cout);
+  B2_CHECK_CUDA(cudaGetLastError());
+  return B2_OK;
+}

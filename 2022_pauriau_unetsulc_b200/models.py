@@ -1,0 +1,398 @@
+"""B200-native ``UNet3D`` — drop-in for ``deepsulci.deeptools.models.UNet3D`` as the reference uses it.
+
+Reference call sites (relative to /root/reference): ctor ``training.py:65-67``, ``pattern_class.py:352-356``,
+``transfer_learning/transfer_learning.py:155-157``; ``model(inputs)`` ``training.py:206``, ``pattern_class.py:266``;
+post-construction ``model.final_conv = nn.Conv3d(...)`` ``pattern_class.py:364``; prefix freezing by
+``named_parameters`` ``transfer_learning/transfer_learning.py:330-335``; ``state_dict`` / ``.mdsm``
+``pattern_class.py:304,366``.
+
+The module holds ordinary fp32 ``nn.Parameter`` s under the upstream names (so ``state_dict``, ``deepcopy``,
+``optim.SGD(model.parameters())`` and ``requires_grad`` masks keep working), but ``forward`` / ``backward`` never call
+``nn.Conv3d`` / ``nn.GroupNorm``: they read the parameters and enqueue the hand-written sm_100a kernels of
+``libunetsulc_b200.so`` (NDHWC bf16 activations, fp32 accumulation and statistics).  There is no CPU fallback.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import ActView
+
+GN_EPS = 1e-5
+
+
+def _double_conv(in_ch, out_ch, encoder, order, num_groups):
+    if encoder:
+        c1 = (in_ch, max(out_ch // 2, in_ch))
+        c2 = (c1[1], out_ch)
+    else:
+        c1 = (in_ch, out_ch)
+        c2 = (out_ch, out_ch)
+    seq = nn.Sequential()
+    for pos, (ci, co) in ((1, c1), (2, c2)):
+        seq.add_module("conv%d" % pos, nn.Conv3d(ci, co, 3, padding=1, bias=False))
+        seq.add_module("relu%d" % pos, nn.ReLU())
+        seq.add_module("norm%d" % pos, nn.GroupNorm(num_groups, co, eps=GN_EPS))
+    return seq
+
+
+class _Block(nn.Module):
+    """Parameter holder for one encoder / decoder level (names match upstream: ``double_conv.conv1`` ...)."""
+
+    def __init__(self, in_ch, out_ch, encoder, order, num_groups, is_max_pool=False):
+        super().__init__()
+        self.is_max_pool = is_max_pool
+        self.double_conv = _double_conv(in_ch, out_ch, encoder, order, num_groups)
+
+    def forward(self, *a, **k):  # never used: the network is executed by UNet3D as a whole
+        raise RuntimeError("unetsulc_b200 blocks are parameter holders; call UNet3D.forward")
+
+
+class _ConvLayer(object):
+    """One (conv, norm) pair with its packed bf16 weights (re-packed when the fp32 master changes)."""
+
+    def __init__(self, conv, norm):
+        self.conv, self.norm = conv, norm
+        self.cin, self.cout = conv.in_channels, conv.out_channels
+        self._key = None
+        self.wf = self.wd = None
+
+    def packs(self):
+        w = self.conv.weight
+        key = (w._version, w.data_ptr(), str(w.device))
+        if key != self._key:
+            if self.cin == 1:
+                self.wf, self.wd = None, None
+            else:
+                self.wf, self.wd = ops.pack_conv_weights(w)
+            self._key = key
+        return self.wf, self.wd
+
+
+class _Saved(object):
+    """Activations kept between forward and backward (all bf16 NDHWC)."""
+    pass
+
+
+class UNet3D(nn.Module):
+    def __init__(self, in_channels, out_channels, final_sigmoid=False, interpolate=True, dropout=0.,
+                 conv_layer_order='crg', init_channel_number=64):
+        super().__init__()
+        if in_channels != 1:
+            raise ValueError("unetsulc_b200.UNet3D: in_channels=%r unsupported (skeleton volumes have 1)" % in_channels)
+        if conv_layer_order != 'crg':
+            raise ValueError("unetsulc_b200.UNet3D: conv_layer_order=%r unsupported ('crg' only)" % conv_layer_order)
+        if not interpolate:
+            raise ValueError("unetsulc_b200.UNet3D: interpolate=False (transposed conv) unsupported")
+        if final_sigmoid:
+            raise ValueError("unetsulc_b200.UNet3D: final_sigmoid=True unsupported (softmax head)")
+        if dropout not in (0, 0., None):
+            raise ValueError("unetsulc_b200.UNet3D: dropout=%r unsupported (reference passes 0.)" % dropout)
+        f = init_channel_number
+        if f != 64:
+            raise ValueError("unetsulc_b200.UNet3D: init_channel_number=%r unsupported (64 only: the tcgen05 conv "
+                             "kernels need channel counts that are multiples of 32/64)" % f)
+        g = min(f // 2, 32)
+        self.num_groups = g
+        self.init_channel_number = f
+        o = conv_layer_order
+        self.encoders = nn.ModuleList([
+            _Block(in_channels, f, True, o, g, False),
+            _Block(f, 2 * f, True, o, g, True),
+            _Block(2 * f, 4 * f, True, o, g, True),
+            _Block(4 * f, 8 * f, True, o, g, True)])
+        self.decoders = nn.ModuleList([
+            _Block(4 * f + 8 * f, 4 * f, False, o, g),
+            _Block(2 * f + 4 * f, 2 * f, False, o, g),
+            _Block(f + 2 * f, f, False, o, g)])
+        self.final_conv = nn.Conv3d(f, out_channels, 1)
+        self.final_activation = nn.Softmax(dim=1)
+        self._layers_cache = None
+        # data-parallel hook: called as hook(name_prefix, [grad tensors]) when a level's gradients are ready
+        self.grad_ready_hook = None
+
+    # ------------------------------------------------------------------------------------------ plumbing
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k == "_layers_cache":
+                new.__dict__[k] = None
+            else:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    def _layers(self):
+        if self._layers_cache is None:
+            L = []
+            for blk in list(self.encoders) + list(self.decoders):
+                dc = blk.double_conv
+                L.append(_ConvLayer(dc.conv1, dc.norm1))
+                L.append(_ConvLayer(dc.conv2, dc.norm2))
+            self._layers_cache = L
+        return self._layers_cache
+
+    def _head(self):
+        fc = self.final_conv
+        if isinstance(fc, nn.Sequential):
+            raise RuntimeError("unetsulc_b200.UNet3D: final_conv = nn.Sequential (num_conv > 1) is not supported by "
+                               "the B200 head kernels; use num_conv = 1")
+        if not isinstance(fc, nn.Conv3d) or tuple(fc.kernel_size) != (1, 1, 1):
+            raise RuntimeError("unetsulc_b200.UNet3D: final_conv must be a 1x1x1 nn.Conv3d")
+        return fc
+
+    def trunk_parameters(self):
+        """Parameters in the order the autograd functions take them (14 x (w, gamma, beta))."""
+        ps = []
+        for l in self._layers():
+            ps += [l.conv.weight, l.norm.weight, l.norm.bias]
+        return ps
+
+    def _check_input(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("unetsulc_b200.UNet3D runs on a B200 (sm_100a) only: input is on %s and there is no "
+                               "CPU fallback" % x.device)
+        if x.dim() != 5 or x.shape[1] != 1:
+            raise RuntimeError("unetsulc_b200.UNet3D: expected input [B,1,D,H,W], got %s" % (tuple(x.shape),))
+        p = self.final_conv.weight if isinstance(self.final_conv, nn.Conv3d) else None
+        if not self.encoders[0].double_conv.conv1.weight.is_cuda:
+            raise RuntimeError("unetsulc_b200.UNet3D: parameters are on CPU; call model.to('cuda') (no CPU fallback)")
+        x = x.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        return x.contiguous()
+
+    # ------------------------------------------------------------------------------------------ trunk forward
+    def _trunk_forward(self, x, save):
+        """x fp32 [B,1,D,H,W] -> feature ActView [B,D,H,W,f]; fills `save` (a _Saved) when not None."""
+        L = self._layers()
+        B, _, D0, H0, W0 = x.shape
+        dev = x.device
+        G = self.num_groups
+        dims = [(D0, H0, W0)]
+        for _ in range(3):
+            d, h, w = dims[-1]
+            dims.append((d // 2, h // 2, w // 2))
+        if min(dims[3]) < 1:
+            raise RuntimeError("unetsulc_b200.UNet3D: volume %s too small for 3 poolings" % ((D0, H0, W0),))
+        f = self.init_channel_number
+        skip_c = [f, 2 * f, 4 * f]                 # channels of encoder 0..2 outputs (skips)
+        up_c = [2 * f, 4 * f, 8 * f]               # channels upsampled into cat at level 0..2
+        cats = [ActView.alloc(B, *dims[l], skip_c[l] + up_c[l], dev) for l in range(3)]
+        rec = []                                   # per conv layer: dict(x=ActView|tensor, r=ActView, mr=tensor)
+
+        def conv_gn(layer, xin, out_view, pooled=None, first=False):
+            cin, cout = layer.cin, layer.cout
+            d, h, w = (out_view.D, out_view.H, out_view.W)
+            r = ActView.alloc(B, d, h, w, cout, dev)
+            if first:
+                ops.conv3d_first_fwd(xin, layer.conv.weight.detach(), r, relu=True)
+            else:
+                wf, _ = layer.packs()
+                ops.conv3d_igemm(xin, wf, r, cin, cout, relu=True)
+            mr, ss = ops.relu_gn_stats(r, G, layer.norm.eps, layer.norm.weight.detach(), layer.norm.bias.detach())
+            ops.relu_gn_apply(r, ss, out_view, pooled)
+            rec.append(dict(x=xin, r=r, mr=mr))
+
+        cur = x
+        li = 0
+        # encoders
+        for lvl in range(4):
+            d, h, w = dims[lvl]
+            y1 = ActView.alloc(B, d, h, w, L[li].cout, dev)
+            conv_gn(L[li], cur, y1, first=(lvl == 0))
+            li += 1
+            if lvl < 3:
+                out = cats[lvl].window(0, skip_c[lvl])
+                pooled = ActView.alloc(B, *dims[lvl + 1], skip_c[lvl], dev)
+                conv_gn(L[li], y1, out, pooled=pooled)
+                cur = pooled
+            else:
+                out = ActView.alloc(B, d, h, w, L[li].cout, dev)
+                conv_gn(L[li], y1, out)
+                cur = out
+            li += 1
+        # decoders
+        for k, lvl in enumerate((2, 1, 0)):
+            d, h, w = dims[lvl]
+            ops.upcat_fwd(cur, cats[lvl].window(skip_c[lvl], up_c[lvl]))
+            y1 = ActView.alloc(B, d, h, w, L[li].cout, dev)
+            conv_gn(L[li], cats[lvl], y1)
+            li += 1
+            y2 = ActView.alloc(B, d, h, w, L[li].cout, dev)
+            conv_gn(L[li], y1, y2)
+            li += 1
+            cur = y2
+        if save is not None:
+            save.rec, save.cats, save.dims, save.x = rec, cats, dims, x
+            save.skip_c, save.up_c = skip_c, up_c
+        return cur
+
+    # ------------------------------------------------------------------------------------------ trunk backward
+    def _trunk_backward(self, save, dfeat, needs):
+        """dfeat: ActView gradient w.r.t. the trunk output.  needs: list of 42 bools (w, gamma, beta per layer).
+        Returns list of 42 grads (None where not needed)."""
+        L = self._layers()
+        G = self.num_groups
+        rec, cats, dims = save.rec, save.cats, save.dims
+        skip_c, up_c = save.skip_c, save.up_c
+        grads = [None] * 42
+        first_needed = None
+        for i in range(14):
+            if needs[3 * i] or needs[3 * i + 1] or needs[3 * i + 2]:
+                first_needed = i
+                break
+        if first_needed is None:
+            return grads
+        hook = self.grad_ready_hook
+
+        def layer_bwd(i, dy):
+            """dy: gradient w.r.t. the GN output of layer i.  Returns gradient w.r.t. the layer input (or None)."""
+            layer, rc = L[i], rec[i]
+            want_gb = needs[3 * i + 1] or needs[3 * i + 2]
+            dr, dg, db = ops.relu_gn_bwd(dy, rc["r"], G, layer.norm.weight.detach(), rc["mr"], want_gb)
+            if needs[3 * i + 1]:
+                grads[3 * i + 1] = dg
+            if needs[3 * i + 2]:
+                grads[3 * i + 2] = db
+            if needs[3 * i]:
+                if layer.cin == 1:
+                    grads[3 * i] = ops.conv3d_first_wgrad(rc["x"], dr, layer.cout)
+                else:
+                    grads[3 * i] = ops.conv3d_wgrad(rc["x"], dr, layer.cin, layer.cout)
+            if hook is not None:
+                hook(i, [g for g in grads[3 * i:3 * i + 3] if g is not None])
+            if i <= first_needed or layer.cin == 1:
+                return None
+            xin = rc["x"]
+            dx = ActView.alloc(xin.N, xin.D, xin.H, xin.W, layer.cin, dr.buf.device)
+            _, wd = layer.packs()
+            ops.conv3d_igemm(dr, wd, dx, layer.cout, layer.cin, relu=False)
+            return dx
+
+        dy = dfeat
+        dcat = [None, None, None]
+        # decoders: layers 13,12 (lvl 0), 11,10 (lvl 1), 9,8 (lvl 2)
+        li = 13
+        for lvl in (0, 1, 2):
+            dy = layer_bwd(li, dy)
+            li -= 1
+            if dy is None:
+                return grads
+            dc = layer_bwd(li, dy)
+            li -= 1
+            if dc is None:
+                return grads
+            dcat[lvl] = dc
+            dy = ops.upcat_bwd(dc.window(skip_c[lvl], up_c[lvl]), *dims[lvl + 1])
+        # encoders: layers 7,6 (lvl 3) ... 1,0 (lvl 0)
+        for lvl in (3, 2, 1, 0):
+            if lvl < 3:
+                ywin = cats[lvl].window(0, skip_c[lvl])
+                dy = ops.maxpool3d_bwd_add(ywin, dcat[lvl].window(0, skip_c[lvl]), dy)
+            dy = layer_bwd(li, dy)
+            li -= 1
+            if dy is None:
+                return grads
+            dy = layer_bwd(li, dy)
+            li -= 1
+            if dy is None:
+                return grads
+        return grads
+
+    # ------------------------------------------------------------------------------------------ public API
+    def forward(self, x):
+        """Dense nn.Module surface: logits [B,C,D,H,W] fp32 in train(), Softmax(dim=1) in eval()."""
+        x = self._check_input(x)
+        head = self._head()
+        params = self.trunk_parameters() + [head.weight, head.bias]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _DenseFunction.apply(self, x, not self.training, *params)
+        feat = self._trunk_forward(x, None)
+        return ops.head_dense_fwd(feat, head.weight.detach(), head.bias.detach(), softmax=not self.training)
+
+    def loss_and_preds(self, x, labels):
+        """Fused head: CrossEntropyLoss(ignore_index=-1)(model(x), labels) and torch.max(model(x), 1)[1] at the
+        labelled voxels, without materialising the dense [B,C,D,H,W] tensor.  In eval() the loss is the reference's
+        val-phase loss (CE applied to the Softmax outputs, training.py:189,205-208).
+        Returns (loss: 0-dim fp32 tensor wired into autograd, preds: int32 [B,D,H,W], -1 where unlabelled)."""
+        x = self._check_input(x)
+        head = self._head()
+        params = self.trunk_parameters() + [head.weight, head.bias]
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in params):
+            return _FusedLossFunction.apply(self, x, labels, *params)
+        feat = self._trunk_forward(x, None)
+        out = ops.head_ce(feat, labels, head.weight.detach(), head.bias.detach(), compute_grad=False,
+                          eval_softmax=not self.training)
+        return out["loss"][0], out["preds"]
+
+    def scores_at(self, x, index):
+        """Eval forward + Softmax scores gathered at linear voxel indices (labeling(), pattern_class.py:266-277).
+        Returns (scores fp32 [n, C], preds int32 [n])."""
+        x = self._check_input(x)
+        head = self._head()
+        with torch.no_grad():
+            feat = self._trunk_forward(x, None)
+            return ops.head_gather(feat, index, head.weight.detach(), head.bias.detach(), softmax=True)
+
+
+def _needs(ctx_needs, offset):
+    return list(ctx_needs[offset:offset + 42])
+
+
+class _DenseFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, softmax, *params):
+        save = _Saved()
+        feat = model._trunk_forward(x, save)
+        head = model._head()
+        out = ops.head_dense_fwd(feat, head.weight.detach(), head.bias.detach(), softmax=softmax)
+        ctx.model, ctx.save_, ctx.feat, ctx.softmax = model, save, feat, softmax
+        if softmax:
+            ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        model, save, feat = ctx.model, ctx.save_, ctx.feat
+        head = model._head()
+        g = g.contiguous().float()
+        if ctx.softmax:  # d softmax: g_logit = p * (g - sum_c g*p)
+            (p,) = ctx.saved_tensors
+            g = p * (g - (g * p).sum(dim=1, keepdim=True))
+        dfeat, dW, db = ops.head_dense_bwd(g, feat, head.weight.detach())
+        needs = list(ctx.needs_input_grad[3:3 + 42])
+        grads = model._trunk_backward(save, dfeat, needs)
+        nh = ctx.needs_input_grad[45:47]
+        if model.grad_ready_hook is not None:
+            model.grad_ready_hook(14, [t for t, n in zip((dW, db), nh) if n])
+        return (None, None, None) + tuple(grads) + (dW if nh[0] else None, db if nh[1] else None)
+
+
+class _FusedLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, labels, *params):
+        save = _Saved()
+        feat = model._trunk_forward(x, save)
+        head = model._head()
+        out = ops.head_ce(feat, labels, head.weight.detach(), head.bias.detach(), compute_grad=False,
+                          eval_softmax=False)
+        ctx.model, ctx.save_, ctx.feat, ctx.labels = model, save, feat, labels
+        ctx.mark_non_differentiable(out["preds"])
+        return out["loss"][0].clone(), out["preds"]
+
+    @staticmethod
+    def backward(ctx, gloss, _gpreds):
+        model, save, feat = ctx.model, ctx.save_, ctx.feat
+        head = model._head()
+        gl = gloss.detach().float().reshape(1).contiguous()
+        needs = list(ctx.needs_input_grad[3:3 + 42])
+        nh = ctx.needs_input_grad[45:47]
+        out = ops.head_ce(feat, ctx.labels, head.weight.detach(), head.bias.detach(), compute_grad=True,
+                          eval_softmax=False, grad_scale=1.0, grad_scale_dev=gl, want_preds=False,
+                          want_dx=any(needs))
+        if model.grad_ready_hook is not None:
+            model.grad_ready_hook(14, [t for t, n in zip((out["dW"], out["db"]), nh) if n])
+        grads = model._trunk_backward(save, out["dx"], needs) if any(needs) else [None] * 42
+        return (None, None, None) + tuple(grads) + (out["dW"] if nh[0] else None, out["db"] if nh[1] else None)

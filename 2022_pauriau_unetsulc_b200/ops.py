@@ -1,0 +1,295 @@
+"""Thin torch-tensor wrappers over the C-ABI (include/unetsulc_b200.h).
+
+PyTorch here is plumbing only: device memory, the current stream, autograd bookkeeping.  Every function below
+enqueues hand-written sm_100a kernels from libunetsulc_b200.so on ``torch.cuda.current_stream()``.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+
+
+def _s():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("unetsulc_b200: tensor on %s — the B200 path has no CPU fallback" % t.device)
+
+
+class Workspace(object):
+    """Grow-only scratch buffer per device (the C-ABI never allocates)."""
+    _bufs = {}
+
+    @classmethod
+    def get(cls, nbytes, device, tag="ws"):
+        key = (str(device), tag)
+        buf = cls._bufs.get(key)
+        nbytes = int(nbytes)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf
+
+
+class ActView(object):
+    """A channel window [coff, coff+C) of an NDHWC bf16 buffer [N, D, H, W, ld]."""
+    __slots__ = ("buf", "N", "D", "H", "W", "C", "ld", "coff")
+
+    def __init__(self, buf, N, D, H, W, C, ld=None, coff=0):
+        self.buf, self.N, self.D, self.H, self.W, self.C = buf, N, D, H, W, C
+        self.ld = C if ld is None else ld
+        self.coff = coff
+
+    @property
+    def V(self):
+        return self.D * self.H * self.W
+
+    @staticmethod
+    def alloc(N, D, H, W, C, device, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return ActView(f((N, D, H, W, C), dtype=BF16, device=device), N, D, H, W, C)
+
+    def window(self, coff, C):
+        return ActView(self.buf, self.N, self.D, self.H, self.W, C, self.ld, self.coff + coff)
+
+    def dense(self):
+        """[N, D, H, W, C] torch view (strided if this is a window)."""
+        return self.buf.view(self.N, self.D, self.H, self.W, self.ld)[..., self.coff:self.coff + self.C]
+
+
+def conv3d_igemm(x, wpack, y, cin, cout, relu, y_fp32=False):
+    """x, y: ActView; wpack bf16 [27, cout, cin]."""
+    lib = _lib.load()
+    _need_cuda(x.buf, wpack, y.buf)
+    _lib.check(lib.b2_conv3d_igemm(_p(x.buf), x.ld, x.coff, _p(wpack), _p(y.buf), y.ld, y.coff, int(y_fp32),
+                                   x.N, x.D, x.H, x.W, cin, cout, int(relu), _s()), "b2_conv3d_igemm")
+
+
+def conv3d_wgrad(x, dy, cin, cout):
+    """returns dW fp32 [cout, cin, 3, 3, 3]"""
+    lib = _lib.load()
+    _need_cuda(x.buf, dy.buf)
+    need = lib.b2_conv3d_wgrad_workspace_bytes(x.N, x.D, x.H, x.W, cin, cout)
+    if need < 0:
+        raise RuntimeError("b2_conv3d_wgrad: unsupported shape Cin=%d Cout=%d" % (cin, cout))
+    ws = Workspace.get(need, x.buf.device, "wgrad")
+    dw = torch.empty((cout, cin, 3, 3, 3), dtype=torch.float32, device=x.buf.device)
+    _lib.check(lib.b2_conv3d_wgrad(_p(x.buf), x.ld, x.coff, _p(dy.buf), dy.ld, dy.coff, _p(dw), _p(ws), ws.numel(),
+                                   x.N, x.D, x.H, x.W, cin, cout, _s()), "b2_conv3d_wgrad")
+    return dw
+
+
+def conv3d_first_fwd(x, w, y, relu=True):
+    """x fp32 [N, 1, D, H, W] contiguous; w fp32 [cout, 1, 3, 3, 3]; y ActView"""
+    lib = _lib.load()
+    _need_cuda(x, w, y.buf)
+    _lib.check(lib.b2_conv3d_first_fwd(_p(x), _p(w), _p(y.buf), y.ld, y.coff, y.N, y.D, y.H, y.W, w.shape[0],
+                                       int(relu), _s()), "b2_conv3d_first_fwd")
+
+
+def conv3d_first_wgrad(x, dy, cout):
+    lib = _lib.load()
+    _need_cuda(x, dy.buf)
+    need = lib.b2_conv3d_first_wgrad_workspace_bytes(cout)
+    ws = Workspace.get(need, x.device, "wgrad")
+    dw = torch.empty((cout, 1, 3, 3, 3), dtype=torch.float32, device=x.device)
+    _lib.check(lib.b2_conv3d_first_wgrad(_p(x), _p(dy.buf), dy.ld, dy.coff, _p(dw), _p(ws), ws.numel(), dy.N, dy.D,
+                                         dy.H, dy.W, cout, _s()), "b2_conv3d_first_wgrad")
+    return dw
+
+
+def relu_gn_stats(r, groups, eps, gamma, beta):
+    """r: dense ActView (post-ReLU conv output).  Returns (mean_rstd [N,C,2], scale_shift [N,C,2]) fp32."""
+    lib = _lib.load()
+    _need_cuda(r.buf, gamma, beta)
+    dev = r.buf.device
+    mean_rstd = torch.empty((r.N, r.C, 2), dtype=torch.float32, device=dev)
+    scale_shift = torch.empty((r.N, r.C, 2), dtype=torch.float32, device=dev)
+    ws = Workspace.get(lib.b2_gn_workspace_bytes(r.N, r.C), dev, "gn")
+    _lib.check(lib.b2_relu_gn_stats(_p(r.buf), r.N, r.V, r.C, groups, float(eps), _p(gamma), _p(beta), _p(mean_rstd),
+                                    _p(scale_shift), _p(ws), ws.numel(), _s()), "b2_relu_gn_stats")
+    return mean_rstd, scale_shift
+
+
+def relu_gn_apply(r, scale_shift, y, pooled=None):
+    lib = _lib.load()
+    _lib.check(lib.b2_relu_gn_apply(_p(r.buf), r.N, r.D, r.H, r.W, r.C, _p(scale_shift), _p(y.buf), y.ld, y.coff,
+                                    _p(pooled.buf) if pooled is not None else C.c_void_p(0), _s()),
+               "b2_relu_gn_apply")
+
+
+def relu_gn_bwd(dy, r, groups, gamma, mean_rstd, want_param_grads=True):
+    """dy: ActView (any window); r dense.  Returns (dr ActView dense, dgamma, dbeta)."""
+    lib = _lib.load()
+    dev = r.buf.device
+    dr = ActView.alloc(r.N, r.D, r.H, r.W, r.C, dev)
+    dgamma = torch.empty(r.C, dtype=torch.float32, device=dev) if want_param_grads else None
+    dbeta = torch.empty(r.C, dtype=torch.float32, device=dev) if want_param_grads else None
+    ws = Workspace.get(lib.b2_relu_gn_bwd_workspace_bytes(r.N, r.C), dev, "gn")
+    _lib.check(lib.b2_relu_gn_bwd(_p(dy.buf), dy.ld, dy.coff, _p(r.buf), r.N, r.V, r.C, groups, _p(gamma),
+                                  _p(mean_rstd), _p(dr.buf), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _s()),
+               "b2_relu_gn_bwd")
+    return dr, dgamma, dbeta
+
+
+def maxpool3d_bwd_add(y, dskip, dpool):
+    """y: forward tensor window (pre-pool); dskip: ActView or None; dpool: dense ActView at half res."""
+    lib = _lib.load()
+    out = ActView.alloc(y.N, y.D, y.H, y.W, y.C, y.buf.device)
+    _lib.check(lib.b2_maxpool3d_bwd_add(_p(y.buf), y.ld, y.coff, _p(dskip.buf) if dskip is not None else C.c_void_p(0),
+                                        dskip.ld if dskip is not None else 8, dskip.coff if dskip is not None else 0,
+                                        _p(dpool.buf), _p(out.buf), y.N, y.D, y.H, y.W, y.C, _s()),
+               "b2_maxpool3d_bwd_add")
+    return out
+
+
+def upcat_fwd(x, cat_window):
+    lib = _lib.load()
+    c = cat_window
+    _lib.check(lib.b2_upcat_fwd(_p(x.buf), x.N, x.D, x.H, x.W, x.C, _p(c.buf), c.ld, c.coff, c.D, c.H, c.W, _s()),
+               "b2_upcat_fwd")
+
+
+def upcat_bwd(dcat_window, Di, Hi, Wi):
+    lib = _lib.load()
+    c = dcat_window
+    dx = ActView.alloc(c.N, Di, Hi, Wi, c.C, c.buf.device)
+    _lib.check(lib.b2_upcat_bwd(_p(c.buf), c.ld, c.coff, c.N, c.D, c.H, c.W, _p(dx.buf), Di, Hi, Wi, c.C, _s()),
+               "b2_upcat_bwd")
+    return dx
+
+
+def head_ce(x, labels, W, b, compute_grad, eval_softmax=False, grad_scale=1.0, grad_scale_dev=None,
+            want_preds=True, want_dx=True):
+    """x: dense ActView [N,D,H,W,Cin]; labels int64 [N,D,H,W] (-1 = ignore).
+    Returns dict(loss [2] fp32 (mean, sum), count int32 [1], preds int32 [N,D,H,W] or None, dx ActView, dW, db)."""
+    lib = _lib.load()
+    _need_cuda(x.buf, labels, W, b)
+    dev = x.buf.device
+    cout, cin = W.shape[0], W.shape[1]
+    if labels.dtype != torch.int64 or not labels.is_contiguous():
+        labels = labels.to(torch.int64).contiguous()
+    NV = x.N * x.V
+    loss = torch.empty(2, dtype=torch.float32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    preds = torch.full((x.N, x.D, x.H, x.W), -1, dtype=torch.int32, device=dev) if want_preds else None
+    dx = ActView.alloc(x.N, x.D, x.H, x.W, cin, dev) if (compute_grad and want_dx) else None
+    dW = torch.empty_like(W, dtype=torch.float32) if compute_grad else None
+    db = torch.empty(cout, dtype=torch.float32, device=dev) if compute_grad else None
+    ws = Workspace.get(lib.b2_head_workspace_bytes(cin), dev, "head")
+    Wc = W.reshape(cout, cin)
+    if not Wc.is_contiguous():
+        Wc = Wc.contiguous()
+    _lib.check(lib.b2_head_ce(_p(x.buf), _p(labels), NV, _p(Wc), _p(b), cin, cout, float(grad_scale),
+                              _p(grad_scale_dev), int(compute_grad), int(eval_softmax), _p(preds),
+                              _p(dx.buf) if dx is not None else C.c_void_p(0), _p(dW), _p(db), _p(loss), _p(count),
+                              _p(ws), ws.numel(), _s()), "b2_head_ce")
+    return dict(loss=loss, count=count, preds=preds, dx=dx, dW=dW, db=db)
+
+
+def head_gather(x, index, W, b, softmax=True):
+    """index: int64 linear voxel indices into [N*D*H*W].  Returns (scores fp32 [n, cout], preds int32 [n])."""
+    lib = _lib.load()
+    dev = x.buf.device
+    cout, cin = W.shape[0], W.shape[1]
+    n = index.numel()
+    scores = torch.empty((n, cout), dtype=torch.float32, device=dev)
+    preds = torch.empty(n, dtype=torch.int32, device=dev)
+    Wc = W.reshape(cout, cin).contiguous()
+    _lib.check(lib.b2_head_gather(_p(x.buf), _p(index), n, _p(Wc), _p(b), cin, cout, int(softmax), _p(scores),
+                                  _p(preds), _s()), "b2_head_gather")
+    return scores, preds
+
+
+def head_dense_fwd(x, W, b, softmax):
+    lib = _lib.load()
+    dev = x.buf.device
+    cout, cin = W.shape[0], W.shape[1]
+    out = torch.empty((x.N, cout, x.D, x.H, x.W), dtype=torch.float32, device=dev)
+    Wc = W.reshape(cout, cin).contiguous()
+    _lib.check(lib.b2_head_dense_fwd(_p(x.buf), x.N, x.V, _p(Wc), _p(b), cin, cout, int(softmax), _p(out), _s()),
+               "b2_head_dense_fwd")
+    return out
+
+
+def head_dense_bwd(g, x, W):
+    """g fp32 [N, cout, D, H, W] contiguous.  Returns (dx ActView, dW, db)."""
+    lib = _lib.load()
+    dev = x.buf.device
+    cout, cin = W.shape[0], W.shape[1]
+    g = g.contiguous().float()
+    dx = ActView.alloc(x.N, x.D, x.H, x.W, cin, dev)
+    dW = torch.empty_like(W, dtype=torch.float32)
+    db = torch.empty(cout, dtype=torch.float32, device=dev)
+    ws = Workspace.get(lib.b2_head_workspace_bytes(cin), dev, "head")
+    Wc = W.reshape(cout, cin).contiguous()
+    _lib.check(lib.b2_head_dense_bwd(_p(g), _p(x.buf), x.N, x.V, _p(Wc), cin, cout, _p(dx.buf), _p(dW), _p(db),
+                                     _p(ws), ws.numel(), _s()), "b2_head_dense_bwd")
+    return dx, dW, db
+
+
+def sgd_step(params, grads, moms, lr, momentum, grad_scale=1.0):
+    lib = _lib.load()
+    n = len(params)
+    if n == 0:
+        return
+    arr = C.c_void_p * n
+    ll = C.c_longlong * n
+    P = arr(*[p.data_ptr() for p in params])
+    G = arr(*[g.data_ptr() for g in grads])
+    M = arr(*[m.data_ptr() for m in moms])
+    Nn = ll(*[p.numel() for p in params])
+    _lib.check(lib.b2_sgd_step(P, G, M, Nn, n, float(lr), float(momentum), float(grad_scale), _s()), "b2_sgd_step")
+
+
+def pack_conv_weights(w, want_dgrad=True):
+    """w fp32 [cout, cin, 3, 3, 3] -> (wf bf16 [27, cout, cin], wd bf16 [27, cin, cout])"""
+    lib = _lib.load()
+    _need_cuda(w)
+    cout, cin = w.shape[0], w.shape[1]
+    wf = torch.empty((27, cout, cin), dtype=BF16, device=w.device)
+    wd = torch.empty((27, cin, cout), dtype=BF16, device=w.device) if want_dgrad else None
+    wc = w.detach()
+    if not wc.is_contiguous():
+        wc = wc.contiguous()
+    _lib.check(lib.b2_pack_conv_weights(_p(wc), _p(wf), _p(wd), cout, cin, _s()), "b2_pack_conv_weights")
+    return wf, wd
+
+
+def fold_vote(scores, fold_dense, n_folds, thresholds):
+    """scores fp32 [n, C] cuda; fold_dense int32 [n] in [0, n_folds); thresholds: list of ints.
+    Returns int32 [T, n]."""
+    lib = _lib.load()
+    _need_cuda(scores, fold_dense)
+    dev = scores.device
+    n, Cc = scores.shape
+    T = len(thresholds)
+    out = torch.empty((T, n), dtype=torch.int32, device=dev)
+    if n == 0:
+        return out
+    th = torch.tensor(list(thresholds), dtype=torch.int32, device=dev)
+    ws = Workspace.get(lib.b2_fold_vote_workspace_bytes(n, Cc, n_folds, T), dev, "vote")
+    _lib.check(lib.b2_fold_vote(_p(scores.contiguous()), _p(fold_dense.contiguous()), n, Cc, n_folds, _p(th), T,
+                                _p(out), _p(ws), ws.numel(), _s()), "b2_fold_vote")
+    return out
+
+
+def esi_counts(y_true, y_pred, n_classes, counts=None):
+    """int32 cuda vectors -> uint64-valued int64 tensor [3, n_classes] (TP, FP, FN), accumulated into `counts`."""
+    lib = _lib.load()
+    _need_cuda(y_true, y_pred)
+    if counts is None:
+        counts = torch.zeros((3, n_classes), dtype=torch.int64, device=y_true.device)
+    _lib.check(lib.b2_esi_counts(_p(y_true.contiguous()), _p(y_pred.contiguous()), y_true.numel(), n_classes,
+                                 _p(counts), _s()), "b2_esi_counts")
+    return counts

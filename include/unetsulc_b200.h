@@ -1,0 +1,103 @@
+/* C-ABI of libunetsulc_b200.so — the B200-native (sm_100a) hot path behind UnetPatternSulciLabelling.
+ *
+ * Everything here replaces arithmetic that the reference reaches through the `deepsulci` import boundary
+ * (reference pattern_class.py:19-23): `UNet3D.forward/backward` (training.py:206-211), `nn.CrossEntropyLoss`
+ * + `torch.max` on its output (training.py:207-208), `optim.SGD.step` (training.py:212), the Softmax scores
+ * gathered by `labeling()` (pattern_class.py:266-277), `cutting(...)` (pattern_class.py:230) and the counters
+ * behind `esi_score(...)` (training.py:223-225).  The Python host side (2022_pauriau_unetsulc_b200/ops.py) binds
+ * these with ctypes; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless stated otherwise
+ *   - activations: NDHWC bf16, addressed as base[(voxel) * ld + coff + c] ("channel window" of a wider buffer)
+ *   - every function returns 0 on success, <0 on error; b2_last_error() returns the thread-local message
+ *   - re-entrant; work is enqueued on the cudaStream_t passed in; no allocation, no host synchronisation
+ *   - the caller owns every buffer, including workspaces (sizes from the *_workspace_bytes queries)
+ *   - no CPU fallback: unsupported shapes are hard errors
+ */
+#ifndef UNETSULC_B200_H_
+#define UNETSULC_B200_H_
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* b2_last_error(void);
+
+/* ---- 3x3x3 stride-1 pad-1 Conv3d (the 14 convs inside deepsulci UNet3D; training.py:206, 211) -------------------
+ * Implicit GEMM on tcgen05/TMEM fed by TMA.  fprop: x = layer input, wpack = fprop pack, relu=1.
+ * dgrad: x = dY, wpack = dgrad pack, Cin/Cout swapped, relu=0.  y_is_fp32 selects a fp32 output buffer.      */
+int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff,
+                    int y_is_fp32, int N, int D, int H, int W, int Cin, int Cout, int relu, cudaStream_t stream);
+
+/* dW[co][ci][3][3][3] (fp32, PyTorch layout) = sum_v dY[v,co] * X[v+off,ci]                                      */
+long long b2_conv3d_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout);
+int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* dy, int ldy, int y_coff, float* dw,
+                    void* workspace, long long workspace_bytes, int N, int D, int H, int W, int Cin, int Cout,
+                    cudaStream_t stream);
+
+/* encoders.0.conv1 (Cin = 1): direct convolution on the fp32 [N,D,H,W] skeleton volume (dataset.py:78-80)        */
+int b2_conv3d_first_fwd(const float* x, const float* w, void* y, int ldy, int y_coff, int N, int D, int H, int W,
+                        int Cout, int relu, cudaStream_t stream);
+long long b2_conv3d_first_wgrad_workspace_bytes(int Cout);
+int b2_conv3d_first_wgrad(const float* x, const void* dy, int lddy, int dy_coff, float* dw, void* workspace,
+                          long long workspace_bytes, int N, int D, int H, int W, int Cout, cudaStream_t stream);
+
+/* ---- ReLU + GroupNorm ('crg' order), r = relu(conv) is produced by the conv epilogue --------------------------- */
+long long b2_gn_workspace_bytes(int N, int C);
+int b2_relu_gn_stats(const void* r, int N, long long V, int C, int G, float eps, const float* gamma,
+                     const float* beta, float* mean_rstd, float* scale_shift, void* workspace,
+                     long long workspace_bytes, cudaStream_t stream);
+/* y = GN(r); pooled != NULL additionally writes MaxPool3d(2,2,0)(y) in the same pass (encoder -> next level)      */
+int b2_relu_gn_apply(const void* r, int N, int D, int H, int W, int C, const float* scale_shift, void* y, int ldy,
+                     int y_coff, void* pooled, cudaStream_t stream);
+long long b2_relu_gn_bwd_workspace_bytes(int N, int C);
+int b2_relu_gn_bwd(const void* dy, int lddy, int dy_coff, const void* r, int N, long long V, int C, int G,
+                   const float* gamma, const float* mean_rstd, void* dr, float* dgamma, float* dbeta,
+                   void* workspace, long long workspace_bytes, cudaStream_t stream);
+
+/* ---- MaxPool3d(2) backward (+ skip gradient add), trilinear upsample + concat and its backward ------------------ */
+int b2_maxpool3d_bwd_add(const void* y, int ldy, int y_coff, const void* dskip, int ldd, int d_coff,
+                         const void* dpool, void* out, int N, int D, int H, int W, int C, cudaStream_t stream);
+int b2_upcat_fwd(const void* x, int N, int Di, int Hi, int Wi, int C, void* cat, int ldc, int coff, int Do, int Ho,
+                 int Wo, cudaStream_t stream);
+int b2_upcat_bwd(const void* dcat, int ldc, int coff, int N, int Do, int Ho, int Wo, void* dx, int Di, int Hi,
+                 int Wi, int C, cudaStream_t stream);
+
+/* ---- final_conv 1x1x1 (pattern_class.py:364) fused with softmax / cross-entropy / argmax ------------------------ */
+long long b2_head_workspace_bytes(int Cin);
+/* loss_out[0] = mean CE over voxels with label >= 0 (NaN if none), loss_out[1] = sum; count_out = #labelled.
+ * compute_grad: also d(loss)/d(x, W, b), scaled by grad_scale * (*grad_scale_dev if non-NULL).
+ * eval_softmax: loss of Softmax outputs fed to CrossEntropyLoss, the reference's val-phase loss (training.py:189). */
+int b2_head_ce(const void* x, const long long* labels, long long NV, const float* W, const float* b, int Cin,
+               int Cout, float grad_scale, const float* grad_scale_dev, int compute_grad, int eval_softmax,
+               int* preds, void* dx, float* dW, float* db, float* loss_out, int* count_out, void* workspace,
+               long long workspace_bytes, cudaStream_t stream);
+int b2_head_gather(const void* x, const long long* index, long long nidx, const float* W, const float* b, int Cin,
+                   int Cout, int softmax, float* scores, int* preds, cudaStream_t stream);
+int b2_head_dense_fwd(const void* x, int N, long long V, const float* W, const float* b, int Cin, int Cout,
+                      int softmax, float* out, cudaStream_t stream);
+int b2_head_dense_bwd(const float* g, const void* x, int N, long long V, const float* W, int Cin, int Cout, void* dx,
+                      float* dW, float* db, void* workspace, long long workspace_bytes, cudaStream_t stream);
+
+/* ---- optimiser (training.py:140, 212) and bf16 weight packs ------------------------------------------------------
+ * params/grads/moms/numels are HOST arrays of `count` entries (device pointers / element counts).                */
+int b2_sgd_step(float* const* params, const float* const* grads, float* const* moms, const long long* numels,
+                int count, float lr, float momentum, float grad_scale, cudaStream_t stream);
+int b2_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t stream);
+
+/* ---- post-inference integer pass: cutting(yscores, vert_notcut, bck2, threshold) (pattern_class.py:230) ---------
+ * fold: dense ids in [0,F); thresholds: device int32 [T]; out: int32 [T][n].                                      */
+long long b2_fold_vote_workspace_bytes(long long n, int C, int F, int T);
+int b2_fold_vote(const float* scores, const int* fold, long long n, int C, int F, const int* thresholds, int T,
+                 int* out, void* workspace, long long workspace_bytes, cudaStream_t stream);
+/* esi_score counters (training.py:223): counts uint64 [3][C] = TP, FP, FN, accumulated                            */
+int b2_esi_counts(const int* y_true, const int* y_pred, long long n, int C, unsigned long long* counts,
+                  cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNETSULC_B200_H_ */

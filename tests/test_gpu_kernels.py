@@ -1,0 +1,373 @@
+"""GPU parity tests, kernel by kernel, through the C-ABI (ctypes) of libunetsulc_b200.so.
+
+Checker = plain PyTorch fp32 ops on the same (bf16-rounded) inputs.  Tolerances:
+  * bf16-output conv kernels ............ rel-L2 <= 2e-3 (one bf16 rounding of an fp32-accumulated result)
+  * fp32-output conv / wgrad kernels .... rel-L2 <= 1e-4 (summation order only)
+  * GroupNorm / resample (bf16 out) ..... rel-L2 <= 4e-3
+  * integer pass (fold vote, counters) .. bit-exact
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import unetsulc_b200  # noqa: F401
+    from unetsulc_b200 import ops
+    return ops
+
+
+def rel_l2(a, b):
+    a = a.double().flatten()
+    b = b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+def to_ndhwc(t):   # [N,C,D,H,W] fp32 -> contiguous [N,D,H,W,C] bf16
+    return t.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16)
+
+
+def from_view(v):  # ActView -> [N,C,D,H,W] fp32
+    return v.dense().float().permute(0, 4, 1, 2, 3).contiguous()
+
+
+CONV_SHAPES = [
+    # N, Cin, Cout, D, H, W
+    (1, 64, 64, 8, 16, 32),
+    (1, 32, 64, 6, 10, 36),      # 64-byte swizzle path (Cin = 32)
+    (1, 192, 64, 8, 8, 32),
+    (1, 128, 256, 6, 7, 6),
+    (1, 256, 512, 3, 4, 5),      # two N tiles
+    (2, 64, 128, 5, 7, 9),       # odd sizes, batch 2
+    (1, 64, 32, 4, 8, 16),       # dgrad shape of encoders.0.conv2
+    (1, 128, 384, 4, 6, 8),      # N tile 192 (dgrad of decoders.1.conv1)
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+@pytest.mark.parametrize("fp32_out", [True, False])
+def test_conv_fprop(shape, fp32_out):
+    ops = _ops()
+    N, Cin, Cout, D, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = bf16_round(torch.randn(N, Cin, D, H, W, device="cuda", generator=g))
+    w = bf16_round(torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=g) * (1.0 / (27 * Cin) ** 0.5))
+    ref = F.conv3d(x, w, padding=1)
+    wf, _ = ops.pack_conv_weights(w)
+    assert torch.equal(wf.float(), w.permute(2, 3, 4, 0, 1).reshape(27, Cout, Cin))
+    xv = ops.ActView(to_ndhwc(x), N, D, H, W, Cin)
+    if fp32_out:
+        ybuf = torch.zeros(N, D, H, W, Cout, device="cuda", dtype=torch.float32)
+        yv = ops.ActView(ybuf, N, D, H, W, Cout)
+        ops.conv3d_igemm(xv, wf, yv, Cin, Cout, relu=False, y_fp32=True)
+        torch.cuda.synchronize()
+        got = ybuf.permute(0, 4, 1, 2, 3)
+        err = rel_l2(got, ref)
+        assert err < 1e-4, "fp32-out conv rel-L2 %.3e" % err
+    else:
+        yv = ops.ActView.alloc(N, D, H, W, Cout, "cuda", zero=True)
+        ops.conv3d_igemm(xv, wf, yv, Cin, Cout, relu=True)
+        torch.cuda.synchronize()
+        err = rel_l2(from_view(yv), F.relu(ref))
+        assert err < 2e-3, "bf16-out conv rel-L2 %.3e" % err
+
+
+def test_conv_fprop_channel_windows():
+    """input read from / output written into channel windows of wider buffers (concat buffers)."""
+    ops = _ops()
+    N, Cin, Cout, D, H, W = 1, 64, 64, 4, 8, 16
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = bf16_round(torch.randn(N, Cin, D, H, W, device="cuda", generator=g))
+    w = bf16_round(torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=g) * 0.03)
+    wide_in = torch.randn(N, D, H, W, 192, device="cuda", generator=g).to(torch.bfloat16)
+    wide_in[..., 128:192] = to_ndhwc(x)
+    wide_out = torch.full((N, D, H, W, 160), 7.0, device="cuda", dtype=torch.bfloat16)
+    wf, _ = ops.pack_conv_weights(w)
+    xv = ops.ActView(wide_in, N, D, H, W, Cin, ld=192, coff=128)
+    yv = ops.ActView(wide_out, N, D, H, W, Cout, ld=160, coff=32)
+    ops.conv3d_igemm(xv, wf, yv, Cin, Cout, relu=True)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv3d(x, w, padding=1))
+    assert rel_l2(from_view(yv), ref) < 2e-3
+    assert bool((wide_out[..., :32] == 7.0).all()) and bool((wide_out[..., 96:] == 7.0).all())
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES[:6])
+def test_conv_dgrad(shape):
+    ops = _ops()
+    N, Cin, Cout, D, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(3)
+    dy = bf16_round(torch.randn(N, Cout, D, H, W, device="cuda", generator=g))
+    w = bf16_round(torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=g) * (1.0 / (27 * Cout) ** 0.5))
+    x = torch.zeros(N, Cin, D, H, W, device="cuda", requires_grad=True)
+    F.conv3d(x, w, padding=1).backward(dy)
+    ref = x.grad
+    _, wd = ops.pack_conv_weights(w)
+    dyv = ops.ActView(to_ndhwc(dy), N, D, H, W, Cout)
+    dxbuf = torch.zeros(N, D, H, W, Cin, device="cuda", dtype=torch.float32)
+    ops.conv3d_igemm(dyv, wd, ops.ActView(dxbuf, N, D, H, W, Cin), Cout, Cin, relu=False, y_fp32=True)
+    torch.cuda.synchronize()
+    err = rel_l2(dxbuf.permute(0, 4, 1, 2, 3), ref)
+    assert err < 1e-4, "dgrad rel-L2 %.3e" % err
+
+
+WGRAD_SHAPES = [
+    (1, 64, 64, 8, 16, 32),
+    (1, 32, 64, 6, 10, 36),      # 64-byte swizzle slots (Cin = 32)
+    (1, 192, 64, 8, 8, 32),
+    (1, 128, 256, 6, 7, 6),
+    (1, 256, 512, 3, 4, 5),
+    (2, 64, 128, 5, 7, 9),
+    (1, 384, 128, 4, 6, 8),
+]
+
+
+@pytest.mark.parametrize("shape", WGRAD_SHAPES)
+def test_conv_wgrad(shape):
+    ops = _ops()
+    N, Cin, Cout, D, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = bf16_round(torch.randn(N, Cin, D, H, W, device="cuda", generator=g))
+    dy = bf16_round(torch.randn(N, Cout, D, H, W, device="cuda", generator=g))
+    w = torch.zeros(Cout, Cin, 3, 3, 3, device="cuda", requires_grad=True)
+    F.conv3d(x, w, padding=1).backward(dy)
+    ref = w.grad
+    got = ops.conv3d_wgrad(ops.ActView(to_ndhwc(x), N, D, H, W, Cin), ops.ActView(to_ndhwc(dy), N, D, H, W, Cout),
+                           Cin, Cout)
+    torch.cuda.synchronize()
+    err = rel_l2(got, ref)
+    assert err < 1e-4, "wgrad rel-L2 %.3e" % err
+
+
+def test_conv_first_layer():
+    ops = _ops()
+    N, Cout, D, H, W = 2, 32, 9, 12, 17
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.rand(N, 1, D, H, W, device="cuda", generator=g) < 0.05).float()
+    w = torch.randn(Cout, 1, 3, 3, 3, device="cuda", generator=g) * 0.2
+    yv = ops.ActView.alloc(N, D, H, W, Cout, "cuda")
+    ops.conv3d_first_fwd(x, w, yv, relu=True)
+    ref = F.relu(F.conv3d(x, w, padding=1))
+    assert rel_l2(from_view(yv), ref) < 2e-3
+    dy = bf16_round(torch.randn(N, Cout, D, H, W, device="cuda", generator=g))
+    wp = w.clone().requires_grad_(True)
+    F.conv3d(x, wp, padding=1).backward(dy)
+    got = ops.conv3d_first_wgrad(x, ops.ActView(to_ndhwc(dy), N, D, H, W, Cout), Cout)
+    torch.cuda.synchronize()
+    assert rel_l2(got, wp.grad) < 1e-5
+
+
+@pytest.mark.parametrize("C,D,H,W,N", [(32, 8, 10, 12, 1), (64, 9, 11, 13, 2), (256, 4, 6, 6, 1), (512, 3, 4, 5, 1)])
+def test_relu_groupnorm_fwd_bwd(C, D, H, W, N):
+    ops = _ops()
+    G = 32
+    g = torch.Generator(device="cuda").manual_seed(6)
+    conv_out = torch.randn(N, C, D, H, W, device="cuda", generator=g)
+    r = bf16_round(F.relu(conv_out))                     # what the conv epilogue stores
+    gamma = torch.randn(C, device="cuda", generator=g) * 0.5 + 1.0
+    beta = torch.randn(C, device="cuda", generator=g) * 0.1
+    rv = ops.ActView(to_ndhwc(r), N, D, H, W, C)
+    mr, ss = ops.relu_gn_stats(rv, G, 1e-5, gamma, beta)
+    # plain apply into a channel window
+    wide = torch.zeros(N, D, H, W, C + 16, device="cuda", dtype=torch.bfloat16)
+    yv = ops.ActView(wide, N, D, H, W, C, ld=C + 16, coff=8)
+    ops.relu_gn_apply(rv, ss, yv)
+    rq = r.clone().requires_grad_(True)
+    gq, bq = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.group_norm(rq, G, gq, bq, 1e-5)
+    torch.cuda.synchronize()
+    assert rel_l2(from_view(yv), ref) < 4e-3
+    # apply + pool
+    y2 = ops.ActView.alloc(N, D, H, W, C, "cuda")
+    pooled = ops.ActView.alloc(N, D // 2, H // 2, W // 2, C, "cuda")
+    ops.relu_gn_apply(rv, ss, y2, pooled)
+    torch.cuda.synchronize()
+    assert torch.equal(y2.dense(), yv.dense())
+    assert torch.equal(from_view(pooled), F.max_pool3d(from_view(y2), 2))
+    # backward
+    dy = bf16_round(torch.randn(N, C, D, H, W, device="cuda", generator=g))
+    ref.backward(dy)
+    dr, dg, db = ops.relu_gn_bwd(ops.ActView(to_ndhwc(dy), N, D, H, W, C), rv, G, gamma, mr)
+    torch.cuda.synchronize()
+    ref_dr = rq.grad * (r > 0).float()
+    assert rel_l2(from_view(dr), ref_dr) < 4e-3
+    assert rel_l2(dg, gq.grad) < 1e-3
+    assert rel_l2(db, bq.grad) < 1e-3
+
+
+@pytest.mark.parametrize("D,H,W", [(8, 10, 12), (7, 9, 11)])
+def test_maxpool_bwd_add(D, H, W):
+    ops = _ops()
+    N, C = 1, 64
+    g = torch.Generator(device="cuda").manual_seed(7)
+    y = bf16_round(torch.randn(N, C, D, H, W, device="cuda", generator=g)).requires_grad_(True)
+    dskip = bf16_round(torch.randn(N, C, D, H, W, device="cuda", generator=g))
+    dpool = bf16_round(torch.randn(N, C, D // 2, H // 2, W // 2, device="cuda", generator=g))
+    F.max_pool3d(y, 2).backward(dpool)
+    ref = y.grad + dskip
+    wide = torch.zeros(N, D, H, W, 192, device="cuda", dtype=torch.bfloat16)
+    wide[..., :C] = to_ndhwc(y.detach())
+    dwide = torch.zeros(N, D, H, W, 192, device="cuda", dtype=torch.bfloat16)
+    dwide[..., :C] = to_ndhwc(dskip)
+    out = ops.maxpool3d_bwd_add(ops.ActView(wide, N, D, H, W, C, ld=192), ops.ActView(dwide, N, D, H, W, C, ld=192),
+                                ops.ActView(to_ndhwc(dpool), N, D // 2, H // 2, W // 2, C))
+    torch.cuda.synchronize()
+    assert rel_l2(from_view(out), ref) < 4e-3
+
+
+@pytest.mark.parametrize("din,dout", [((4, 5, 6), (8, 10, 12)), ((3, 4, 5), (7, 9, 11)), ((6, 7, 6), (12, 14, 12))])
+def test_upsample_concat_fwd_bwd(din, dout):
+    ops = _ops()
+    N, C, Cs = 1, 128, 64
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = bf16_round(torch.randn(N, C, *din, device="cuda", generator=g)).requires_grad_(True)
+    ref = F.interpolate(x, size=dout, mode="trilinear", align_corners=False)
+    cat = torch.zeros(N, *dout, Cs + C, device="cuda", dtype=torch.bfloat16)
+    ops.upcat_fwd(ops.ActView(to_ndhwc(x.detach()), N, *din, C), ops.ActView(cat, N, *dout, C, ld=Cs + C, coff=Cs))
+    torch.cuda.synchronize()
+    got = cat[..., Cs:].float().permute(0, 4, 1, 2, 3)
+    assert rel_l2(got, ref) < 4e-3
+    assert bool((cat[..., :Cs] == 0).all())
+    dcat = bf16_round(torch.randn(N, Cs + C, *dout, device="cuda", generator=g))
+    ref.backward(dcat[:, Cs:])
+    dx = ops.upcat_bwd(ops.ActView(to_ndhwc(dcat), N, *dout, C, ld=Cs + C, coff=Cs), *din)
+    torch.cuda.synchronize()
+    assert rel_l2(from_view(dx), x.grad) < 4e-3
+
+
+def _head_inputs(seed, N=1, D=6, H=7, W=8, Cin=64, Cout=56, frac=0.2):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = bf16_round(torch.randn(N, Cin, D, H, W, device="cuda", generator=g))
+    Wt = torch.randn(Cout, Cin, 1, 1, 1, device="cuda", generator=g) * 0.2
+    b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    labels = torch.randint(0, Cout, (N, D, H, W), device="cuda", generator=g)
+    mask = torch.rand(N, D, H, W, device="cuda", generator=g) < frac
+    labels = torch.where(mask, labels, torch.full_like(labels, -1))
+    return x, Wt, b, labels
+
+
+@pytest.mark.parametrize("Cout", [56, 64, 3])
+def test_head_ce_fused(Cout):
+    ops = _ops()
+    x, Wt, b, labels = _head_inputs(9, Cout=Cout)
+    N, Cin, D, H, W = x.shape
+    xq = x.clone().requires_grad_(True)
+    Wq, bq = Wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    logits = F.conv3d(xq, Wq, bq)
+    loss = F.cross_entropy(logits, labels, ignore_index=-1)
+    loss.backward()
+    xv = ops.ActView(to_ndhwc(x), N, D, H, W, Cin)
+    out = ops.head_ce(xv, labels, Wt, b, compute_grad=True)
+    torch.cuda.synchronize()
+    assert abs(float(out["loss"][0]) - float(loss)) < 1e-4 * max(1.0, abs(float(loss)))
+    assert int(out["count"]) == int((labels >= 0).sum())
+    m = labels >= 0
+    assert torch.equal(out["preds"][m].long(), logits.argmax(1)[m])
+    assert bool((out["preds"][~m] == -1).all())
+    assert rel_l2(out["dW"], Wq.grad) < 1e-4
+    assert rel_l2(out["db"], bq.grad) < 1e-4
+    assert rel_l2(from_view(out["dx"]), xq.grad) < 4e-3
+    # reference val-phase loss: CrossEntropyLoss applied to Softmax outputs (training.py:189,205-208)
+    out2 = ops.head_ce(xv, labels, Wt, b, compute_grad=False, eval_softmax=True)
+    ref2 = F.cross_entropy(torch.softmax(logits.detach(), 1), labels, ignore_index=-1)
+    assert abs(float(out2["loss"][0]) - float(ref2)) < 1e-4 * max(1.0, abs(float(ref2)))
+
+
+def test_head_ce_no_labelled_voxel_is_nan():
+    ops = _ops()
+    x, Wt, b, labels = _head_inputs(10)
+    labels = torch.full_like(labels, -1)
+    N, Cin, D, H, W = x.shape
+    out = ops.head_ce(ops.ActView(to_ndhwc(x), N, D, H, W, Cin), labels, Wt, b, compute_grad=True)
+    assert bool(torch.isnan(out["loss"][0]))          # same as PyTorch's mean over an empty set
+    assert int(out["count"]) == 0
+    assert float(out["dW"].abs().sum()) == 0.0
+
+
+def test_head_gather_and_dense():
+    ops = _ops()
+    x, Wt, b, labels = _head_inputs(11, N=2)
+    N, Cin, D, H, W = x.shape
+    xv = ops.ActView(to_ndhwc(x), N, D, H, W, Cin)
+    logits = F.conv3d(x, Wt, b)
+    probs = torch.softmax(logits, 1)
+    dense_l = ops.head_dense_fwd(xv, Wt, b, softmax=False)
+    dense_p = ops.head_dense_fwd(xv, Wt, b, softmax=True)
+    torch.cuda.synchronize()
+    assert dense_l.shape == logits.shape
+    assert rel_l2(dense_l, logits) < 1e-5
+    assert rel_l2(dense_p, probs) < 1e-5
+    idx = torch.nonzero(labels.flatten() >= 0).flatten()
+    sc, pr = ops.head_gather(xv, idx, Wt, b, softmax=True)
+    torch.cuda.synchronize()
+    pflat = probs.permute(0, 2, 3, 4, 1).reshape(-1, probs.shape[1])
+    assert rel_l2(sc, pflat[idx]) < 1e-5
+    assert torch.equal(pr.long(), logits.permute(0, 2, 3, 4, 1).reshape(-1, logits.shape[1])[idx].argmax(1))
+    # dense backward (grad of an arbitrary loss on the dense logits, mostly-zero rows)
+    gq = torch.zeros_like(logits)
+    m = (labels >= 0).unsqueeze(1).expand_as(gq)
+    gq[m] = torch.randn(int(m.sum()), device="cuda")
+    xq = x.clone().requires_grad_(True)
+    Wq, bq = Wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    F.conv3d(xq, Wq, bq).backward(gq)
+    dx, dW, db = ops.head_dense_bwd(gq, xv, Wt)
+    torch.cuda.synchronize()
+    assert rel_l2(dW, Wq.grad) < 1e-4
+    assert rel_l2(db, bq.grad) < 1e-4
+    assert rel_l2(from_view(dx), xq.grad) < 4e-3
+
+
+def test_sgd_matches_torch():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(12)
+    shapes = [(64, 32, 3, 3, 3), (64,), (56, 64, 1, 1, 1), (5000,)]
+    ps = [torch.randn(s, device="cuda", generator=g) for s in shapes]
+    ref_ps = [p.clone().requires_grad_(True) for p in ps]
+    opt = torch.optim.SGD(ref_ps, lr=1e-2, momentum=0.9, weight_decay=0)
+    moms = [torch.zeros_like(p) for p in ps]
+    for step in range(3):
+        grads = [torch.randn(s, device="cuda", generator=g) for s in shapes]
+        for rp, gr in zip(ref_ps, grads):
+            rp.grad = gr.clone()
+        opt.step()
+        ops.sgd_step(ps, grads, moms, 1e-2, 0.9)
+    torch.cuda.synchronize()
+    for p, rp in zip(ps, ref_ps):
+        assert torch.allclose(p, rp.detach(), rtol=1e-6, atol=1e-7)
+
+
+def test_fold_vote_bit_exact_vs_oracle():
+    ops = _ops()
+    from oracle.cutting_ref import cutting_ref
+    from oracle.synth import synth_scores
+    rng = np.random.RandomState(0)
+    n, C = 20000, 56
+    scores = synth_scores(n, C, seed=7)
+    fold_raw = rng.randint(0, 64, size=n) * 17 + 3          # arbitrary (non-dense) vertex ids
+    uniq, inv = np.unique(fold_raw, return_inverse=True)
+    ths = [50, 100, 150]
+    got = ops.fold_vote(scores.cuda(), torch.from_numpy(inv.astype(np.int32)).cuda(), len(uniq), ths).cpu().numpy()
+    for t, th in enumerate(ths):
+        ref = np.asarray(cutting_ref(scores.numpy(), fold_raw, np.zeros((n, 3), int), th))
+        assert np.array_equal(got[t], ref), "threshold %d mismatch" % th
+    # empty input
+    e = ops.fold_vote(torch.zeros(0, C, device="cuda"), torch.zeros(0, dtype=torch.int32, device="cuda"), 1, ths)
+    assert e.shape == (3, 0)
+
+
+def test_esi_counts_exact():
+    ops = _ops()
+    from oracle.stats_ref import esi_counts_ref
+    rng = np.random.RandomState(1)
+    yt = rng.randint(0, 56, size=50000).astype(np.int32)
+    yp = np.where(rng.rand(50000) < 0.7, yt, rng.randint(0, 56, size=50000)).astype(np.int32)
+    c = ops.esi_counts(torch.from_numpy(yt).cuda(), torch.from_numpy(yp).cuda(), 56).cpu().numpy()
+    tp, fp, fn = esi_counts_ref(yt, yp, list(range(56)))
+    assert np.array_equal(c[0], tp) and np.array_equal(c[1], fp) and np.array_equal(c[2], fn)
