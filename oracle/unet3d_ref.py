@@ -80,9 +80,33 @@ class _Decoder(nn.Module):
         return self.double_conv(x)
 
 
+def _rb(t):
+    """bf16 storage emulation with a straight-through gradient."""
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+
+def _double_conv_emulated(seq, x, first_layer_fp32):
+    """Same arithmetic as the nn.Sequential, with the B200 path's bf16 storage points made explicit:
+    3x3x3 weights (except the Cin=1 first conv), relu(conv) and the GroupNorm output are rounded to bf16."""
+    for pos in (1, 2):
+        conv = getattr(seq, "conv%d" % pos)
+        norm = getattr(seq, "norm%d" % pos)
+        w = conv.weight if (first_layer_fp32 and pos == 1) else _rb(conv.weight)
+        x = F.conv3d(x, w, conv.bias, padding=1)
+        x = _rb(F.relu(x))
+        x = _rb(F.group_norm(x, norm.num_groups, norm.weight, norm.bias, norm.eps))
+    return x
+
+
 class UNet3DRef(nn.Module):
     """Oracle network.  state_dict keys (44 tensors for 'crg'):
-    {encoders.{0-3},decoders.{0-2}}.double_conv.{conv,norm}{1,2}.*, final_conv.*"""
+    {encoders.{0-3},decoders.{0-2}}.double_conv.{conv,norm}{1,2}.*, final_conv.*
+
+    ``emulate_bf16_storage = True`` keeps the fp32 arithmetic but rounds tensors to bf16 at exactly the points
+    where the B200 path stores them (weights, relu(conv), GroupNorm output, upsample output).  Parity against
+    this variant isolates kernel bugs from the precision budget of bf16 storage: ReLU masks then agree, so
+    gradients can be compared tightly."""
+    emulate_bf16_storage = False
 
     def __init__(self, in_channels, out_channels, final_sigmoid=False, interpolate=True,
                  dropout=0.0, conv_layer_order="crg", init_channel_number=64):
@@ -106,13 +130,29 @@ class UNet3DRef(nn.Module):
         self.final_conv = nn.Conv3d(f, out_channels, 1)
         self.final_activation = nn.Sigmoid() if final_sigmoid else nn.Softmax(dim=1)
 
-    def forward(self, x):
+    def _forward_emulated(self, x):
         feats = []
-        for enc in self.encoders:
-            x = enc(x)
+        for i, enc in enumerate(self.encoders):
+            if enc.max_pool is not None:
+                x = enc.max_pool(x)
+            x = _double_conv_emulated(enc.double_conv, x, first_layer_fp32=(i == 0))
             feats.insert(0, x)
         for dec, skip in zip(self.decoders, feats[1:]):
-            x = dec(skip, x)
+            x = _rb(F.interpolate(x, size=skip.shape[2:], mode=UPSAMPLE_MODE,
+                                  align_corners=UPSAMPLE_ALIGN_CORNERS))
+            x = _double_conv_emulated(dec.double_conv, torch.cat((skip, x), dim=1), False)
+        return x
+
+    def forward(self, x):
+        if self.emulate_bf16_storage:
+            x = self._forward_emulated(x)
+        else:
+            feats = []
+            for enc in self.encoders:
+                x = enc(x)
+                feats.insert(0, x)
+            for dec, skip in zip(self.decoders, feats[1:]):
+                x = dec(skip, x)
         x = self.final_conv(x)                    # read lazily: callers replace it
         if SOFTMAX_ONLY_IN_EVAL and not self.training:
             x = self.final_activation(x)

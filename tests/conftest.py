@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200, sm_100a)")
+    try:  # the fp32 PyTorch checker must be true fp32 (no TF32) or it is less accurate than the kernels under test
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:
+        pass
 
 
 def pytest_collection_modifyitems(config, items):

@@ -146,6 +146,41 @@ def test_conv_wgrad(shape):
     assert err < 1e-4, "wgrad rel-L2 %.3e" % err
 
 
+@pytest.mark.parametrize("cin,cout,dims", [(64, 128, (48, 56, 48)), (192, 64, (40, 56, 96)), (768, 256, (24, 28, 24))])
+def test_conv_full_size_layers_deterministic_and_exact(cin, cout, dims):
+    """BASELINE-sized layers: many tiles per persistent CTA (exercises the smem ring and the TMEM double buffer);
+    results must be bit-identical run to run and match the fp32 checker."""
+    ops = _ops()
+    D, H, W = dims
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = bf16_round(torch.randn(1, cin, D, H, W, device="cuda", generator=g))
+    dy = bf16_round(torch.randn(1, cout, D, H, W, device="cuda", generator=g))
+    w = bf16_round(torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) * (1.0 / (27 * cin) ** 0.5))
+    wf, wd = ops.pack_conv_weights(w)
+    xv = ops.ActView(to_ndhwc(x), 1, D, H, W, cin)
+    dyv = ops.ActView(to_ndhwc(dy), 1, D, H, W, cout)
+    outs = []
+    for _ in range(2):
+        y = ops.ActView.alloc(1, D, H, W, cout, "cuda", zero=True)
+        ops.conv3d_igemm(xv, wf, y, cin, cout, relu=True)
+        dx = ops.ActView.alloc(1, D, H, W, cin, "cuda", zero=True)
+        ops.conv3d_igemm(dyv, wd, dx, cout, cin, relu=False)
+        dw = ops.conv3d_wgrad(xv, dyv, cin, cout)
+        torch.cuda.synchronize()
+        outs.append((y.buf.clone(), dx.buf.clone(), dw.clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    xq = x.clone().requires_grad_(True)
+    wq = w.clone().requires_grad_(True)
+    ref = F.conv3d(xq, wq, padding=1)
+    ref.backward(dy)
+    assert rel_l2(outs[0][0].float().permute(0, 4, 1, 2, 3), F.relu(ref)) < 2e-3
+    assert rel_l2(outs[0][1].float().permute(0, 4, 1, 2, 3), xq.grad) < 2e-3
+    e = rel_l2(outs[0][2], wq.grad)
+    print("full-size wgrad rel-L2 %.3e" % e)
+    assert e < 2e-4
+
+
 def test_conv_first_layer():
     ops = _ops()
     N, Cout, D, H, W = 2, 32, 9, 12, 17
