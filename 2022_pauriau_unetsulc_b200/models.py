@@ -230,9 +230,10 @@ class UNet3D(nn.Module):
         return cur
 
     # ------------------------------------------------------------------------------------------ trunk backward
-    def _trunk_backward(self, save, dfeat, needs):
+    def _trunk_backward(self, save, dfeat, needs, outs=None):
         """dfeat: ActView gradient w.r.t. the trunk output.  needs: list of 42 bools (w, gamma, beta per layer).
-        Returns list of 42 grads (None where not needed)."""
+        outs: optional list of 42 pre-allocated fp32 tensors the gradients are written into (views of the
+        data-parallel buckets).  Returns list of 42 grads (None where not needed)."""
         L = self._layers()
         G = self.num_groups
         rec, cats, dims = save.rec, save.cats, save.dims
@@ -246,21 +247,24 @@ class UNet3D(nn.Module):
         if first_needed is None:
             return grads
         hook = self.grad_ready_hook
+        if outs is None:
+            outs = [None] * 42
 
         def layer_bwd(i, dy):
             """dy: gradient w.r.t. the GN output of layer i.  Returns gradient w.r.t. the layer input (or None)."""
             layer, rc = L[i], rec[i]
             want_gb = needs[3 * i + 1] or needs[3 * i + 2]
-            dr, dg, db = ops.relu_gn_bwd(dy, rc["r"], G, layer.norm.weight.detach(), rc["mr"], want_gb)
+            dr, dg, db = ops.relu_gn_bwd(dy, rc["r"], G, layer.norm.weight.detach(), rc["mr"], want_gb,
+                                         outs[3 * i + 1] if want_gb else None, outs[3 * i + 2] if want_gb else None)
             if needs[3 * i + 1]:
                 grads[3 * i + 1] = dg
             if needs[3 * i + 2]:
                 grads[3 * i + 2] = db
             if needs[3 * i]:
                 if layer.cin == 1:
-                    grads[3 * i] = ops.conv3d_first_wgrad(rc["x"], dr, layer.cout)
+                    grads[3 * i] = ops.conv3d_first_wgrad(rc["x"], dr, layer.cout, outs[3 * i])
                 else:
-                    grads[3 * i] = ops.conv3d_wgrad(rc["x"], dr, layer.cin, layer.cout)
+                    grads[3 * i] = ops.conv3d_wgrad(rc["x"], dr, layer.cin, layer.cout, outs[3 * i])
             if hook is not None:
                 hook(i, [g for g in grads[3 * i:3 * i + 3] if g is not None])
             if i <= first_needed or layer.cin == 1:
@@ -326,6 +330,35 @@ class UNet3D(nn.Module):
         out = ops.head_ce(feat, labels, head.weight.detach(), head.bias.detach(), compute_grad=False,
                           eval_softmax=not self.training)
         return out["loss"][0], out["preds"]
+
+    def forward_backward(self, x, labels, outs=None, loss_scale=1.0):
+        """One fused training step without autograd: forward, CrossEntropyLoss(ignore_index=-1), backward.
+        Gradients are returned (and written into `outs`, 44 tensors in ``parameters()`` order, when given) for the
+        parameters with ``requires_grad``; nothing is accumulated into ``.grad``.
+        Returns (loss_and_count: fp32 [2] = (mean, sum) device tensor, count int32 [1], preds int32 [B,D,H,W],
+        grads: list of 44 tensors or None)."""
+        x = self._check_input(x)
+        head = self._head()
+        params = list(self.trunk_parameters()) + [head.weight, head.bias]
+        needs = [bool(p.requires_grad) for p in params]
+        if outs is None:
+            outs = [None] * 44
+        save = _Saved()
+        with torch.no_grad():
+            feat = self._trunk_forward(x, save)
+            out = ops.head_ce(feat, labels, head.weight.detach(), head.bias.detach(), compute_grad=True,
+                              eval_softmax=False, grad_scale=float(loss_scale), want_preds=True,
+                              want_dx=any(needs[:42]), dW_out=outs[42], db_out=outs[43])
+            if self.grad_ready_hook is not None:
+                self.grad_ready_hook(14, [t for t, n in zip((out["dW"], out["db"]), needs[42:]) if n])
+            grads = self._trunk_backward(save, out["dx"], needs[:42], outs[:42]) if any(needs[:42]) else [None] * 42
+        grads = list(grads) + [out["dW"] if needs[42] else None, out["db"] if needs[43] else None]
+        return out["loss"], out["count"], out["preds"], grads
+
+    def ordered_parameters(self):
+        """The 44 parameters in the order forward_backward() reports gradients."""
+        head = self._head()
+        return list(self.trunk_parameters()) + [head.weight, head.bias]
 
     def scores_at(self, x, index):
         """Eval forward + Softmax scores gathered at linear voxel indices (labeling(), pattern_class.py:266-277).

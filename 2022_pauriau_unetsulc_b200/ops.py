@@ -11,6 +11,35 @@ from . import _lib
 
 BF16 = torch.bfloat16
 
+# Number of kernels of libunetsulc_b200.so enqueued so far (bench.py reports the delta over its timed region).
+LAUNCHES = [0]
+# Optional per-op CUDA-event profile: name -> list of (start_event, end_event, work) ; enabled by bench.py only.
+PROFILE = None
+
+
+def _count(n):
+    LAUNCHES[0] += n
+
+
+class _Prof(object):
+    """with _Prof("igemm", flops): ...  records CUDA events on the launching stream when PROFILE is a dict."""
+
+    def __init__(self, name, work=0.0):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.b.record()
+            PROFILE.setdefault(self.name, []).append((self.a, self.b, self.work))
+        return False
+
 
 def _s():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -71,21 +100,25 @@ def conv3d_igemm(x, wpack, y, cin, cout, relu, y_fp32=False):
     """x, y: ActView; wpack bf16 [27, cout, cin]."""
     lib = _lib.load()
     _need_cuda(x.buf, wpack, y.buf)
-    _lib.check(lib.b2_conv3d_igemm(_p(x.buf), x.ld, x.coff, _p(wpack), _p(y.buf), y.ld, y.coff, int(y_fp32),
-                                   x.N, x.D, x.H, x.W, cin, cout, int(relu), _s()), "b2_conv3d_igemm")
+    with _Prof("conv3d_igemm", 2.0 * x.N * x.V * 27 * cin * cout):
+        _lib.check(lib.b2_conv3d_igemm(_p(x.buf), x.ld, x.coff, _p(wpack), _p(y.buf), y.ld, y.coff, int(y_fp32),
+                                       x.N, x.D, x.H, x.W, cin, cout, int(relu), _s()), "b2_conv3d_igemm")
+    _count(1)
 
 
-def conv3d_wgrad(x, dy, cin, cout):
-    """returns dW fp32 [cout, cin, 3, 3, 3]"""
+def conv3d_wgrad(x, dy, cin, cout, out=None):
+    """returns dW fp32 [cout, cin, 3, 3, 3] (written into `out` when given)"""
     lib = _lib.load()
     _need_cuda(x.buf, dy.buf)
     need = lib.b2_conv3d_wgrad_workspace_bytes(x.N, x.D, x.H, x.W, cin, cout)
     if need < 0:
         raise RuntimeError("b2_conv3d_wgrad: unsupported shape Cin=%d Cout=%d" % (cin, cout))
     ws = Workspace.get(need, x.buf.device, "wgrad")
-    dw = torch.empty((cout, cin, 3, 3, 3), dtype=torch.float32, device=x.buf.device)
-    _lib.check(lib.b2_conv3d_wgrad(_p(x.buf), x.ld, x.coff, _p(dy.buf), dy.ld, dy.coff, _p(dw), _p(ws), ws.numel(),
-                                   x.N, x.D, x.H, x.W, cin, cout, _s()), "b2_conv3d_wgrad")
+    dw = out if out is not None else torch.empty((cout, cin, 3, 3, 3), dtype=torch.float32, device=x.buf.device)
+    with _Prof("conv3d_wgrad", 2.0 * x.N * x.V * 27 * cin * cout):
+        _lib.check(lib.b2_conv3d_wgrad(_p(x.buf), x.ld, x.coff, _p(dy.buf), dy.ld, dy.coff, _p(dw), _p(ws),
+                                       ws.numel(), x.N, x.D, x.H, x.W, cin, cout, _s()), "b2_conv3d_wgrad")
+    _count(2)
     return dw
 
 
@@ -95,16 +128,18 @@ def conv3d_first_fwd(x, w, y, relu=True):
     _need_cuda(x, w, y.buf)
     _lib.check(lib.b2_conv3d_first_fwd(_p(x), _p(w), _p(y.buf), y.ld, y.coff, y.N, y.D, y.H, y.W, w.shape[0],
                                        int(relu), _s()), "b2_conv3d_first_fwd")
+    _count(1)
 
 
-def conv3d_first_wgrad(x, dy, cout):
+def conv3d_first_wgrad(x, dy, cout, out=None):
     lib = _lib.load()
     _need_cuda(x, dy.buf)
     need = lib.b2_conv3d_first_wgrad_workspace_bytes(cout)
     ws = Workspace.get(need, x.device, "wgrad")
-    dw = torch.empty((cout, 1, 3, 3, 3), dtype=torch.float32, device=x.device)
+    dw = out if out is not None else torch.empty((cout, 1, 3, 3, 3), dtype=torch.float32, device=x.device)
     _lib.check(lib.b2_conv3d_first_wgrad(_p(x), _p(dy.buf), dy.ld, dy.coff, _p(dw), _p(ws), ws.numel(), dy.N, dy.D,
                                          dy.H, dy.W, cout, _s()), "b2_conv3d_first_wgrad")
+    _count(2)
     return dw
 
 
@@ -118,6 +153,7 @@ def relu_gn_stats(r, groups, eps, gamma, beta):
     ws = Workspace.get(lib.b2_gn_workspace_bytes(r.N, r.C), dev, "gn")
     _lib.check(lib.b2_relu_gn_stats(_p(r.buf), r.N, r.V, r.C, groups, float(eps), _p(gamma), _p(beta), _p(mean_rstd),
                                     _p(scale_shift), _p(ws), ws.numel(), _s()), "b2_relu_gn_stats")
+    _count(2)
     return mean_rstd, scale_shift
 
 
@@ -126,19 +162,23 @@ def relu_gn_apply(r, scale_shift, y, pooled=None):
     _lib.check(lib.b2_relu_gn_apply(_p(r.buf), r.N, r.D, r.H, r.W, r.C, _p(scale_shift), _p(y.buf), y.ld, y.coff,
                                     _p(pooled.buf) if pooled is not None else C.c_void_p(0), _s()),
                "b2_relu_gn_apply")
+    _count(1)
 
 
-def relu_gn_bwd(dy, r, groups, gamma, mean_rstd, want_param_grads=True):
+def relu_gn_bwd(dy, r, groups, gamma, mean_rstd, want_param_grads=True, dgamma_out=None, dbeta_out=None):
     """dy: ActView (any window); r dense.  Returns (dr ActView dense, dgamma, dbeta)."""
     lib = _lib.load()
     dev = r.buf.device
     dr = ActView.alloc(r.N, r.D, r.H, r.W, r.C, dev)
-    dgamma = torch.empty(r.C, dtype=torch.float32, device=dev) if want_param_grads else None
-    dbeta = torch.empty(r.C, dtype=torch.float32, device=dev) if want_param_grads else None
+    dgamma = dgamma_out if dgamma_out is not None else (
+        torch.empty(r.C, dtype=torch.float32, device=dev) if want_param_grads else None)
+    dbeta = dbeta_out if dbeta_out is not None else (
+        torch.empty(r.C, dtype=torch.float32, device=dev) if want_param_grads else None)
     ws = Workspace.get(lib.b2_relu_gn_bwd_workspace_bytes(r.N, r.C), dev, "gn")
     _lib.check(lib.b2_relu_gn_bwd(_p(dy.buf), dy.ld, dy.coff, _p(r.buf), r.N, r.V, r.C, groups, _p(gamma),
                                   _p(mean_rstd), _p(dr.buf), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _s()),
                "b2_relu_gn_bwd")
+    _count(3)
     return dr, dgamma, dbeta
 
 
@@ -150,6 +190,7 @@ def maxpool3d_bwd_add(y, dskip, dpool):
                                         dskip.ld if dskip is not None else 8, dskip.coff if dskip is not None else 0,
                                         _p(dpool.buf), _p(out.buf), y.N, y.D, y.H, y.W, y.C, _s()),
                "b2_maxpool3d_bwd_add")
+    _count(1)
     return out
 
 
@@ -158,6 +199,7 @@ def upcat_fwd(x, cat_window):
     c = cat_window
     _lib.check(lib.b2_upcat_fwd(_p(x.buf), x.N, x.D, x.H, x.W, x.C, _p(c.buf), c.ld, c.coff, c.D, c.H, c.W, _s()),
                "b2_upcat_fwd")
+    _count(1)
 
 
 def upcat_bwd(dcat_window, Di, Hi, Wi):
@@ -166,11 +208,12 @@ def upcat_bwd(dcat_window, Di, Hi, Wi):
     dx = ActView.alloc(c.N, Di, Hi, Wi, c.C, c.buf.device)
     _lib.check(lib.b2_upcat_bwd(_p(c.buf), c.ld, c.coff, c.N, c.D, c.H, c.W, _p(dx.buf), Di, Hi, Wi, c.C, _s()),
                "b2_upcat_bwd")
+    _count(1)
     return dx
 
 
 def head_ce(x, labels, W, b, compute_grad, eval_softmax=False, grad_scale=1.0, grad_scale_dev=None,
-            want_preds=True, want_dx=True):
+            want_preds=True, want_dx=True, dW_out=None, db_out=None):
     """x: dense ActView [N,D,H,W,Cin]; labels int64 [N,D,H,W] (-1 = ignore).
     Returns dict(loss [2] fp32 (mean, sum), count int32 [1], preds int32 [N,D,H,W] or None, dx ActView, dW, db)."""
     lib = _lib.load()
@@ -184,8 +227,8 @@ def head_ce(x, labels, W, b, compute_grad, eval_softmax=False, grad_scale=1.0, g
     count = torch.empty(1, dtype=torch.int32, device=dev)
     preds = torch.full((x.N, x.D, x.H, x.W), -1, dtype=torch.int32, device=dev) if want_preds else None
     dx = ActView.alloc(x.N, x.D, x.H, x.W, cin, dev) if (compute_grad and want_dx) else None
-    dW = torch.empty_like(W, dtype=torch.float32) if compute_grad else None
-    db = torch.empty(cout, dtype=torch.float32, device=dev) if compute_grad else None
+    dW = (dW_out if dW_out is not None else torch.empty_like(W, dtype=torch.float32)) if compute_grad else None
+    db = (db_out if db_out is not None else torch.empty(cout, dtype=torch.float32, device=dev)) if compute_grad else None
     ws = Workspace.get(lib.b2_head_workspace_bytes(cin), dev, "head")
     Wc = W.reshape(cout, cin)
     if not Wc.is_contiguous():
@@ -194,6 +237,7 @@ def head_ce(x, labels, W, b, compute_grad, eval_softmax=False, grad_scale=1.0, g
                               _p(grad_scale_dev), int(compute_grad), int(eval_softmax), _p(preds),
                               _p(dx.buf) if dx is not None else C.c_void_p(0), _p(dW), _p(db), _p(loss), _p(count),
                               _p(ws), ws.numel(), _s()), "b2_head_ce")
+    _count(3)
     return dict(loss=loss, count=count, preds=preds, dx=dx, dW=dW, db=db)
 
 
@@ -208,6 +252,7 @@ def head_gather(x, index, W, b, softmax=True):
     Wc = W.reshape(cout, cin).contiguous()
     _lib.check(lib.b2_head_gather(_p(x.buf), _p(index), n, _p(Wc), _p(b), cin, cout, int(softmax), _p(scores),
                                   _p(preds), _s()), "b2_head_gather")
+    _count(1)
     return scores, preds
 
 
@@ -219,6 +264,7 @@ def head_dense_fwd(x, W, b, softmax):
     Wc = W.reshape(cout, cin).contiguous()
     _lib.check(lib.b2_head_dense_fwd(_p(x.buf), x.N, x.V, _p(Wc), _p(b), cin, cout, int(softmax), _p(out), _s()),
                "b2_head_dense_fwd")
+    _count(1)
     return out
 
 
@@ -235,6 +281,7 @@ def head_dense_bwd(g, x, W):
     Wc = W.reshape(cout, cin).contiguous()
     _lib.check(lib.b2_head_dense_bwd(_p(g), _p(x.buf), x.N, x.V, _p(Wc), cin, cout, _p(dx.buf), _p(dW), _p(db),
                                      _p(ws), ws.numel(), _s()), "b2_head_dense_bwd")
+    _count(2)
     return dx, dW, db
 
 
@@ -250,6 +297,7 @@ def sgd_step(params, grads, moms, lr, momentum, grad_scale=1.0):
     M = arr(*[m.data_ptr() for m in moms])
     Nn = ll(*[p.numel() for p in params])
     _lib.check(lib.b2_sgd_step(P, G, M, Nn, n, float(lr), float(momentum), float(grad_scale), _s()), "b2_sgd_step")
+    _count((n + 63) // 64)
 
 
 def pack_conv_weights(w, want_dgrad=True):
@@ -263,6 +311,7 @@ def pack_conv_weights(w, want_dgrad=True):
     if not wc.is_contiguous():
         wc = wc.contiguous()
     _lib.check(lib.b2_pack_conv_weights(_p(wc), _p(wf), _p(wd), cout, cin, _s()), "b2_pack_conv_weights")
+    _count(1)
     return wf, wd
 
 
@@ -281,6 +330,7 @@ def fold_vote(scores, fold_dense, n_folds, thresholds):
     ws = Workspace.get(lib.b2_fold_vote_workspace_bytes(n, Cc, n_folds, T), dev, "vote")
     _lib.check(lib.b2_fold_vote(_p(scores.contiguous()), _p(fold_dense.contiguous()), n, Cc, n_folds, _p(th), T,
                                 _p(out), _p(ws), ws.numel(), _s()), "b2_fold_vote")
+    _count(3)
     return out
 
 
@@ -292,4 +342,5 @@ def esi_counts(y_true, y_pred, n_classes, counts=None):
         counts = torch.zeros((3, n_classes), dtype=torch.int64, device=y_true.device)
     _lib.check(lib.b2_esi_counts(_p(y_true.contiguous()), _p(y_pred.contiguous()), y_true.numel(), n_classes,
                                  _p(counts), _s()), "b2_esi_counts")
+    _count(1)
     return counts

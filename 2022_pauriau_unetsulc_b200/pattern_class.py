@@ -1,0 +1,413 @@
+"""``UnetPatternSulciLabelling`` — API-keeping base class (reference pattern_class.py:32-368).
+
+Same constructor, attributes, methods, file layout and result keys as the reference; the arithmetic underneath is
+the B200 path: ``labeling`` runs the eval forward and gathers Softmax scores at the skeleton voxels on the GPU
+(``UNet3D.scores_at``), ``test_thresholds`` evaluates all cutting thresholds in one ``b2_fold_vote`` pass, and the
+epoch loop shared by the training classes (``_fit``) uses the fused forward+loss+backward step, the fused SGD and
+on-device ESI counters.  Data-parallel training over subjects is enabled when ``torch.distributed`` is initialised.
+"""
+import copy
+import json
+import os
+import os.path as op
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops, parallel
+from .cutting import cutting_multi
+from .dataset import SulciDataset, extract_data
+from .early_stopping import EarlyStopping
+from .models import UNet3D
+from .optim import SGD
+from .stats import esi_from_counts, esi_score
+
+_BV_MODELS = '/casa/host/build/share/brainvisa-share-5.1/models/models_2019/cnn_models/'
+
+_MODEL_DEFAULTS = (  # attribute, dict_model key, default, printed label
+    ('num_filter', 'num_filter', 64, 'Number of filters : '),
+    ('num_channel', 'num_channel', 1, 'Number of channels : '),
+    ('interpolate', 'interpolate', True, 'Interpolate : '),
+    ('final_sigmoid', 'final_sigmoid', False, 'Final Sigmoid : '),
+    ('conv_layer_order', 'conv_layer_order', 'crg', 'Convolutional Layer Order : '),
+)
+
+
+def _summary_writer(log_dir):
+    try:
+        from torch.utils.tensorboard import SummaryWriter
+        return SummaryWriter(log_dir=log_dir)
+    except Exception:  # tensorboard not installed: results dict / JSON still carry every number
+        return None
+
+
+def make_head(init_channels, out_channels, num_conv):
+    """final_conv as the reference builds it (pattern_class.py:357-365): one 1x1x1 conv, or a chain of them."""
+    if num_conv > 1:
+        fac = (init_channels - out_channels) / num_conv
+        seq = nn.Sequential()
+        for n in range(num_conv):
+            seq.add_module(str(n), nn.Conv3d(init_channels - round(n * fac), init_channels - round((n + 1) * fac), 1))
+        return seq
+    return nn.Conv3d(init_channels, out_channels, 1)
+
+
+class UnetPatternSulciLabelling(object):
+
+    def __init__(self, graphs, hemi, cuda=-1, working_path=None, dict_model={},
+                 dict_names=None, dict_bck2=None, sulci_side_list=None):
+        self.graphs = graphs
+        self.hemi = hemi
+        self.dict_bck2 = dict_bck2
+        self.dict_names = dict_names
+        self.background = -1
+        self._set_sulci(sulci_side_list)
+        self.working_path = os.getcwd() if working_path is None else working_path
+
+        self.model = None
+        self.dict_model = dict_model
+        if 'name' in dict_model:
+            self.model_name = dict_model['name']
+            print('Model name: ', self.model_name)
+        else:
+            self.model_name = 'UnknownModel_hemi' + hemi
+        for attr, key, default, label in _MODEL_DEFAULTS:
+            if key in dict_model:
+                setattr(self, attr, dict_model[key])
+                print(label, dict_model[key])
+            else:
+                setattr(self, attr, default)
+        self.num_conv = dict_model.get('num_conv', 1)
+
+        self.results = {}
+        self.dict_scores = {}
+        self.trfile = None
+        # optional pre-extracted graph data {gfile: {'nbck','bck2','names','vert'}} (avoids soma.aims in test_thresholds)
+        self.dict_graph_data = {}
+
+        if cuda == -1:
+            self.device = torch.device('cpu')
+        else:
+            self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu", index=cuda)
+        print('Working on', self.device)
+
+    # ------------------------------------------------------------------------------------------ label dictionaries
+    def _set_sulci(self, sulci_side_list):
+        self.sulci_side_list = sulci_side_list
+        if sulci_side_list is None:
+            self.dict_sulci = None
+            self.sslist = None
+            return
+        self.dict_sulci = {s: i for i, s in enumerate(sulci_side_list)}
+        self.dict_sulci.setdefault('background', -1)
+        self.sslist = [s for s in sulci_side_list if not s.startswith('unknown') and not s.startswith('ventricle')]
+
+    def _graph_data(self, gfile):
+        if gfile in self.dict_graph_data:
+            return self.dict_graph_data[gfile]
+        from soma import aims
+        graph = aims.read(gfile)
+        if self.trfile is not None:
+            self.flt.translate(graph)
+        return extract_data(graph)
+
+    def extract_data_from_graphs(self):
+        print('Creating sulci side list...')
+        found = set()
+        dict_bck2, dict_names = {}, {}
+        for gfile in self.graphs:
+            data = self._graph_data(gfile)
+            dict_bck2[gfile] = data['bck2']
+            dict_names[gfile] = data['names']
+            found.update(data['names'])
+        self._set_sulci(sorted(found))
+        print(len(self.sulci_side_list), ' sulci detected')
+        self.dict_bck2 = dict_bck2
+        self.dict_names = dict_names
+
+    def fill_dict_model(self, dict_model):
+        side = 'left' if self.hemi == 'L' else 'right'
+        dict_model.setdefault('in_channels', 1)
+        if 'out_channels' not in dict_model:
+            dict_model['out_channels'] = _BV_MODELS + 'sulci_unet_model_params_%s.json' % side
+        if isinstance(dict_model['out_channels'], str):
+            with open(dict_model['out_channels'], 'r') as f:
+                dict_model['out_channels'] = len(json.load(f)['sulci_side_list'])
+        dict_model.setdefault('final_sigmoid', False)
+        dict_model.setdefault('interpolate', True)
+        dict_model.setdefault('conv_layer_order', 'crg')
+        dict_model.setdefault('init_channel_number', 64)
+        dict_model.setdefault('model_file', _BV_MODELS + 'sulci_unet_model_%s.mdsm' % side)
+        dict_model.setdefault('num_conv', 1)
+        return dict_model
+
+    # ------------------------------------------------------------------------------------------ inference
+    def labeling(self, gfile, bck2=None, names=None, imgsize=None):
+        """Returns (ytrue, ypred, yscores): lists over the skeleton points and a float64 [Npoints, C] array."""
+        print('Labeling', gfile)
+        self.model = self.model.to(self.device)
+        self.model.eval()
+        if bck2 is None:
+            bck2 = self.dict_bck2[gfile]
+        if names is None:
+            names = self.dict_names[gfile]
+        dataset = SulciDataset([gfile], self.dict_sulci, train=False, translation_file=self.trfile,
+                               dict_bck2={gfile: bck2}, dict_names={gfile: names}, img_size=imgsize)
+        inputs, labels = dataset[0]
+        pts = np.asarray(bck2) - np.min(bck2, axis=0)
+        D, H, W = labels.shape
+        lin = torch.as_tensor((pts[:, 0] * H + pts[:, 1]) * W + pts[:, 2], dtype=torch.long)
+        with torch.no_grad():
+            x = inputs.unsqueeze(0).to(self.device)
+            scores, preds = self.model.scores_at(x, lin.to(self.device))
+        ypred = preds.cpu().tolist()
+        ytrue = labels.reshape(-1)[lin].tolist()
+        yscores = scores.cpu().numpy().astype(np.float64)
+        return ytrue, ypred, yscores
+
+    def test_thresholds(self, gfile_list_test, gfile_list_notcut_test, threshold_range, save_results=True):
+        print('test thresholds')
+        since = time.time()
+        threshold_range = list(threshold_range)
+        for th in threshold_range:
+            self.dict_scores[th] = []
+        for gfile, gfile_notcut in zip(gfile_list_test, gfile_list_notcut_test):
+            data = self._graph_data(gfile)
+            nbck = np.asarray(data['nbck'])
+            bck2 = np.asarray(data['bck2'])
+            names = np.asarray(data['names'])
+            data_nc = self._graph_data(gfile_notcut)
+            nbck_nc = np.asarray(data_nc['nbck'])
+            vert_nc = np.asarray(data_nc['vert'])
+
+            _, _, yscores = self.labeling(gfile)
+
+            if len(nbck) != len(nbck_nc):
+                print()
+                print('ERROR no matches between %s and %s' % (gfile, gfile_notcut))
+                print('--- Files ignored to fix the threshold')
+                print()
+                continue
+            # match the voxels of the cut and not-cut graphs: both sorted by native (x, y, z)
+            order = np.lexsort((nbck[:, 2], nbck[:, 1], nbck[:, 0]))
+            order_nc = np.lexsort((nbck_nc[:, 2], nbck_nc[:, 1], nbck_nc[:, 0]))
+            vert_for_point = np.empty(len(nbck), dtype=vert_nc.dtype)
+            vert_for_point[order] = vert_nc[order_nc]
+            cut = cutting_multi(yscores, vert_for_point, bck2, threshold_range, device=self.device)
+            for th, ypred_cut in zip(threshold_range, cut):
+                pred_names = [self.sulci_side_list[y] for y in ypred_cut]
+                self.dict_scores[th].append((1 - esi_score(names, pred_names, self.sslist)) * 100)
+        if save_results:
+            store = self.results.setdefault('threshold_scores', {})
+            for th, sc in self.dict_scores.items():
+                store.setdefault(th, []).append(sc)
+        elapsed = time.time() - since
+        print('Cutting complete in {:.0f}m {:.0f}s'.format(elapsed // 60, elapsed % 60))
+
+    # ------------------------------------------------------------------------------------------ persistence
+    def _dump(self, sub, fname, payload):
+        os.makedirs(op.join(self.working_path, sub), exist_ok=True)
+        with open(op.join(self.working_path, sub, fname), 'w') as f:
+            json.dump(payload, f)
+
+    def save_data(self, name=None):
+        fname = self.model_name + '.json' if name is None else name + '_data.json'
+        self._dump('data', fname, {'dict_bck2': self.dict_bck2, 'dict_names': self.dict_names,
+                                   'sulci_side_list': self.sulci_side_list})
+        print('Data saved')
+
+    def _model_path(self, name):
+        if name is None:
+            return op.join(self.working_path, 'models', self.model_name + '_model.mdsm')
+        return op.join(self.working_path, 'models', self.model_name, name + '_model.mdsm')
+
+    def save_model(self, name=None):
+        path = self._model_path(name)
+        os.makedirs(op.dirname(path), exist_ok=True)
+        self.model.to(torch.device('cpu'))          # the reference leaves the model on the CPU (pattern_class.py:303)
+        torch.save(self.model.state_dict(), path)
+        print('Model saved')
+
+    def save_results(self, name=None):
+        self._dump('results', (self.model_name if name is None else name) + '_results.json', self.results)
+        print('Results saved')
+
+    def save_params(self, best_threshold=None, name=None):
+        os.makedirs(op.join(self.working_path, 'models'), exist_ok=True)
+        self.dict_model['model_file'] = self._model_path(name)
+        self.dict_model['out_channels'] = len(self.sulci_side_list)
+        params = {'dict_bck2': self.dict_bck2, 'dict_names': self.dict_names,
+                  'sulci_side_list': self.sulci_side_list, 'dict_model': self.dict_model}
+        if best_threshold is not None:
+            params['cutting_threshold'] = best_threshold
+        folder = op.join(self.working_path, 'models', self.model_name)
+        if not op.exists(folder):
+            folder = op.join(self.working_path, 'models')
+        fname = (self.model_name if name is None else name) + '_params.json'
+        with open(op.join(folder, fname), 'w') as f:
+            json.dump(params, f)
+        print('Parameters saved')
+
+    def reset_results(self):
+        self.results = {}
+
+    def load_saved_model(self, dict_model):
+        dict_model = self.fill_dict_model(dict_model)
+        self.model = UNet3D(dict_model['in_channels'], dict_model['out_channels'],
+                            final_sigmoid=dict_model['final_sigmoid'], interpolate=dict_model['interpolate'],
+                            conv_layer_order=dict_model['conv_layer_order'],
+                            init_channel_number=dict_model['init_channel_number'])
+        self.model.final_conv = make_head(dict_model['init_channel_number'], dict_model['out_channels'],
+                                          dict_model['num_conv'])
+        self.model.load_state_dict(torch.load(dict_model['model_file'], map_location='cpu'))
+        self.model.to(self.device)
+        print("Model Loaded !")
+
+    # ------------------------------------------------------------------------------------------ shared epoch loop
+    def _loaders(self, gfile_list_train, gfile_list_test, batch_size, num_epochs):
+        """Train / val DataLoaders as the reference builds them (training.py:84-136): batch 1 uses each subject's own
+        bounding box; batch > 1 pads every volume to the largest box seen over `num_epochs` augmented passes."""
+        import random
+
+        def make(files, train, img_size=None):
+            return SulciDataset(files, self.dict_sulci, train=train, translation_file=self.trfile,
+                                dict_bck2=self.dict_bck2, dict_names=self.dict_names, img_size=img_size)
+
+        def loader(ds):
+            return torch.utils.data.DataLoader(ds, batch_size=batch_size, shuffle=False, num_workers=0)
+
+        def max_size(ds, passes):
+            size = [0, 0, 0]
+            for _ in range(passes):
+                for vol, _ in ds:
+                    size = [max(size[i], vol.shape[i + 1]) for i in range(3)]
+            return size
+
+        sizes = {}
+        print('Extract validation dataloader...')
+        if batch_size == 1:
+            valloader = loader(make(gfile_list_test, False))
+        else:
+            sizes['val'] = max_size(make(gfile_list_test, False), 1)
+            print('Val dataset image size:', sizes['val'], sep=' ')
+            valloader = loader(make(gfile_list_test, False, sizes['val']))
+        print('Extract train dataloader...')
+        if batch_size == 1:
+            trainloader = loader(make(gfile_list_train, True))
+        else:
+            random.seed(42)
+            np.random.seed(42)
+            sizes['train'] = max_size(make(gfile_list_train, True), num_epochs)
+            print('Train dataset image size:', sizes['train'], sep=' ')
+            trainloader = loader(make(gfile_list_train, True, sizes['train']))
+            np.random.seed(42)
+            random.seed(42)
+        return trainloader, valloader, sizes
+
+    def _dist(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
+    def _run_phase(self, phase, loader, optimizer, reducer, before_step=None):
+        """One pass over `loader`.  Returns (epoch_loss, epoch_acc).  Losses and ESI counters stay on the device
+        until the end of the phase (one D2H read per phase instead of three per batch)."""
+        train = phase == 'train'
+        self.model.train() if train else self.model.eval()
+        rank, world = self._dist()
+        n_classes = len(self.sulci_side_list)
+        counts = torch.zeros((3, n_classes), dtype=torch.int64, device=self.device)
+        loss_sum = torch.zeros((), dtype=torch.float64, device=self.device)
+        n_seen = 0
+        for batch, (inputs, labels) in enumerate(loader):
+            if world > 1 and batch % world != rank:
+                continue                           # data parallel over subjects: rank r takes batches r, r+W, ...
+            inputs = inputs.to(self.device, non_blocking=True)
+            labels = labels.to(self.device, non_blocking=True)
+            if train:
+                if before_step is not None:
+                    before_step()
+                if reducer is not None:
+                    reducer.begin()
+                loss, _, preds, grads = self.model.forward_backward(
+                    inputs, labels, outs=reducer.outs() if reducer is not None else None)
+                if reducer is not None:
+                    grads = [g if n is not None else None for g, n in zip(reducer.finish(), grads)]
+                optimizer.step(grads=grads)
+                loss = loss[0]
+            else:
+                with torch.no_grad():
+                    loss, preds = self.model.loss_and_preds(inputs, labels)
+            loss_sum += loss.double() * inputs.size(0)
+            n_seen += inputs.size(0)
+            ops.esi_counts(labels.reshape(-1).to(torch.int32), preds.reshape(-1), n_classes, counts)
+        total = len(loader.dataset)
+        counts, loss_total, _ = parallel.allreduce_metrics(counts, float(loss_sum), n_seen)
+        epoch_loss = loss_total / total
+        epoch_acc = 1 - esi_from_counts(counts, [self.dict_sulci[ss] for ss in self.sslist])
+        return epoch_loss, epoch_acc
+
+    def _fit(self, lr, momentum, num_epochs, trainloader, valloader, patience, save_results, num_training,
+             tb_dir, before_step=None, after_epoch=None):
+        """Epoch loop shared by full training and transfer learning.  `after_epoch(epoch, val_loss, state)` may
+        change state['lr'] / request a new optimiser (LR division, fine-tuning switch).  Returns elapsed seconds."""
+        _, world = self._dist()
+        ordered = self.model.ordered_parameters()
+        state = {'lr': lr, 'optimizer': SGD(ordered, lr=lr, momentum=momentum, weight_decay=0)}
+        reducer = parallel.BucketedGradReducer(self.model) if world > 1 else None
+        writer = _summary_writer(tb_dir) if save_results else None
+        es_stop = EarlyStopping(patience=patience['early_stopping']) if 'early_stopping' in patience else None
+
+        print('training...')
+        since = time.time()
+        best_wts = copy.deepcopy(self.model.state_dict())
+        best_acc, best_epoch = 0., 0
+        for epoch in range(num_epochs):
+            print('Epoch {}/{}'.format(epoch, num_epochs - 1))
+            print('-' * 10)
+            t0 = time.time()
+            for phase in ('train', 'val'):
+                loader = trainloader if phase == 'train' else valloader
+                epoch_loss, epoch_acc = self._run_phase(phase, loader, state['optimizer'], reducer, before_step)
+                print('{} Loss: {:.4f} Acc: {:.4f}'.format(phase, epoch_loss, epoch_acc))
+                if save_results:
+                    if writer is not None:
+                        writer.add_scalar('Loss/' + phase, epoch_loss, epoch)
+                        writer.add_scalar('Accuracy/' + phase, epoch_acc, epoch)
+                    if epoch == 0:
+                        self.results['epoch_loss_' + phase].append([epoch_loss])
+                        self.results['epoch_acc_' + phase].append([epoch_acc])
+                    else:
+                        self.results['epoch_loss_' + phase][num_training].append(epoch_loss)
+                        self.results['epoch_acc_' + phase][num_training].append(epoch_acc)
+                if phase == 'val' and epoch_acc > best_acc:
+                    best_acc, best_epoch = epoch_acc, epoch
+                    best_wts = copy.deepcopy(self.model.state_dict())
+            # epoch_loss is now the VAL loss (CE of the softmax outputs, as in the reference)
+            if after_epoch is not None:
+                after_epoch(epoch, epoch_loss, state)
+                if state.pop('new_optimizer', False):   # a rebuilt optimiser starts with empty momentum buffers
+                    state['optimizer'] = SGD(ordered, lr=state['lr'], momentum=momentum)
+            if es_stop is not None:
+                es_stop(epoch_loss, self.model)
+                if es_stop.early_stop:
+                    print("Early stopping")
+                    break
+            print('Epoch took %i s.' % (time.time() - t0))
+            print('\n')
+        elapsed = time.time() - since
+        print('Training complete in {:.0f}m {:.0f}s'.format(elapsed // 60, elapsed % 60))
+        print('Best val Acc: {:4f}, Epoch {}'.format(best_acc, best_epoch))
+        if save_results:
+            self.results['best_acc'].append(best_acc)
+            self.results['best_epoch'].append(best_epoch)
+            self.results['duration'].append(elapsed)
+            if writer is not None:
+                writer.close()
+        if reducer is not None:
+            self.model.grad_ready_hook = None
+        self.model.load_state_dict(best_wts)
+        return elapsed

@@ -1,0 +1,45 @@
+"""CPU: the C-ABI shared library loads and exports exactly the symbols include/unetsulc_b200.h declares."""
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "unetsulc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_ctypes_table_agree():
+    import unetsulc_b200
+    from unetsulc_b200 import _lib
+    assert _declared() == sorted(_lib.SIGNATURES)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from unetsulc_b200 import _lib
+    lib = _lib.load()
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (b2_[a-z0-9_]+)", out))
+    for name in _declared():
+        assert name in exported, name
+        assert getattr(lib, name) is not None
+    assert lib.b2_last_error() is not None
+    # size queries are host-only arithmetic: callable without a GPU
+    assert lib.b2_gn_workspace_bytes(1, 64) == 592 * 64 * 2 * 4
+    assert lib.b2_conv3d_first_wgrad_workspace_bytes(32) == 296 * 27 * 32 * 4
+    assert lib.b2_head_workspace_bytes(64) > 0
+    assert lib.b2_fold_vote_workspace_bytes(100, 56, 7, 3) > 0
+
+
+def test_sass_contains_tcgen05_and_tma():
+    from unetsulc_b200 import _lib
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass          # tcgen05.mma
+    assert "UTMALDG" in sass          # cp.async.bulk.tensor
+    assert "LDTM" in sass             # tcgen05.ld
+    assert "HMMA." not in sass.replace("UTCHMMA", "")   # no legacy mma.sync path
