@@ -9,7 +9,11 @@
 // (out-of-volume voxels are zero-filled by TMA = the conv's zero padding) and one 2-D load brings the
 // BN x KC weight tile; both land 128B-swizzled, K-major, and feed tcgen05.mma (128 x BN x 16) with the
 // accumulator in TMEM (double-buffered so the epilogue of tile i overlaps the main loop of tile i+1).
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM owner), warps 2-5 epilogue.
+// Warp roles: warp 0 MMA issuer (+TMEM owner), warps 1-8 TMA producers, warps 9-12 epilogue.
+// Eight producer warps, not one: measured on B200 (tools/micro/tma_bench2.cu) a single thread retires one TMA op
+// per ~735 cycles whatever its size (<= 32 KB) and however many are in flight, while ops issued by different warps
+// proceed in parallel (1/2/4 warps: 22/45/89 B/clk/SM).  Stage s of the ring is filled by producer pair (s mod 4):
+// the even warp of the pair loads the A box, the odd warp the weight tile.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -31,16 +35,9 @@ struct IgemmParams {
   long long total_tiles;
 };
 
-static constexpr int kThreads = 192;
+static constexpr int kProducerPairs = 4;
+static constexpr int kThreads = 32 * (1 + 2 * kProducerPairs + 4);
 static constexpr int kAccStride = 256;  // TMEM columns between the two accumulators
-
-__device__ __forceinline__ bool tap_active(int tap, int w0, int h0, int d0, const IgemmParams& p) {
-  const int dd = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
-  if (d0 + dd + p.bd <= 0 || d0 + dd >= p.D) return false;
-  if (h0 + dh + p.bh <= 0 || h0 + dh >= p.H) return false;
-  if (w0 + dw + p.bw <= 0 || w0 + dw >= p.W) return false;
-  return true;
-}
 
 __device__ __forceinline__ void decode_tile(long long tile, const IgemmParams& p, int& n, int& d0, int& h0,
                                             int& w0, int& n0) {
@@ -58,13 +55,20 @@ __device__ __forceinline__ void decode_tile(long long tile, const IgemmParams& p
   n0 = nt * p.BN;
 }
 
+// All role loops are executed by the WHOLE warp with warp-uniform control flow and values; only the single
+// TMA / tcgen05 instruction is predicated on an elected lane.  (Round-1 finding, tools/timeline_igemm.py: running the
+// loops inside `if (lane == 0)` made every descriptor take the R2UR path into the uniform datapath and cost ~140
+// cycles per tcgen05.mma issue — the issuing thread, not TMA or the tensor pipe, bounded the kernel at ~900 cycles
+// per stage.)
+template <int KC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kABytes = 128 * KC * 2;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + (size_t)p.stages * p.a_bytes;
+  uint8_t* smem_b = smem + (size_t)p.stages * kABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * p.b_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
@@ -72,14 +76,14 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], 2);   // A loader + B loader each arrive with their own expect_tx
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -88,83 +92,80 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int n, d0, h0, w0, n0;
-        decode_tile(tile, p, n, d0, h0, w0, n0);
-        for (int tap = 0; tap < 27; ++tap) {
-          if (!tap_active(tap, w0, h0, d0, p)) continue;
-          const int dd = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
-          for (int ch = 0; ch < p.n_chunks; ++ch) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_bytes + p.b_bytes));
-            tma_load_5d(smem_a + (size_t)stage * p.a_bytes, &tmap_a, &full[stage], ch * p.KC, w0 + dw, h0 + dh,
-                        d0 + dd, n);
-            tma_load_2d(smem_b + (size_t)stage * p.b_bytes, &tmap_b, &full[stage], ch * p.KC, tap * p.Cout + n0);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1;
+  if (warp >= 1 && warp <= 2 * kProducerPairs) {
+    // ------------------------------------------------------------------ TMA producers
+    const int me = (warp - 1) >> 1;
+    const bool loads_a = ((warp - 1) & 1) == 0;
+    uint32_t gs = 0;  // global stage counter, identical in every producer and in the MMA issuer
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int n, d0, h0, w0, n0;
+      decode_tile(tile, p, n, d0, h0, w0, n0);
+      for (int tap = 0; tap < 27; ++tap) {
+        const int dd = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
+        for (int ch = 0; ch < p.n_chunks; ++ch, ++gs) {
+          if ((int)(gs % kProducerPairs) != me) continue;
+          const int stage = (int)(gs % (uint32_t)p.stages);
+          const uint32_t phase = (gs / (uint32_t)p.stages) & 1u;
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
+            if (loads_a) {
+              mbar_arrive_expect_tx(&full[stage], (uint32_t)kABytes);
+              tma_load_5d(smem_a + (size_t)stage * kABytes, &tmap_a, &full[stage], ch * KC, w0 + dw, h0 + dh, d0 + dd,
+                          n);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], (uint32_t)p.b_bytes);
+              tma_load_2d(smem_b + (size_t)stage * p.b_bytes, &tmap_b, &full[stage], ch * KC, tap * p.Cout + n0);
             }
           }
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN, 0, 0);
-      const uint32_t layout = (p.KC == 64) ? SWZ_128B : SWZ_64B;
-      const uint32_t sbo = 8u * (uint32_t)p.KC * 2u;
-      const int ksteps = p.KC / 16;
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        int n, d0, h0, w0, n0;
-        decode_tile(tile, p, n, d0, h0, w0, n0);
-        const uint32_t acc = it & 1u;
-        const uint32_t acc_phase = (it >> 1) & 1u;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN, 0, 0);
+    constexpr uint32_t kLayout = (KC == 64) ? SWZ_128B : SWZ_64B;
+    constexpr uint32_t kSbo = 8u * KC * 2u;
+    const uint64_t desc_hi = make_smem_desc(0, 16, kSbo, kLayout);           // everything but the start address
+    const uint32_t a0 = smem_u32(smem_a) >> 4, b0 = smem_u32(smem_b) >> 4;   // encoded start addresses of stage 0
+    const uint32_t a_step = kABytes >> 4, b_step = (uint32_t)p.b_bytes >> 4;
+    const int n_stage_per_tile = 27 * p.n_chunks;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kAccStride;
+      for (int ks = 0; ks < n_stage_per_tile; ++ks) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        uint32_t accumulate = 0;
-        for (int tap = 0; tap < 27; ++tap) {
-          if (!tap_active(tap, w0, h0, d0, p)) continue;
-          for (int ch = 0; ch < p.n_chunks; ++ch) {
-            mbar_wait(&full[stage], phase);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(smem_a + (size_t)stage * p.a_bytes);
-            const uint32_t b_base = smem_u32(smem_b + (size_t)stage * p.b_bytes);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t adesc = make_smem_desc(a_base + k * 32, 16, sbo, layout);
-              const uint64_t bdesc = make_smem_desc(b_base + k * 32, 16, sbo, layout);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
-              accumulate = 1;
-            }
-            umma_commit(&empty[stage]);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
+        if (elect_one()) {
+          const uint64_t adesc = desc_hi | (uint64_t)(a0 + (uint32_t)stage * a_step);
+          const uint64_t bdesc = desc_hi | (uint64_t)(b0 + (uint32_t)stage * b_step);
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the encoded address
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (ks == n_stage_per_tile - 1) umma_commit(&tmem_full[acc]);
         }
-        umma_commit(&tmem_full[acc]);
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
-    __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 9..12)
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;     // accumulator row == voxel within the box
     const int lw = row % p.bw;
@@ -228,7 +229,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -301,7 +302,10 @@ extern "C" int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* w
   const int smem_budget = 227 * 1024 - 1024 /*align*/ - 512 /*barriers*/;
   p.stages = smem_budget / (p.a_bytes + p.b_bytes);
   if (p.stages > 12) p.stages = 12;
-  B2_REQUIRE(p.stages >= 2, "b2_conv3d_igemm: tile does not fit shared memory");
+  // every stage has a fixed producer pair (stage mod kProducerPairs), so that no producer can run two ring
+  // phases ahead of the consumer
+  p.stages = (p.stages / kProducerPairs) * kProducerPairs;
+  B2_REQUIRE(p.stages >= kProducerPairs, "b2_conv3d_igemm: tile does not fit shared memory");
   p.relu = relu;
   p.ldy = ldy; p.y_coff = y_coff;
   p.y = y_is_fp32 ? nullptr : reinterpret_cast<__nv_bfloat16*>(y);
@@ -319,9 +323,15 @@ extern "C" int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* w
     if (rc) return rc;
   }
   const size_t smem_bytes = (size_t)p.stages * (p.a_bytes + p.b_bytes) + 1024 + 512;
-  B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv3d_igemm_kernel<<<(unsigned)grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+  if (p.KC == 64) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    conv3d_igemm_kernel<64><<<(unsigned)grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+  } else {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    conv3d_igemm_kernel<32><<<(unsigned)grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+  }
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }
+

@@ -28,12 +28,16 @@ struct WgradParams {
   int BN, n_cout_tiles;
   int splits;
   long long ksteps_total;
-  int stages_a;
+  int stages_a, n_prod;   // ring depth (a multiple of n_prod) and number of active slot-group producers
   int a_bytes, b_bytes, slot_bytes;
   float* ws;
 };
 
-static constexpr int kWgThreads = 192;
+// warp 0: MMA issuer (+TMEM owner); warps 1-4: TMA producers of the slot-group ring (stage s by producer s mod 4);
+// warp 5: TMA producer of the dY ring; warps 6-9: epilogue.  (One thread retires only one TMA op per ~735 cycles on
+// B200, ops of different warps run in parallel: tools/micro/tma_bench2.cu.)
+static constexpr int kWgProducers = 4;
+static constexpr int kWgThreads = 32 * (1 + kWgProducers + 1 + 4);
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
@@ -50,7 +54,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   uint64_t* acc_full = empty_b + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
 
   const int gchunk = blockIdx.x % p.n_gchunks;
@@ -62,7 +66,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const long long t_begin = p.ksteps_total * split / p.splits;
   const long long t_end = p.ksteps_total * (split + 1) / p.splits;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_dy);
     for (int s = 0; s < p.stages_a; ++s) {
@@ -76,33 +80,32 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      for (long long t = t_begin; t < t_end; ++t) {
-        long long mt = t;
-        const int w0 = (int)(mt % p.tiles_w) * p.bw;
-        mt /= p.tiles_w;
-        const int h0 = (int)(mt % p.tiles_h) * p.bh;
-        mt /= p.tiles_h;
-        const int d0 = (int)(mt % p.tiles_d) * p.bd;
-        const int n = (int)(mt / p.tiles_d);
-        // dY tile (B operand): BN/64 column blocks of [128 voxels][64 channels]
-        mbar_wait(&empty_b[sb], pb ^ 1);
-        mbar_arrive_expect_tx(&full_b[sb], (uint32_t)p.b_bytes);
-        for (int j = 0; j < p.BN / 64; ++j)
-          tma_load_5d(smem_b + (size_t)sb * p.b_bytes + (size_t)j * 16384, &tmap_dy, &full_b[sb], n0 + j * 64, w0,
-                      h0, d0, n);
-        if (++sb == 2) { sb = 0; pb ^= 1; }
-        for (int g = g_begin; g < g_end; ++g) {
-          mbar_wait(&empty_a[sa], pa ^ 1);
+  // Role loops run on the whole warp with warp-uniform control flow; only the TMA / tcgen05 instruction itself is
+  // issued by an elected lane (keeps descriptors and addresses in uniform registers, see conv_igemm.cu).
+  if (warp >= 1 && warp <= kWgProducers) {
+    // ---------------------------------------------------------------- producers of the shifted-X slot groups
+    const int me = warp - 1;
+    uint32_t ga = 0;
+    for (long long t = t_begin; t < t_end; ++t) {
+      long long mt = t;
+      const int w0 = (int)(mt % p.tiles_w) * p.bw;
+      mt /= p.tiles_w;
+      const int h0 = (int)(mt % p.tiles_h) * p.bh;
+      mt /= p.tiles_h;
+      const int d0 = (int)(mt % p.tiles_d) * p.bd;
+      const int n = (int)(mt / p.tiles_d);
+      for (int g = g_begin; g < g_end; ++g, ++ga) {
+        if ((int)(ga % (uint32_t)p.n_prod) != me) continue;   // stage s is always filled by producer s mod n_prod
+        const int sa = (int)(ga % (uint32_t)p.stages_a);
+        const uint32_t pa = (ga / (uint32_t)p.stages_a) & 1u;
+        mbar_wait(&empty_a[sa], pa ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full_a[sa], (uint32_t)p.a_bytes);
           for (int j = 0; j < p.SPG; ++j) {
             int s = g * p.SPG + j;
@@ -112,42 +115,66 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             tma_load_5d(smem_a + (size_t)sa * p.a_bytes + (size_t)j * p.slot_bytes, &tmap_x, &full_a[sa],
                         cc * p.SWC, w0 + dw, h0 + dh, d0 + dd, n);
           }
-          if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
         }
+        __syncwarp();
       }
     }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN, 1, 1);
-      const uint32_t layout_a = (p.SWC == 64) ? SWZ_128B : SWZ_64B;
-      const uint32_t row_a = (uint32_t)p.SWC * 2u;
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      for (long long t = t_begin; t < t_end; ++t) {
-        mbar_wait(&full_b[sb], pb);
+  } else if (warp == kWgProducers + 1) {
+    // ---------------------------------------------------------------- producer of the dY tiles
+    int sb = 0;
+    uint32_t pb = 0;
+    for (long long t = t_begin; t < t_end; ++t) {
+      long long mt = t;
+      const int w0 = (int)(mt % p.tiles_w) * p.bw;
+      mt /= p.tiles_w;
+      const int h0 = (int)(mt % p.tiles_h) * p.bh;
+      mt /= p.tiles_h;
+      const int d0 = (int)(mt % p.tiles_d) * p.bd;
+      const int n = (int)(mt / p.tiles_d);
+      mbar_wait(&empty_b[sb], pb ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full_b[sb], (uint32_t)p.b_bytes);
+        for (int j = 0; j < p.BN / 64; ++j)
+          tma_load_5d(smem_b + (size_t)sb * p.b_bytes + (size_t)j * 16384, &tmap_dy, &full_b[sb], n0 + j * 64, w0, h0,
+                      d0, n);
+      }
+      __syncwarp();
+      if (++sb == 2) { sb = 0; pb ^= 1; }
+    }
+  } else if (warp == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN, 1, 1);
+    const uint32_t layout_a = (p.SWC == 64) ? SWZ_128B : SWZ_64B;
+    const uint32_t row_a = (uint32_t)p.SWC * 2u;
+    const uint64_t a_hi = make_smem_desc(0, (uint32_t)p.slot_bytes, 8 * row_a, layout_a);
+    const uint64_t b_hi = make_smem_desc(0, 16384, 1024, SWZ_128B);
+    const uint32_t a0 = smem_u32(smem_a) >> 4, b0 = smem_u32(smem_b) >> 4;
+    const uint32_t a_kstep = (16 * row_a) >> 4, b_kstep = (16 * 128) >> 4;   // encoded advance per K16 (16 voxels)
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (long long t = t_begin; t < t_end; ++t) {
+      mbar_wait(&full_b[sb], pb);
+      tc_fence_after();
+      const uint64_t bdesc = b_hi | (uint64_t)(b0 + (uint32_t)sb * ((uint32_t)p.b_bytes >> 4));
+      for (int g = g_begin; g < g_end; ++g) {
+        mbar_wait(&full_a[sa], pa);
         tc_fence_after();
-        const uint32_t b_base = smem_u32(smem_b + (size_t)sb * p.b_bytes);
-        for (int g = g_begin; g < g_end; ++g) {
-          mbar_wait(&full_a[sa], pa);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(smem_a + (size_t)sa * p.a_bytes);
+        if (elect_one()) {
+          const uint64_t adesc = a_hi | (uint64_t)(a0 + (uint32_t)sa * ((uint32_t)p.a_bytes >> 4));
           const uint32_t d_tmem = tmem_base + (uint32_t)(g - g_begin) * p.BN;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {  // 128 voxels = 8 x K16
-            const uint64_t adesc = make_smem_desc(a_base + k * 16 * row_a, (uint32_t)p.slot_bytes, 8 * row_a, layout_a);
-            const uint64_t bdesc = make_smem_desc(b_base + k * 16 * 128, 16384, 1024, SWZ_128B);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (t != t_begin || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 8; ++k)   // 128 voxels = 8 x K16
+            umma_bf16(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc, (t != t_begin || k > 0) ? 1u : 0u);
           umma_commit(&empty_a[sa]);
-          if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+          if (g == g_end - 1) {
+            umma_commit(&empty_b[sb]);
+            if (t == t_end - 1) umma_commit(acc_full);
+          }
         }
-        umma_commit(&empty_b[sb]);
-        if (++sb == 2) { sb = 0; pb ^= 1; }
+        __syncwarp();
+        if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
       }
-      umma_commit(acc_full);
+      if (++sb == 2) { sb = 0; pb ^= 1; }
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -177,7 +204,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -240,7 +267,10 @@ static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int C
   p.b_bytes = 128 * p.BN * 2;
   const int budget = 227 * 1024 - 1024 - 512;
   p.stages_a = (budget - 2 * p.b_bytes) / p.a_bytes;
-  if (p.stages_a > 5) p.stages_a = 5;
+  if (p.stages_a > 4) p.stages_a = 4;
+  // a producer must never be two ring phases ahead of the consumer: give every stage a fixed owner
+  p.n_prod = p.stages_a < kWgProducers ? p.stages_a : kWgProducers;
+  p.stages_a = (p.stages_a / p.n_prod) * p.n_prod;
   return p.stages_a >= 2 ? 0 : -1;
 }
 

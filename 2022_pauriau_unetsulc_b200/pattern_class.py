@@ -312,6 +312,21 @@ class UnetPatternSulciLabelling(object):
             return dist.get_rank(), dist.get_world_size()
         return 0, 1
 
+    def train_step(self, inputs, labels, optimizer, reducer=None):
+        """One training step from HOST tensors (pinned memory recommended): H2D copy, fused forward + loss +
+        backward, gradient all-reduce when data parallel, fused SGD.  Returns the loss as a Python float (one D2H
+        read), i.e. what the reference's batch loop does per batch (training.py:198-215)."""
+        self.model.train()
+        x = inputs.to(self.device, non_blocking=True)
+        y = labels.to(self.device, non_blocking=True)
+        if reducer is not None:
+            reducer.begin()
+        loss, _, _, grads = self.model.forward_backward(x, y, outs=reducer.outs() if reducer is not None else None)
+        if reducer is not None:
+            grads = [g if n is not None else None for g, n in zip(reducer.finish(), grads)]
+        optimizer.step(grads=grads)
+        return float(loss[0].item())
+
     def _run_phase(self, phase, loader, optimizer, reducer, before_step=None):
         """One pass over `loader`.  Returns (epoch_loss, epoch_acc).  Losses and ESI counters stay on the device
         until the end of the phase (one D2H read per phase instead of three per batch)."""
