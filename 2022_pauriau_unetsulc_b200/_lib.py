@@ -20,10 +20,10 @@ SIGNATURES = {
     "b2_conv3d_first_wgrad_workspace_bytes": (_ll, [_i]),
     "b2_conv3d_first_wgrad": (_i, [_vp, _vp, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     "b2_gn_workspace_bytes": (_ll, [_i, _i]),
-    "b2_relu_gn_stats": (_i, [_vp, _i, _ll, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "b2_relu_gn_stats": (_i, [_vp, _i, _ll, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp]),
     "b2_relu_gn_apply": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "b2_relu_gn_bwd_workspace_bytes": (_ll, [_i, _i]),
-    "b2_relu_gn_bwd": (_i, [_vp, _i, _i, _vp, _i, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "b2_relu_gn_bwd": (_i, [_vp, _i, _i, _vp, _i, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp]),
     "b2_maxpool3d_bwd_add": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b2_upcat_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "b2_upcat_bwd": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
@@ -34,6 +34,7 @@ SIGNATURES = {
     "b2_head_dense_bwd": (_i, [_vp, _vp, _i, _ll, _vp, _i, _i, _vp, _vp, _vp, _vp, _ll, _vp]),
     "b2_sgd_step": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _vp]),
     "b2_pack_conv_weights": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "b2_pack_conv_weights_multi": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "b2_fold_vote_workspace_bytes": (_ll, [_ll, _i, _i, _i]),
     "b2_fold_vote": (_i, [_vp, _vp, _ll, _i, _i, _vp, _i, _vp, _vp, _ll, _vp]),
     "b2_esi_counts": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),

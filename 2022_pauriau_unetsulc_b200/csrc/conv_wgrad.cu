@@ -210,14 +210,39 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   }
 }
 
-// dW[co][ci][tap] = sum_s ws[s][tap][ci][co]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int Cin,
-                                    int Cout) {
+// dW[co][ci][tap] = sum_s ws[s][tap][ci][co]: block = (32-wide co tile, 8-wide ci tile), all 27 taps; reads run along
+// co (128-byte runs), writes run along (ci, tap) (864-byte runs) through a padded shared-memory transpose.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int Cin, int Cout) {
+  __shared__ float t[32 * 217];
+  const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 8;
+  const long long total = 27LL * Cin * Cout;
+  for (int e = threadIdx.x; e < 27 * 8 * 32; e += 256) {
+    const int co = e & 31, ci = (e >> 5) & 7, tap = e >> 8;
+    const long long src = ((long long)tap * Cin + ci0 + ci) * Cout + co0 + co;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[(long long)s * total + src];
+    t[co * 217 + ci * 27 + tap] = acc;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * 216; e += 256) {
+    const int co = e / 216, r = e % 216;   // r = ci*27 + tap
+    dw[((long long)(co0 + co) * Cin + ci0) * 27 + r] = t[co * 217 + r];
+  }
+}
+
+// small layers (few (co, ci) tiles): one thread per element, all splits summed in registers
+__global__ void __launch_bounds__(256)
+wgrad_reduce_simple_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int Cin, int Cout) {
   const long long total = 27LL * Cin * Cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += ws[(long long)s * total + i];
+    int s = 0;
+    for (; s + 3 < splits; s += 4)
+      acc += (ws[(long long)s * total + i] + ws[(long long)(s + 1) * total + i]) +
+             (ws[(long long)(s + 2) * total + i] + ws[(long long)(s + 3) * total + i]);
+    for (; s < splits; ++s) acc += ws[(long long)s * total + i];
     const int co = (int)(i % Cout);
     const long long r = i / Cout;
     const int ci = (int)(r % Cin);
@@ -311,10 +336,12 @@ extern "C" int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* d
   dim3 grid((unsigned)(p.n_gchunks * p.n_cout_tiles), (unsigned)p.splits);
   conv3d_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tx, ty, p);
   B2_CHECK_CUDA(cudaGetLastError());
-  const long long total = 27LL * Cin * Cout;
-  int rblocks = (int)((total + 255) / 256);
-  if (rblocks > num_sms() * 8) rblocks = num_sms() * 8;
-  wgrad_reduce_kernel<<<rblocks, 256, 0, stream>>>(p.ws, dw, p.splits, Cin, Cout);
+  if ((Cout / 32) * (Cin / 8) >= 2 * num_sms()) {
+    wgrad_reduce_kernel<<<dim3(Cout / 32, Cin / 8), 256, 0, stream>>>(p.ws, dw, p.splits, Cin, Cout);
+  } else {
+    const long long total = 27LL * Cin * Cout;
+    wgrad_reduce_simple_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p.ws, dw, p.splits, Cin, Cout);
+  }
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }

@@ -1,7 +1,8 @@
 // GroupNorm over post-ReLU activations ('crg' order: conv -> ReLU -> GroupNorm), NDHWC bf16, fp32 statistics.
 //
-// forward : stats pass  (sum x, sum x^2 per channel, per-block partials, deterministic two-stage reduce)
-//           finalize    (per (n, group): mean, rstd; per (n, channel): scale = rstd*gamma, shift = beta - mean*scale)
+// forward : stats pass  (sum x, sum x^2 per channel, per-block partials; the last block to finish reduces them in
+//                        a fixed order -> per (n, group) mean, rstd; per (n, channel) scale = rstd*gamma,
+//                        shift = beta - mean*scale; deterministic, no separate finalize launch)
 //           apply pass  y = r*scale + shift  (optionally also writes the 2x2x2 max-pooled tensor in the same read)
 // backward: stats pass  (sum dy, sum dy*xhat per channel), finalize (group sums, dgamma, dbeta, per-channel coefs),
 //           apply pass  dr = relu'(r) * rstd*(dy*gamma - mean_g(dy*gamma) - xhat*mean_g(dy*gamma*xhat))
@@ -11,79 +12,125 @@
 
 namespace b2 {
 
-static constexpr int kStatBlocks = 592;  // 4 x 148 SMs
+static constexpr int kStatBlocks = 296;  // 2 x 148 SMs (upper bound; small tensors use fewer, >= 64 KB per block)
 static constexpr int kStatThreads = 256;
 
 // ------------------------------------------------------------------------------------------------- forward stats
+// The block that finishes last (per sample, ticket from an integer atomic) reduces the per-block partials in a
+// fixed order and writes mean/rstd and the per-channel scale/shift: deterministic, and no separate finalize launch.
+__device__ __forceinline__ bool last_block_done(int* counter, int total) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1) == total - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// Last block only: per-channel totals over the per-block partials -> csum[C][2] (double, shared memory).
+// L = 256/C lanes cooperate per channel (independent loads in flight), combined in a fixed order.
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int n, int nblk, int C,
+                                                double* csum) {
+  const int L = (C >= kStatThreads) ? 1 : kStatThreads / C;     // power of two (C is a power-of-two multiple of 8)
+  const int sub = threadIdx.x % L;
+  for (int c = threadIdx.x / L; c < C; c += kStatThreads / L) {
+    double a = 0.0, b = 0.0;
+    const float* base = partial + ((size_t)n * nblk * C + c) * 2;
+    int blk = sub;
+    for (; blk + 3 * L < nblk; blk += 4 * L) {
+      const float2 p0 = __ldcg(reinterpret_cast<const float2*>(base + (size_t)blk * C * 2));
+      const float2 p1 = __ldcg(reinterpret_cast<const float2*>(base + (size_t)(blk + L) * C * 2));
+      const float2 p2 = __ldcg(reinterpret_cast<const float2*>(base + (size_t)(blk + 2 * L) * C * 2));
+      const float2 p3 = __ldcg(reinterpret_cast<const float2*>(base + (size_t)(blk + 3 * L) * C * 2));
+      a += ((double)p0.x + (double)p1.x) + ((double)p2.x + (double)p3.x);
+      b += ((double)p0.y + (double)p1.y) + ((double)p2.y + (double)p3.y);
+    }
+    for (; blk < nblk; blk += L) {
+      const float2 p0 = __ldcg(reinterpret_cast<const float2*>(base + (size_t)blk * C * 2));
+      a += (double)p0.x;
+      b += (double)p0.y;
+    }
+    for (int o = L >> 1; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (sub == 0) { csum[2 * c] = a; csum[2 * c + 1] = b; }
+  }
+}
+
 __global__ void __launch_bounds__(kStatThreads)
-gn_stats_kernel(const __nv_bfloat16* __restrict__ r, long long V, int C, float* __restrict__ partial) {
+gn_stats_kernel(const __nv_bfloat16* __restrict__ r, long long V, int C, float* __restrict__ partial, int* counters,
+                int G, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float* __restrict__ mean_rstd, float* __restrict__ scale_shift) {
   extern __shared__ float sh[];  // [vpi][C][2]
   const int C8 = C >> 3;
   const int vpi = kStatThreads / C8;
   const int oct = threadIdx.x % C8;
   const int vloc = threadIdx.x / C8;
   const int n = blockIdx.y;
-  const __nv_bfloat16* rn = r + (size_t)n * V * C;
+  const int nblk = gridDim.x;
+  const __nv_bfloat16* rn = r + (size_t)n * V * C + oct * 8;
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; q[i] = 0.f; }
-  if (vloc < vpi) {
-    for (long long v = (long long)blockIdx.x * vpi + vloc; v < V; v += (long long)gridDim.x * vpi) {
-      const f8 x = unpack8(ldg16(rn + v * C + oct * 8));
+  {
+    const long long stride = (long long)nblk * vpi;
+    long long v = (long long)blockIdx.x * vpi + vloc;
+    for (; v + 3 * stride < V; v += 4 * stride) {   // 4 independent 16-byte loads in flight per thread
+      const uint4 u0 = ldg16(rn + v * C), u1 = ldg16(rn + (v + stride) * C);
+      const uint4 u2 = ldg16(rn + (v + 2 * stride) * C), u3 = ldg16(rn + (v + 3 * stride) * C);
+      const f8 x0 = unpack8(u0), x1 = unpack8(u1), x2 = unpack8(u2), x3 = unpack8(u3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += (x0.v[i] + x1.v[i]) + (x2.v[i] + x3.v[i]);
+        q[i] = fmaf(x0.v[i], x0.v[i], fmaf(x1.v[i], x1.v[i], fmaf(x2.v[i], x2.v[i], fmaf(x3.v[i], x3.v[i], q[i]))));
+      }
+    }
+    for (; v < V; v += stride) {
+      const f8 x = unpack8(ldg16(rn + v * C));
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] += x.v[i]; q[i] = fmaf(x.v[i], x.v[i], q[i]); }
     }
+  }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      sh[((size_t)vloc * C + oct * 8 + i) * 2 + 0] = s[i];
-      sh[((size_t)vloc * C + oct * 8 + i) * 2 + 1] = q[i];
-    }
+  for (int i = 0; i < 8; ++i) {
+    sh[((size_t)vloc * C + oct * 8 + i) * 2 + 0] = s[i];
+    sh[((size_t)vloc * C + oct * 8 + i) * 2 + 1] = q[i];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f, b = 0.f;
     for (int j = 0; j < vpi; ++j) { a += sh[((size_t)j * C + c) * 2]; b += sh[((size_t)j * C + c) * 2 + 1]; }
-    float* dst = partial + (((size_t)n * gridDim.x + blockIdx.x) * C + c) * 2;
+    float* dst = partial + (((size_t)n * nblk + blockIdx.x) * C + c) * 2;
     dst[0] = a;
     dst[1] = b;
   }
-}
-
-// one block per (group, n)
-__global__ void __launch_bounds__(128)
-gn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int G, long long V, float eps,
-                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                   float* __restrict__ mean_rstd /*[N][C][2]*/, float* __restrict__ scale_shift /*[N][C][2]*/) {
-  const int g = blockIdx.x, n = blockIdx.y;
-  const int cpg = C / G;
-  double a = 0.0, b = 0.0;
-  for (int i = threadIdx.x; i < nblk * cpg; i += blockDim.x) {
-    const int blk = i / cpg, c = g * cpg + i % cpg;
-    const float* src = partial + (((size_t)n * nblk + blk) * C + c) * 2;
-    a += (double)src[0];
-    b += (double)src[1];
-  }
-  __shared__ double sa[128], sb[128];
-  sa[threadIdx.x] = a;
-  sb[threadIdx.x] = b;
+  if (!last_block_done(&counters[n], nblk)) return;
+  // ---- finalize sample n
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; }
-    __syncthreads();
+  double* csum = reinterpret_cast<double*>(sh);   // C*16 bytes <= the pass-1 scratch
+  reduce_partials(partial, n, nblk, C, csum);
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < cpg; ++k) { a += csum[2 * (g * cpg + k)]; b += csum[2 * (g * cpg + k) + 1]; }
+    const double m = (double)V * cpg;
+    const double mean = a / m;
+    double var = b / m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    for (int k = 0; k < cpg; ++k) {
+      const int c = g * cpg + k;
+      const float sc = rstd * gamma[c];
+      mean_rstd[((size_t)n * C + c) * 2 + 0] = (float)mean;
+      mean_rstd[((size_t)n * C + c) * 2 + 1] = rstd;
+      scale_shift[((size_t)n * C + c) * 2 + 0] = sc;
+      scale_shift[((size_t)n * C + c) * 2 + 1] = beta[c] - (float)mean * sc;
+    }
   }
-  const double m = (double)V * cpg;
-  const double mean = sa[0] / m;
-  double var = sb[0] / m - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  for (int j = threadIdx.x; j < cpg; j += blockDim.x) {
-    const int c = g * cpg + j;
-    const float sc = rstd * gamma[c];
-    mean_rstd[((size_t)n * C + c) * 2 + 0] = (float)mean;
-    mean_rstd[((size_t)n * C + c) * 2 + 1] = rstd;
-    scale_shift[((size_t)n * C + c) * 2 + 0] = sc;
-    scale_shift[((size_t)n * C + c) * 2 + 1] = beta[c] - (float)mean * sc;
-  }
+  if (threadIdx.x == 0) counters[n] = 0;   // self-resetting ticket
 }
 
 // ------------------------------------------------------------------------------------------------- forward apply
@@ -167,17 +214,22 @@ gn_apply_pool_kernel(const __nv_bfloat16* __restrict__ r, int N, int D, int H, i
 }
 
 // ------------------------------------------------------------------------------------------------- backward stats
+// coef[n][c] = {a, b, c0, pad}: dr = a*dy + b*xhat + c0.  The last block per sample finalizes that sample; the last
+// of those sums dgamma/dbeta over the samples (fixed order).
 __global__ void __launch_bounds__(kStatThreads)
 gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff, const __nv_bfloat16* __restrict__ r,
-                    long long V, int C, const float* __restrict__ mean_rstd, float* __restrict__ partial) {
+                    long long V, int C, const float* __restrict__ mean_rstd, float* __restrict__ partial,
+                    int* counters, int N, int G, const float* __restrict__ gamma, float* __restrict__ coef,
+                    float* __restrict__ dgb_n /*[N][C][2]*/, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float sh[];
   const int C8 = C >> 3;
   const int vpi = kStatThreads / C8;
   const int oct = threadIdx.x % C8;
   const int vloc = threadIdx.x / C8;
   const int n = blockIdx.y;
-  const __nv_bfloat16* rn = r + (size_t)n * V * C;
-  const __nv_bfloat16* dyn = dy + (size_t)n * V * lddy + dy_coff;
+  const int nblk = gridDim.x;
+  const __nv_bfloat16* rn = r + (size_t)n * V * C + oct * 8;
+  const __nv_bfloat16* dyn = dy + (size_t)n * V * lddy + dy_coff + oct * 8;
   float mu[8], rs[8], s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -186,90 +238,85 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
     s[i] = 0.f;
     q[i] = 0.f;
   }
-  if (vloc < vpi) {
-    for (long long v = (long long)blockIdx.x * vpi + vloc; v < V; v += (long long)gridDim.x * vpi) {
-      const f8 x = unpack8(ldg16(rn + v * C + oct * 8));
-      const f8 g = unpack8(ldg16(dyn + v * lddy + oct * 8));
+  {
+    const long long stride = (long long)nblk * vpi;
+    long long v = (long long)blockIdx.x * vpi + vloc;
+    for (; v + stride < V; v += 2 * stride) {   // 4 independent 16-byte loads in flight per thread
+      const uint4 ux0 = ldg16(rn + v * C), ug0 = ldg16(dyn + v * lddy);
+      const uint4 ux1 = ldg16(rn + (v + stride) * C), ug1 = ldg16(dyn + (v + stride) * lddy);
+      const f8 x0 = unpack8(ux0), g0 = unpack8(ug0), x1 = unpack8(ux1), g1 = unpack8(ug1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += g0.v[i] + g1.v[i];
+        q[i] = fmaf(g0.v[i], (x0.v[i] - mu[i]) * rs[i], fmaf(g1.v[i], (x1.v[i] - mu[i]) * rs[i], q[i]));
+      }
+    }
+    for (; v < V; v += stride) {
+      const f8 x = unpack8(ldg16(rn + v * C));
+      const f8 g = unpack8(ldg16(dyn + v * lddy));
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s[i] += g.v[i];
         q[i] = fmaf(g.v[i], (x.v[i] - mu[i]) * rs[i], q[i]);
       }
     }
+  }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      sh[((size_t)vloc * C + oct * 8 + i) * 2 + 0] = s[i];
-      sh[((size_t)vloc * C + oct * 8 + i) * 2 + 1] = q[i];
-    }
+  for (int i = 0; i < 8; ++i) {
+    sh[((size_t)vloc * C + oct * 8 + i) * 2 + 0] = s[i];
+    sh[((size_t)vloc * C + oct * 8 + i) * 2 + 1] = q[i];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f, b = 0.f;
     for (int j = 0; j < vpi; ++j) { a += sh[((size_t)j * C + c) * 2]; b += sh[((size_t)j * C + c) * 2 + 1]; }
-    float* dst = partial + (((size_t)n * gridDim.x + blockIdx.x) * C + c) * 2;
+    float* dst = partial + (((size_t)n * nblk + blockIdx.x) * C + c) * 2;
     dst[0] = a;
     dst[1] = b;
   }
-}
-
-// one block per group; loops over samples. coef[n][c] = {a, b, c0, pad}: dr = a*dy + b*xhat + c0
-__global__ void __launch_bounds__(128)
-gn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int N, int C, int G, long long V,
-                       const float* __restrict__ gamma, const float* __restrict__ mean_rstd,
-                       float* __restrict__ coef /*[N][C][4]*/, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int g = blockIdx.x;
-  const int cpg = C / G;
-  __shared__ double csum[2][64];   // per channel-in-group sums for the current sample (cpg <= 64)
-  __shared__ double dgs[64], dbs[64];
-  for (int j = threadIdx.x; j < cpg; j += blockDim.x) { dgs[j] = 0.0; dbs[j] = 0.0; }
+  if (!last_block_done(&counters[n], nblk)) return;
+  // ---- finalize sample n
   __syncthreads();
-  for (int n = 0; n < N; ++n) {
-    // each channel of the group: reduce over blocks with a sub-team of threads
-    for (int j = 0; j < cpg; ++j) {
-      const int c = g * cpg + j;
-      double a = 0.0, b = 0.0;
-      for (int blk = threadIdx.x; blk < nblk; blk += blockDim.x) {
-        const float* src = partial + (((size_t)n * nblk + blk) * C + c) * 2;
-        a += (double)src[0];
-        b += (double)src[1];
-      }
-      __shared__ double ra[128], rb[128];
-      ra[threadIdx.x] = a;
-      rb[threadIdx.x] = b;
-      __syncthreads();
-      for (int o = 64; o > 0; o >>= 1) {
-        if (threadIdx.x < o) { ra[threadIdx.x] += ra[threadIdx.x + o]; rb[threadIdx.x] += rb[threadIdx.x + o]; }
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) { csum[0][j] = ra[0]; csum[1][j] = rb[0]; }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      double S1 = 0.0, S2 = 0.0;
-      for (int j = 0; j < cpg; ++j) {
-        const double gm = (double)gamma[g * cpg + j];
-        S1 += gm * csum[0][j];
-        S2 += gm * csum[1][j];
-        dbs[j] += csum[0][j];
-        dgs[j] += csum[1][j];
-      }
-      const double m = (double)V * cpg;
-      for (int j = 0; j < cpg; ++j) {
-        const int c = g * cpg + j;
-        const double rstd = (double)mean_rstd[((size_t)n * C + c) * 2 + 1];
-        float* o = coef + ((size_t)n * C + c) * 4;
-        o[0] = (float)(rstd * (double)gamma[c]);
-        o[1] = (float)(-rstd * S2 / m);
-        o[2] = (float)(-rstd * S1 / m);
-        o[3] = 0.f;
-      }
-    }
-    __syncthreads();
+  double* csum = reinterpret_cast<double*>(sh);   // [C][2] per-channel sums over blocks (C*16 bytes <= smem of pass 1)
+  reduce_partials(partial, n, nblk, C, csum);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    dgb_n[((size_t)n * C + c) * 2 + 0] = (float)csum[2 * c + 1];   // d gamma contribution of sample n
+    dgb_n[((size_t)n * C + c) * 2 + 1] = (float)csum[2 * c];       // d beta
   }
-  for (int j = threadIdx.x; j < cpg; j += blockDim.x) {
-    if (dgamma) dgamma[g * cpg + j] = (float)dgs[j];
-    if (dbeta) dbeta[g * cpg + j] = (float)dbs[j];
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double S1 = 0.0, S2 = 0.0;
+    for (int k = 0; k < cpg; ++k) {
+      const double gm = (double)gamma[g * cpg + k];
+      S1 += gm * csum[2 * (g * cpg + k)];
+      S2 += gm * csum[2 * (g * cpg + k) + 1];
+    }
+    const double m = (double)V * cpg;
+    for (int k = 0; k < cpg; ++k) {
+      const int c = g * cpg + k;
+      const double rstd = (double)mean_rstd[((size_t)n * C + c) * 2 + 1];
+      float* o = coef + ((size_t)n * C + c) * 4;
+      o[0] = (float)(rstd * (double)gamma[c]);
+      o[1] = (float)(-rstd * S2 / m);
+      o[2] = (float)(-rstd * S1 / m);
+      o[3] = 0.f;
+    }
   }
+  if (threadIdx.x == 0) counters[n] = 0;
+  if (!last_block_done(&counters[N], N)) return;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float dg = 0.f, db = 0.f;
+    for (int k = 0; k < N; ++k) {
+      const float2 v2 = __ldcg(reinterpret_cast<const float2*>(dgb_n + ((size_t)k * C + c) * 2));
+      dg += v2.x;
+      db += v2.y;
+    }
+    if (dgamma) dgamma[c] = dg;
+    if (dbeta) dbeta[c] = db;
+  }
+  if (threadIdx.x == 0) counters[N] = 0;
 }
 
 __global__ void __launch_bounds__(256)
@@ -309,9 +356,9 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
 }
 
 static inline int stat_blocks(long long V, int C) {
-  const int vpi = kStatThreads / (C / 8);
-  long long nb = (V + vpi - 1) / vpi;
+  long long nb = (V * C * 2) / 65536;   // at least 64 KB of the tensor per block
   if (nb > kStatBlocks) nb = kStatBlocks;
+  if (nb < 1) nb = 1;
   return (int)nb;
 }
 static inline int ew_blocks(long long total) {
@@ -326,6 +373,7 @@ static inline int ew_blocks(long long total) {
 
 using namespace b2;
 
+extern "C" long long b2_relu_gn_bwd_workspace_bytes(int N, int C);
 extern "C" long long b2_gn_workspace_bytes(int N, int C) {
   return (long long)N * kStatBlocks * C * 2 * (long long)sizeof(float);
 }
@@ -334,15 +382,19 @@ static int check_gn_shape(const char* who, int N, long long V, int C, int G) {
   B2_REQUIRE(N > 0 && V > 0, "%s: bad shape", who);
   B2_REQUIRE(C % 8 == 0 && C >= 8 && C / 8 <= kStatThreads && kStatThreads % (C / 8) == 0,
              "%s: C=%d unsupported (C/8 must divide %d)", who, C, kStatThreads);
-  B2_REQUIRE(G > 0 && C % G == 0 && C / G <= 64, "%s: groups=%d unsupported for C=%d", who, G, C);
+  B2_REQUIRE(G > 0 && C % G == 0 && C / G <= 64 && kStatThreads % G == 0 && (kStatThreads / G) <= 32 &&
+                 ((kStatThreads / G) & (kStatThreads / G - 1)) == 0,
+             "%s: groups=%d unsupported for C=%d", who, G, C);
+  B2_REQUIRE(N <= 1024, "%s: batch %d too large", who, N);
   return B2_OK;
 }
 
 // r: bf16 [N][V][C] dense.  Outputs mean_rstd [N][C][2], scale_shift [N][C][2] (fp32).
 extern "C" int b2_relu_gn_stats(const void* r, int N, long long V, int C, int G, float eps, const float* gamma,
                                 const float* beta, float* mean_rstd, float* scale_shift, void* workspace,
-                                long long workspace_bytes, cudaStream_t stream) {
-  B2_REQUIRE(r && gamma && beta && mean_rstd && scale_shift && workspace, "b2_relu_gn_stats: null pointer");
+                                long long workspace_bytes, int* counters, cudaStream_t stream) {
+  B2_REQUIRE(r && gamma && beta && mean_rstd && scale_shift && workspace && counters,
+             "b2_relu_gn_stats: null pointer");
   int rc = check_gn_shape("b2_relu_gn_stats", N, V, C, G);
   if (rc) return rc;
   B2_REQUIRE(workspace_bytes >= b2_gn_workspace_bytes(N, C), "b2_relu_gn_stats: workspace too small");
@@ -350,10 +402,8 @@ extern "C" int b2_relu_gn_stats(const void* r, int N, long long V, int C, int G,
   const int vpi = kStatThreads / (C / 8);
   const size_t sh = (size_t)vpi * C * 2 * sizeof(float);
   gn_stats_kernel<<<dim3(nblk, N), kStatThreads, sh, stream>>>(reinterpret_cast<const __nv_bfloat16*>(r), V, C,
-                                                               reinterpret_cast<float*>(workspace));
-  B2_CHECK_CUDA(cudaGetLastError());
-  gn_finalize_kernel<<<dim3(G, N), 128, 0, stream>>>(reinterpret_cast<const float*>(workspace), nblk, C, G, V, eps,
-                                                     gamma, beta, mean_rstd, scale_shift);
+                                                               reinterpret_cast<float*>(workspace), counters, G, eps,
+                                                               gamma, beta, mean_rstd, scale_shift);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }
@@ -381,23 +431,22 @@ extern "C" int b2_relu_gn_apply(const void* r, int N, int D, int H, int W, int C
 // dr = relu'(r) * GroupNorm-backward(dy);  dgamma/dbeta fp32 [C] (overwritten; may be NULL)
 extern "C" int b2_relu_gn_bwd(const void* dy, int lddy, int dy_coff, const void* r, int N, long long V, int C, int G,
                               const float* gamma, const float* mean_rstd, void* dr, float* dgamma, float* dbeta,
-                              void* workspace, long long workspace_bytes, cudaStream_t stream) {
-  B2_REQUIRE(dy && r && gamma && mean_rstd && dr && workspace, "b2_relu_gn_bwd: null pointer");
+                              void* workspace, long long workspace_bytes, int* counters, cudaStream_t stream) {
+  B2_REQUIRE(dy && r && gamma && mean_rstd && dr && workspace && counters, "b2_relu_gn_bwd: null pointer");
   int rc = check_gn_shape("b2_relu_gn_bwd", N, V, C, G);
   if (rc) return rc;
   B2_REQUIRE(lddy % 8 == 0 && dy_coff % 8 == 0, "b2_relu_gn_bwd: lddy/dy_coff must be multiples of 8");
-  const long long need = b2_gn_workspace_bytes(N, C) + (long long)N * C * 4 * (long long)sizeof(float);
+  const long long need = b2_relu_gn_bwd_workspace_bytes(N, C);
   B2_REQUIRE(workspace_bytes >= need, "b2_relu_gn_bwd: workspace %lld < %lld", workspace_bytes, need);
   float* partial = reinterpret_cast<float*>(workspace);
   float* coef = partial + (size_t)N * kStatBlocks * C * 2;
+  float* dgb_n = coef + (size_t)N * C * 4;
   const int nblk = stat_blocks(V, C);
   const int vpi = kStatThreads / (C / 8);
   const size_t sh = (size_t)vpi * C * 2 * sizeof(float);
   gn_bwd_stats_kernel<<<dim3(nblk, N), kStatThreads, sh, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
-      mean_rstd, partial);
-  B2_CHECK_CUDA(cudaGetLastError());
-  gn_bwd_finalize_kernel<<<G, 128, 0, stream>>>(partial, nblk, N, C, G, V, gamma, mean_rstd, coef, dgamma, dbeta);
+      mean_rstd, partial, counters, N, G, gamma, coef, dgb_n, dgamma, dbeta);
   B2_CHECK_CUDA(cudaGetLastError());
   const long long total = (long long)N * V * (C / 8);
   gn_bwd_apply_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff,
@@ -408,5 +457,5 @@ extern "C" int b2_relu_gn_bwd(const void* dy, int lddy, int dy_coff, const void*
 }
 
 extern "C" long long b2_relu_gn_bwd_workspace_bytes(int N, int C) {
-  return b2_gn_workspace_bytes(N, C) + (long long)N * C * 4 * (long long)sizeof(float);
+  return b2_gn_workspace_bytes(N, C) + (long long)N * C * 6 * (long long)sizeof(float);
 }

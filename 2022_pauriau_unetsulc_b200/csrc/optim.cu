@@ -38,21 +38,56 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(const SgdArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(256)
-pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd,
-                    int Cout, int Cin) {
-  const long long total = 27LL * Cout * Cin;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    // i enumerates the fprop pack [tap][co][ci] (coalesced writes)
-    const int ci = (int)(i % Cin);
-    const long long r = i / Cin;
-    const int co = (int)(r % Cout);
-    const int tap = (int)(r / Cout);
-    const float val = w[((long long)co * Cin + ci) * 27 + tap];
-    const __nv_bfloat16 b = __float2bfloat16_rn(val);
-    if (wf) wf[i] = b;
-    if (wd) wd[((long long)(26 - tap) * Cin + ci) * Cout + co] = b;
+// Multi-layer weight pack, one launch for every conv layer whose fp32 master changed.
+//   role 0 (fprop):  block = (co, 64-wide ci tile): reads W[co][ci0..][27] (contiguous), writes Wf[tap][co][ci0..]
+//   role 1 (dgrad):  block = (ci, 64-wide co tile): reads W[co0..][ci][27] (108-byte runs), writes Wd[26-tap][ci][co0..]
+// Both directions go through a shared-memory transpose so that global reads and writes are contiguous runs.
+static constexpr int kMaxPackLayers = 16;
+struct PackArgs {
+  const float* w[kMaxPackLayers];
+  __nv_bfloat16* wf[kMaxPackLayers];
+  __nv_bfloat16* wd[kMaxPackLayers];
+  int cout[kMaxPackLayers], cin[kMaxPackLayers];
+  int first_block[kMaxPackLayers + 1];
+  int count;
+};
+
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackArgs a) {
+  __shared__ float tile[64][28];
+  int l = 0;
+  while (l + 1 < a.count && (int)blockIdx.x >= a.first_block[l + 1]) ++l;
+  const int Cout = a.cout[l], Cin = a.cin[l];
+  const float* __restrict__ w = a.w[l];
+  int b = blockIdx.x - a.first_block[l];
+  const int ci_tiles = (Cin + 63) / 64, co_tiles = (Cout + 63) / 64;
+  const int n_f = Cout * ci_tiles;
+  if (b < n_f) {
+    if (a.wf[l] == nullptr) return;
+    const int co = b / ci_tiles, ci0 = (b % ci_tiles) * 64;
+    const int tw = min(64, Cin - ci0);
+    const float* src = w + ((size_t)co * Cin + ci0) * 27;
+    for (int e = threadIdx.x; e < tw * 27; e += 256) tile[e / 27][e % 27] = src[e];
+    __syncthreads();
+    __nv_bfloat16* dst = a.wf[l];
+    for (int e = threadIdx.x; e < 27 * tw; e += 256) {
+      const int tap = e / tw, ci = e % tw;
+      dst[((size_t)tap * Cout + co) * Cin + ci0 + ci] = __float2bfloat16_rn(tile[ci][tap]);
+    }
+  } else {
+    if (a.wd[l] == nullptr) return;
+    b -= n_f;
+    const int ci = b / co_tiles, co0 = (b % co_tiles) * 64;
+    const int tw = min(64, Cout - co0);
+    for (int e = threadIdx.x; e < tw * 27; e += 256) {
+      const int j = e / 27, tap = e % 27;
+      tile[j][tap] = w[((size_t)(co0 + j) * Cin + ci) * 27 + tap];
+    }
+    __syncthreads();
+    __nv_bfloat16* dst = a.wd[l];
+    for (int e = threadIdx.x; e < 27 * tw; e += 256) {
+      const int tap = e / tw, j = e % tw;
+      dst[((size_t)(26 - tap) * Cin + ci) * Cout + co0 + j] = __float2bfloat16_rn(tile[j][tap]);
+    }
   }
 }
 
@@ -94,14 +129,39 @@ extern "C" int b2_sgd_step(float* const* params, const float* const* grads, floa
   return B2_OK;
 }
 
-// w: fp32 [Cout][Cin][3][3][3]; wf/wd: bf16 packs (either may be NULL)
+// count layers; w/wf/wd/cout/cin are HOST arrays.  w[i]: fp32 [Cout][Cin][3][3][3]; wf[i]/wd[i]: bf16 packs (may be NULL)
+extern "C" int b2_pack_conv_weights_multi(const float* const* w, void* const* wf, void* const* wd, const int* cout,
+                                          const int* cin, int count, cudaStream_t stream) {
+  B2_REQUIRE(w && wf && wd && cout && cin && count >= 0, "b2_pack_conv_weights_multi: null pointer");
+  int done = 0;
+  while (done < count) {
+    PackArgs a;
+    int k = 0, blocks = 0;
+    while (done + k < count && k < kMaxPackLayers) {
+      const int i = done + k;
+      B2_REQUIRE(w[i] && (wf[i] || wd[i]), "b2_pack_conv_weights_multi: null tensor %d", i);
+      a.w[k] = w[i];
+      a.wf[k] = reinterpret_cast<__nv_bfloat16*>(wf[i]);
+      a.wd[k] = reinterpret_cast<__nv_bfloat16*>(wd[i]);
+      a.cout[k] = cout[i];
+      a.cin[k] = cin[i];
+      a.first_block[k] = blocks;
+      blocks += cout[i] * ((cin[i] + 63) / 64) + cin[i] * ((cout[i] + 63) / 64);
+      ++k;
+    }
+    a.first_block[k] = blocks;
+    a.count = k;
+    if (blocks > 0) {
+      pack_weights_multi_kernel<<<blocks, 256, 0, stream>>>(a);
+      B2_CHECK_CUDA(cudaGetLastError());
+    }
+    done += k;
+  }
+  return B2_OK;
+}
+
+// single layer convenience
 extern "C" int b2_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t stream) {
   B2_REQUIRE(w && (wf || wd), "b2_pack_conv_weights: null pointer");
-  const long long total = 27LL * Cout * Cin;
-  long long blocks = (total + 255) / 256;
-  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  pack_weights_kernel<<<(unsigned)blocks, 256, 0, stream>>>(w, reinterpret_cast<__nv_bfloat16*>(wf),
-                                                            reinterpret_cast<__nv_bfloat16*>(wd), Cout, Cin);
-  B2_CHECK_CUDA(cudaGetLastError());
-  return B2_OK;
+  return b2_pack_conv_weights_multi(&w, &wf, &wd, &Cout, &Cin, 1, stream);
 }

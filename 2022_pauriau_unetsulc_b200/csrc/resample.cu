@@ -86,30 +86,44 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
   l0 = 1.f - l1;
 }
 
+static constexpr int kMaxUpW = 512;   // widest output row the per-row tables support
+static constexpr int kMaxTouch = 8;   // fine samples that can touch one coarse sample along a dimension (ratio <= 3.5)
+
+// one block per output row (n, d, h): the D/H interpolation is uniform per block, the W interpolation comes from a
+// shared-memory table built once per block; threads sweep (w, channel octet) with 32-bit index math.
 __global__ void __launch_bounds__(256)
 upsample_cat_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int Di, int Hi, int Wi, int C,
                         __nv_bfloat16* __restrict__ cat, int ldc, int coff, int Do, int Ho, int Wo) {
+  __shared__ int s_i0[kMaxUpW], s_i1[kMaxUpW];
+  __shared__ float s_l1[kMaxUpW];
   const int C8 = C >> 3;
+  const int row = blockIdx.x;
+  const int h = row % Ho, d = (row / Ho) % Do, n = row / (Ho * Do);
   const float sd = (float)Di / (float)Do, shh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
-  const long long total = (long long)N * Do * Ho * Wo * C8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int oct = (int)(i % C8);
-    long long t = i / C8;
-    const long long vo = t;
-    const int w = (int)(t % Wo); t /= Wo;
-    const int h = (int)(t % Ho); t /= Ho;
-    const int d = (int)(t % Do);
-    const int n = (int)(t / Do);
-    int d0, d1, h0, h1, w0, w1;
-    float ld0, ld1, lh0, lh1, lw0, lw1;
-    src_index(d, sd, Di, d0, d1, ld0, ld1);
-    src_index(h, shh, Hi, h0, h1, lh0, lh1);
-    src_index(w, sw, Wi, w0, w1, lw0, lw1);
-    const __nv_bfloat16* xb = x + (size_t)n * Di * Hi * Wi * C + oct * 8;
-    auto at = [&](int dd, int hh, int ww) { return unpack8(ldg16(xb + (((size_t)dd * Hi + hh) * Wi + ww) * C)); };
-    const f8 a000 = at(d0, h0, w0), a001 = at(d0, h0, w1), a010 = at(d0, h1, w0), a011 = at(d0, h1, w1);
-    const f8 a100 = at(d1, h0, w0), a101 = at(d1, h0, w1), a110 = at(d1, h1, w0), a111 = at(d1, h1, w1);
+  for (int w = threadIdx.x; w < Wo; w += blockDim.x) {
+    int i0, i1; float l0, l1;
+    src_index(w, sw, Wi, i0, i1, l0, l1);
+    s_i0[w] = i0 * C; s_i1[w] = i1 * C; s_l1[w] = l1;
+  }
+  int d0, d1, h0, h1; float ld0, ld1, lh0, lh1;
+  src_index(d, sd, Di, d0, d1, ld0, ld1);
+  src_index(h, shh, Hi, h0, h1, lh0, lh1);
+  __syncthreads();
+  const __nv_bfloat16* xb = x + (size_t)n * Di * Hi * Wi * C;
+  const __nv_bfloat16* r00 = xb + ((size_t)d0 * Hi + h0) * Wi * C;
+  const __nv_bfloat16* r01 = xb + ((size_t)d0 * Hi + h1) * Wi * C;
+  const __nv_bfloat16* r10 = xb + ((size_t)d1 * Hi + h0) * Wi * C;
+  const __nv_bfloat16* r11 = xb + ((size_t)d1 * Hi + h1) * Wi * C;
+  __nv_bfloat16* out = cat + (size_t)row * Wo * ldc + coff;
+  const int total = Wo * C8;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int w = e / C8, oc = (e - w * C8) * 8;
+    const int o0 = s_i0[w] + oc, o1 = s_i1[w] + oc;
+    const float lw1 = s_l1[w], lw0 = 1.f - lw1;
+    const f8 a000 = unpack8(ldg16(r00 + o0)), a001 = unpack8(ldg16(r00 + o1));
+    const f8 a010 = unpack8(ldg16(r01 + o0)), a011 = unpack8(ldg16(r01 + o1));
+    const f8 a100 = unpack8(ldg16(r10 + o0)), a101 = unpack8(ldg16(r10 + o1));
+    const f8 a110 = unpack8(ldg16(r11 + o0)), a111 = unpack8(ldg16(r11 + o1));
     f8 o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -117,70 +131,74 @@ upsample_cat_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int Di, int 
       o.v[k] = ld0 * (lh0 * (lw0 * a000.v[k] + lw1 * a001.v[k]) + lh1 * (lw0 * a010.v[k] + lw1 * a011.v[k])) +
                ld1 * (lh0 * (lw0 * a100.v[k] + lw1 * a101.v[k]) + lh1 * (lw0 * a110.v[k] + lw1 * a111.v[k]));
     }
-    stg16(cat + vo * ldc + coff + oct * 8, pack8(o));
+    stg16(out + (size_t)w * ldc + oc, pack8(o));
   }
 }
 
-// range of output indices whose interpolation touches input index i (conservative; exact test done per element)
-__device__ __forceinline__ void touch_range(int i, float scale, int out_size, int& lo, int& hi) {
-  // src(dst) = scale*(dst+0.5)-0.5 in [i-1, i+1)  =>  dst in ((i-0.5)/scale-0.5, (i+1.5)/scale-0.5)
-  float a = ((float)i - 0.5f) / scale - 0.5f;
-  float b = ((float)i + 1.5f) / scale - 0.5f;
-  lo = (int)floorf(a) - 1;
-  hi = (int)ceilf(b) + 1;
+// fine samples whose interpolation touches coarse index i, with their weights (exact: same src_index as forward)
+__device__ __forceinline__ int touch_list(int i, float scale, int in_size, int out_size, int* idx, float* wt) {
+  const float a = ((float)i - 0.5f) / scale - 0.5f;
+  const float b = ((float)i + 1.5f) / scale - 0.5f;
+  int lo = (int)floorf(a) - 1, hi = (int)ceilf(b) + 1;
   if (lo < 0) lo = 0;
   if (hi > out_size - 1) hi = out_size - 1;
+  int cnt = 0;
+  for (int o = lo; o <= hi; ++o) {
+    int i0, i1; float l0, l1;
+    src_index(o, scale, in_size, i0, i1, l0, l1);
+    const float w = (i0 == i ? l0 : 0.f) + (i1 == i ? l1 : 0.f);
+    if (w != 0.f && cnt < kMaxTouch) { idx[cnt] = o; wt[cnt] = w; ++cnt; }
+  }
+  return cnt;
 }
 
+// adjoint of the trilinear upsample as a deterministic gather: one block per coarse row (n, d, h)
 __global__ void __launch_bounds__(256)
 upsample_cat_bwd_kernel(const __nv_bfloat16* __restrict__ dcat, int ldc, int coff, int N, int Do, int Ho, int Wo,
                         __nv_bfloat16* __restrict__ dx, int Di, int Hi, int Wi, int C) {
+  __shared__ int s_cnt[kMaxUpW];
+  __shared__ int s_idx[kMaxUpW][kMaxTouch];
+  __shared__ float s_wt[kMaxUpW][kMaxTouch];
   const int C8 = C >> 3;
+  const int row = blockIdx.x;
+  const int h = row % Hi, d = (row / Hi) % Di, n = row / (Hi * Di);
   const float sd = (float)Di / (float)Do, shh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
-  const long long total = (long long)N * Di * Hi * Wi * C8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int oct = (int)(i % C8);
-    long long t = i / C8;
-    const long long vi = t;
-    const int w = (int)(t % Wi); t /= Wi;
-    const int h = (int)(t % Hi); t /= Hi;
-    const int d = (int)(t % Di);
-    const int n = (int)(t / Di);
-    int dlo, dhi, hlo, hhi, wlo, whi;
-    touch_range(d, sd, Do, dlo, dhi);
-    touch_range(h, shh, Ho, hlo, hhi);
-    touch_range(w, sw, Wo, wlo, whi);
+  for (int w = threadIdx.x; w < Wi; w += blockDim.x) {
+    int idx[kMaxTouch]; float wt[kMaxTouch];
+    const int c = touch_list(w, sw, Wi, Wo, idx, wt);
+    s_cnt[w] = c;
+    for (int k = 0; k < c; ++k) { s_idx[w][k] = idx[k] * ldc; s_wt[w][k] = wt[k]; }
+  }
+  int didx[kMaxTouch], hidx[kMaxTouch];
+  float dwt[kMaxTouch], hwt[kMaxTouch];
+  const int nd = touch_list(d, sd, Di, Do, didx, dwt);
+  const int nh = touch_list(h, shh, Hi, Ho, hidx, hwt);
+  __syncthreads();
+  const __nv_bfloat16* gb = dcat + (size_t)n * Do * Ho * Wo * ldc + coff;
+  __nv_bfloat16* out = dx + (size_t)row * Wi * C;
+  const int total = Wi * C8;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int w = e / C8, oc = (e - w * C8) * 8;
+    const int nw = s_cnt[w];
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    const __nv_bfloat16* gb = dcat + (size_t)n * Do * Ho * Wo * ldc + coff + oct * 8;
-    for (int od = dlo; od <= dhi; ++od) {
-      int a0, a1; float la0, la1;
-      src_index(od, sd, Di, a0, a1, la0, la1);
-      const float wd = (a0 == d ? la0 : 0.f) + (a1 == d ? la1 : 0.f);
-      if (wd == 0.f) continue;
-      for (int oh = hlo; oh <= hhi; ++oh) {
-        int b0, b1; float lb0, lb1;
-        src_index(oh, shh, Hi, b0, b1, lb0, lb1);
-        const float wh = (b0 == h ? lb0 : 0.f) + (b1 == h ? lb1 : 0.f);
-        if (wh == 0.f) continue;
-        for (int ow = wlo; ow <= whi; ++ow) {
-          int c0, c1; float lc0, lc1;
-          src_index(ow, sw, Wi, c0, c1, lc0, lc1);
-          const float ww = (c0 == w ? lc0 : 0.f) + (c1 == w ? lc1 : 0.f);
-          if (ww == 0.f) continue;
-          const float wt = wd * wh * ww;
-          const f8 g = unpack8(ldg16(gb + (((size_t)od * Ho + oh) * Wo + ow) * ldc));
+    for (int a = 0; a < nd; ++a) {
+      for (int b = 0; b < nh; ++b) {
+        const __nv_bfloat16* rp = gb + ((size_t)didx[a] * Ho + hidx[b]) * Wo * ldc + oc;
+        const float wdh = dwt[a] * hwt[b];
+        for (int c = 0; c < nw; ++c) {
+          const float wgt = wdh * s_wt[w][c];
+          const f8 g = unpack8(ldg16(rp + s_idx[w][c]));
 #pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] = fmaf(wt, g.v[k], acc[k]);
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, g.v[k], acc[k]);
         }
       }
     }
     f8 o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.v[k] = acc[k];
-    stg16(dx + vi * C + oct * 8, pack8(o));
+    stg16(out + (size_t)w * C + oc, pack8(o));
   }
 }
 
@@ -206,8 +224,9 @@ extern "C" int b2_upcat_fwd(const void* x, int N, int Di, int Hi, int Wi, int C,
                             int Ho, int Wo, cudaStream_t stream) {
   B2_REQUIRE(x && cat, "b2_upcat_fwd: null pointer");
   B2_REQUIRE(C % 8 == 0 && ldc % 8 == 0 && coff % 8 == 0, "b2_upcat_fwd: channel counts must be multiples of 8");
-  const long long total = (long long)N * Do * Ho * Wo * (C / 8);
-  upsample_cat_fwd_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, Di, Hi,
+  B2_REQUIRE(Wo <= kMaxUpW && Wi <= kMaxUpW, "b2_upcat_fwd: row width %d > %d", Wo, kMaxUpW);
+  B2_REQUIRE((long long)Wi * C < (1LL << 31) && (long long)Wo * ldc < (1LL << 31), "b2_upcat_fwd: row too large");
+  upsample_cat_fwd_kernel<<<(unsigned)(N * Do * Ho), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, Di, Hi,
                                                                 Wi, C, reinterpret_cast<__nv_bfloat16*>(cat), ldc, coff,
                                                                 Do, Ho, Wo);
   B2_CHECK_CUDA(cudaGetLastError());
@@ -218,8 +237,10 @@ extern "C" int b2_upcat_bwd(const void* dcat, int ldc, int coff, int N, int Do, 
                             int Hi, int Wi, int C, cudaStream_t stream) {
   B2_REQUIRE(dcat && dx, "b2_upcat_bwd: null pointer");
   B2_REQUIRE(C % 8 == 0 && ldc % 8 == 0 && coff % 8 == 0, "b2_upcat_bwd: channel counts must be multiples of 8");
-  const long long total = (long long)N * Di * Hi * Wi * (C / 8);
-  upsample_cat_bwd_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dcat), ldc, coff,
+  B2_REQUIRE(Wo <= kMaxUpW && Wi <= kMaxUpW, "b2_upcat_bwd: row width %d > %d", Wo, kMaxUpW);
+  B2_REQUIRE(2 * Do <= 7 * Di && 2 * Ho <= 7 * Hi && 2 * Wo <= 7 * Wi, "b2_upcat_bwd: upsampling ratio > 3.5 unsupported");
+  B2_REQUIRE((long long)Wo * ldc < (1LL << 31), "b2_upcat_bwd: row too large");
+  upsample_cat_bwd_kernel<<<(unsigned)(N * Di * Hi), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dcat), ldc, coff,
                                                                 N, Do, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(dx), Di,
                                                                 Hi, Wi, C);
   B2_CHECK_CUDA(cudaGetLastError());

@@ -56,15 +56,17 @@ class _ConvLayer(object):
         self._key = None
         self.wf = self.wd = None
 
-    def packs(self):
+    def key(self):
         w = self.conv.weight
-        key = (w._version, w.data_ptr(), str(w.device))
-        if key != self._key:
-            if self.cin == 1:
-                self.wf, self.wd = None, None
-            else:
-                self.wf, self.wd = ops.pack_conv_weights(w)
-            self._key = key
+        return (w._version, w.data_ptr(), str(w.device))
+
+    def stale(self):
+        return self.cin != 1 and self.key() != self._key
+
+    def packs(self):
+        if self.stale():
+            self.wf, self.wd = ops.pack_conv_weights(self.conv.weight)
+            self._key = self.key()
         return self.wf, self.wd
 
 
@@ -167,6 +169,10 @@ class UNet3D(nn.Module):
     def _trunk_forward(self, x, save):
         """x fp32 [B,1,D,H,W] -> feature ActView [B,D,H,W,f]; fills `save` (a _Saved) when not None."""
         L = self._layers()
+        stale = [l for l in L if l.stale()]
+        if stale:   # one launch re-packs every layer whose fp32 master changed (optimiser step, load_state_dict, .to())
+            for l, (wf, wd) in zip(stale, ops.pack_conv_weights_multi([l.conv.weight for l in stale])):
+                l.wf, l.wd, l._key = wf, wd, l.key()
         B, _, D0, H0, W0 = x.shape
         dev = x.device
         G = self.num_groups

@@ -70,6 +70,19 @@ class Workspace(object):
         return buf
 
 
+_COUNTERS = {}
+
+
+def _counters(device):
+    """zero-initialised int32 tickets for the "last block done" reductions (the kernels leave them zero)"""
+    key = str(device)
+    t = _COUNTERS.get(key)
+    if t is None:
+        t = torch.zeros(2048, dtype=torch.int32, device=device)
+        _COUNTERS[key] = t
+    return t
+
+
 class ActView(object):
     """A channel window [coff, coff+C) of an NDHWC bf16 buffer [N, D, H, W, ld]."""
     __slots__ = ("buf", "N", "D", "H", "W", "C", "ld", "coff")
@@ -152,8 +165,9 @@ def relu_gn_stats(r, groups, eps, gamma, beta):
     scale_shift = torch.empty((r.N, r.C, 2), dtype=torch.float32, device=dev)
     ws = Workspace.get(lib.b2_gn_workspace_bytes(r.N, r.C), dev, "gn")
     _lib.check(lib.b2_relu_gn_stats(_p(r.buf), r.N, r.V, r.C, groups, float(eps), _p(gamma), _p(beta), _p(mean_rstd),
-                                    _p(scale_shift), _p(ws), ws.numel(), _s()), "b2_relu_gn_stats")
-    _count(2)
+                                    _p(scale_shift), _p(ws), ws.numel(), _p(_counters(dev)), _s()),
+               "b2_relu_gn_stats")
+    _count(1)
     return mean_rstd, scale_shift
 
 
@@ -176,9 +190,10 @@ def relu_gn_bwd(dy, r, groups, gamma, mean_rstd, want_param_grads=True, dgamma_o
         torch.empty(r.C, dtype=torch.float32, device=dev) if want_param_grads else None)
     ws = Workspace.get(lib.b2_relu_gn_bwd_workspace_bytes(r.N, r.C), dev, "gn")
     _lib.check(lib.b2_relu_gn_bwd(_p(dy.buf), dy.ld, dy.coff, _p(r.buf), r.N, r.V, r.C, groups, _p(gamma),
-                                  _p(mean_rstd), _p(dr.buf), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _s()),
+                                  _p(mean_rstd), _p(dr.buf), _p(dgamma), _p(dbeta), _p(ws), ws.numel(),
+                                  _p(_counters(dev)), _s()),
                "b2_relu_gn_bwd")
-    _count(3)
+    _count(2)
     return dr, dgamma, dbeta
 
 
@@ -313,6 +328,32 @@ def pack_conv_weights(w, want_dgrad=True):
     _lib.check(lib.b2_pack_conv_weights(_p(wc), _p(wf), _p(wd), cout, cin, _s()), "b2_pack_conv_weights")
     _count(1)
     return wf, wd
+
+
+def pack_conv_weights_multi(ws):
+    """ws: list of fp32 [cout, cin, 3, 3, 3] CUDA tensors -> list of (wf, wd), one kernel launch for all of them."""
+    lib = _lib.load()
+    n = len(ws)
+    if n == 0:
+        return []
+    outs, W, WF, WD, CO, CI = [], [], [], [], [], []
+    keep = []
+    for w in ws:
+        _need_cuda(w)
+        cout, cin = w.shape[0], w.shape[1]
+        wc = w.detach()
+        if not wc.is_contiguous():
+            wc = wc.contiguous()
+        keep.append(wc)
+        wf = torch.empty((27, cout, cin), dtype=BF16, device=w.device)
+        wd = torch.empty((27, cin, cout), dtype=BF16, device=w.device)
+        outs.append((wf, wd))
+        W.append(wc.data_ptr()); WF.append(wf.data_ptr()); WD.append(wd.data_ptr()); CO.append(cout); CI.append(cin)
+    vp, ia = C.c_void_p * n, C.c_int * n
+    _lib.check(lib.b2_pack_conv_weights_multi(vp(*W), vp(*WF), vp(*WD), ia(*CO), ia(*CI), n, _s()),
+               "b2_pack_conv_weights_multi")
+    _count((n + 15) // 16)
+    return outs
 
 
 def fold_vote(scores, fold_dense, n_folds, thresholds):

@@ -45,18 +45,19 @@ long long b2_conv3d_first_wgrad_workspace_bytes(int Cout);
 int b2_conv3d_first_wgrad(const float* x, const void* dy, int lddy, int dy_coff, float* dw, void* workspace,
                           long long workspace_bytes, int N, int D, int H, int W, int Cout, cudaStream_t stream);
 
-/* ---- ReLU + GroupNorm ('crg' order), r = relu(conv) is produced by the conv epilogue --------------------------- */
+/* ---- ReLU + GroupNorm ('crg' order), r = relu(conv) is produced by the conv epilogue ---------------------------
+ * counters: device int32 [N+1], zero before the first call; the kernels leave it zero ("last block done" tickets). */
 long long b2_gn_workspace_bytes(int N, int C);
 int b2_relu_gn_stats(const void* r, int N, long long V, int C, int G, float eps, const float* gamma,
                      const float* beta, float* mean_rstd, float* scale_shift, void* workspace,
-                     long long workspace_bytes, cudaStream_t stream);
+                     long long workspace_bytes, int* counters, cudaStream_t stream);
 /* y = GN(r); pooled != NULL additionally writes MaxPool3d(2,2,0)(y) in the same pass (encoder -> next level)      */
 int b2_relu_gn_apply(const void* r, int N, int D, int H, int W, int C, const float* scale_shift, void* y, int ldy,
                      int y_coff, void* pooled, cudaStream_t stream);
 long long b2_relu_gn_bwd_workspace_bytes(int N, int C);
 int b2_relu_gn_bwd(const void* dy, int lddy, int dy_coff, const void* r, int N, long long V, int C, int G,
                    const float* gamma, const float* mean_rstd, void* dr, float* dgamma, float* dbeta,
-                   void* workspace, long long workspace_bytes, cudaStream_t stream);
+                   void* workspace, long long workspace_bytes, int* counters, cudaStream_t stream);
 
 /* ---- MaxPool3d(2) backward (+ skip gradient add), trilinear upsample + concat and its backward ------------------ */
 int b2_maxpool3d_bwd_add(const void* y, int ldy, int y_coff, const void* dskip, int ldd, int d_coff,
@@ -87,6 +88,9 @@ int b2_head_dense_bwd(const float* g, const void* x, int N, long long V, const f
 int b2_sgd_step(float* const* params, const float* const* grads, float* const* moms, const long long* numels,
                 int count, float lr, float momentum, float grad_scale, cudaStream_t stream);
 int b2_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, cudaStream_t stream);
+/* all layers whose master weights changed, one launch; the five arrays are HOST arrays of `count` entries          */
+int b2_pack_conv_weights_multi(const float* const* w, void* const* wf, void* const* wd, const int* cout,
+                               const int* cin, int count, cudaStream_t stream);
 
 /* ---- post-inference integer pass: cutting(yscores, vert_notcut, bck2, threshold) (pattern_class.py:230) ---------
  * fold: dense ids in [0,F); thresholds: device int32 [T]; out: int32 [T][n].                                      */
