@@ -16,6 +16,7 @@
 // the even warp of the pair loads the A box, the odd warp the weight tile.
 #include "common.h"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace b2 {
 
@@ -255,6 +256,10 @@ static void choose_box(int W, int H, int D, int& bw, int& bh, int& bd) {
     }
 }
 
+bool slab_applicable(int N, int D, int H, int W, int Cin, int Cout, int y_is_fp32);
+int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff, int N, int D,
+                int H, int W, int Cin, int Cout, int relu, cudaStream_t stream);
+
 int make_act_tmap(CUtensorMap* map, const void* base, int N, int D, int H, int W, int C, int ld, int coff,
                   int box_c, int bw, int bh, int bd) {
   const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
@@ -281,6 +286,11 @@ extern "C" int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* w
   B2_REQUIRE(ldx % 8 == 0 && x_coff % 8 == 0 && ldy % 8 == 0 && y_coff % 8 == 0,
              "b2_conv3d_igemm: channel strides/offsets must be multiples of 8");
   B2_REQUIRE(x_coff + Cin <= ldx && y_coff + Cout <= ldy, "b2_conv3d_igemm: channel window out of range");
+
+  // narrow-N layers at (almost) tile-aligned resolutions: shared-memory tap-reuse kernel (conv_slab.cu)
+  static const bool no_slab = getenv("B2_NO_SLAB") != nullptr;
+  if (!no_slab && slab_applicable(N, D, H, W, Cin, Cout, y_is_fp32))
+    return launch_slab(x, ldx, x_coff, wpack, y, ldy, y_coff, N, D, H, W, Cin, Cout, relu, stream);
 
   IgemmParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;

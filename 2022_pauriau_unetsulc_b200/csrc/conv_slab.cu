@@ -1,0 +1,298 @@
+// 3x3x3 conv for the narrow-N layers (Cout = 32 or 64: 55 % of the network's FLOPs) with shared-memory tap reuse.
+//
+// Why: with N = 64 the plain implicit GEMM (conv_igemm.cu) needs a fresh 16 KB A tile + 8 KB weight tile per
+// 128 tensor-cycles = 192 B/clk/SM, three times what L2 -> SM delivers (~64 B/clk/SM measured): it saturates at ~35 %
+// of the tensor peak.  Here one CTA owns a 32(w) x 4(h) x 4(d) output tile = 4 accumulators of 128 voxels, and for a
+// fixed w-tap and channel chunk streams the 6 input planes (d0-1 .. d0+4), each ONE TMA box of (4+2) h-lines x 32 w
+// = 192 rows.  A plane in shared memory feeds the 3 h-taps by 1024-byte-aligned descriptor offsets (row offset
+// dh*32) and the up-to-3 d-taps by accumulating into different output planes; the 9 weight tiles of that w-tap stay
+// resident (double-buffered) while the planes stream.  Traffic: (6*24 KB + 72 KB) per 144 MMAs = 47 B/clk/SM.
+//
+// Warp roles: 0 MMA issuer (+TMEM), 1-3 plane producers (ring stage s owned by producer s mod 3), 4-6 weight
+// producers (one d-tap row each), 7 idle, 8-11 epilogue.  Whole-warp uniform loops, elected-lane issue.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b2 {
+
+int make_act_tmap(CUtensorMap* map, const void* base, int N, int D, int H, int W, int C, int ld, int coff,
+                  int box_c, int bw, int bh, int bd);
+
+struct SlabParams {
+  int N, D, H, W;
+  int Cin, Cout;       // Cout == BN (32 or 64)
+  int n_chunks;
+  int tiles_w, tiles_h, tiles_d;
+  int stages;          // plane ring depth (multiple of 3)
+  int relu;
+  int ldy, y_coff;
+  __nv_bfloat16* y;
+  long long total_tiles;
+};
+
+static constexpr int kSlabThreads = 32 * 12;
+static constexpr int kTW = 32, kTH = 4, kTD = 4;
+static constexpr int kPlaneRows = kTW * (kTH + 2);   // 192
+
+template <int KC>
+__global__ void __launch_bounds__(kSlabThreads, 1)
+conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                   const SlabParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kRowBytes = KC * 2;
+  constexpr int kPlaneBytes = kPlaneRows * kRowBytes;
+  const int BN = p.Cout;
+  const int tap_bytes = BN * kRowBytes;          // one weight tile
+  const int b_bytes = 9 * tap_bytes;             // the 9 (dd, dh) taps of one w-tap
+  uint8_t* smem_b = smem;                        // 2 buffers
+  uint8_t* smem_p = smem + 2 * (size_t)b_bytes;  // plane ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + (size_t)p.stages * kPlaneBytes);
+  uint64_t* p_full = bars;
+  uint64_t* p_empty = bars + p.stages;
+  uint64_t* b_full = bars + 2 * p.stages;
+  uint64_t* b_empty = b_full + 2;
+  uint64_t* tmem_full = b_empty + 2;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&p_full[s], 1);
+      mbar_init(&p_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&b_full[s], 3);
+      mbar_init(&b_empty[s], 1);
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_n = p.tiles_w * p.tiles_h * p.tiles_d;
+
+  if (warp >= 1 && warp <= 3) {
+    // ---------------------------------------------------------------- plane producers
+    const int me = warp - 1;
+    uint32_t gp = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n = (int)(tile / tiles_per_n);
+      int t = (int)(tile % tiles_per_n);
+      const int w0 = (t % p.tiles_w) * kTW; t /= p.tiles_w;
+      const int h0 = (t % p.tiles_h) * kTH;
+      const int d0 = (t / p.tiles_h) * kTD;
+      for (int ch = 0; ch < p.n_chunks; ++ch)
+        for (int dw = -1; dw <= 1; ++dw)
+          for (int pl = 0; pl < kTD + 2; ++pl, ++gp) {
+            const int stage = (int)(gp % (uint32_t)p.stages);
+            if (stage % 3 != me) continue;
+            const uint32_t phase = (gp / (uint32_t)p.stages) & 1u;
+            mbar_wait(&p_empty[stage], phase ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&p_full[stage], (uint32_t)kPlaneBytes);
+              tma_load_5d(smem_p + (size_t)stage * kPlaneBytes, &tmap_a, &p_full[stage], ch * KC, w0 + dw, h0 - 1,
+                          d0 - 1 + pl, n);
+            }
+            __syncwarp();
+          }
+    }
+  } else if (warp >= 4 && warp <= 6) {
+    // ---------------------------------------------------------------- weight producers (one d-tap row each)
+    const int ddi = warp - 4;   // dd + 1
+    uint32_t gb = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x)
+      for (int ch = 0; ch < p.n_chunks; ++ch)
+        for (int dwi = 0; dwi < 3; ++dwi, ++gb) {
+          const int bs = (int)(gb & 1u);
+          const uint32_t phase = (gb >> 1) & 1u;
+          mbar_wait(&b_empty[bs], phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&b_full[bs], (uint32_t)(3 * tap_bytes));
+            for (int dhi = 0; dhi < 3; ++dhi) {
+              const int tap = ddi * 9 + dhi * 3 + dwi;   // PyTorch tap order (kd, kh, kw)
+              tma_load_2d(smem_b + (size_t)bs * b_bytes + (size_t)(ddi * 3 + dhi) * tap_bytes, &tmap_b, &b_full[bs],
+                          ch * KC, tap * p.Cout);
+            }
+          }
+          __syncwarp();
+        }
+  } else if (warp == 0) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)BN, 0, 0);
+    constexpr uint32_t kLayout = (KC == 64) ? SWZ_128B : SWZ_64B;
+    constexpr uint32_t kSbo = 8u * kRowBytes;
+    const uint64_t desc_hi = make_smem_desc(0, 16, kSbo, kLayout);
+    const uint32_t p0 = smem_u32(smem_p) >> 4, b0 = smem_u32(smem_b) >> 4;
+    constexpr uint32_t kPlaneStep = kPlaneBytes >> 4;
+    constexpr uint32_t kDhStep = (kTW * kRowBytes) >> 4;   // +32 rows
+    const uint32_t tap_step = (uint32_t)tap_bytes >> 4, bbuf_step = (uint32_t)b_bytes >> 4;
+    int ps = 0;
+    uint32_t pphase = 0, gb = 0, it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u;
+      mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + acc * 256u;
+      uint32_t started = 0;   // bit o: accumulator of output plane o has received its first MMA
+      const int n_groups = p.n_chunks * 3;
+      for (int g = 0; g < n_groups; ++g, ++gb) {
+        const int bs = (int)(gb & 1u);
+        mbar_wait(&b_full[bs], (gb >> 1) & 1u);
+        for (int pl = 0; pl < kTD + 2; ++pl) {
+          mbar_wait(&p_full[ps], pphase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a_plane = desc_hi | (uint64_t)(p0 + (uint32_t)ps * kPlaneStep);
+            const uint64_t b_buf = desc_hi | (uint64_t)(b0 + (uint32_t)bs * bbuf_step);
+#pragma unroll
+            for (int ddi = 0; ddi < 3; ++ddi) {
+              const int o = pl - ddi;               // output plane: input plane pl = o + dd + 1
+              if (o < 0 || o >= kTD) continue;
+#pragma unroll
+              for (int dhi = 0; dhi < 3; ++dhi) {
+                const uint64_t adesc = a_plane + (uint64_t)(dhi * kDhStep);
+                const uint64_t bdesc = b_buf + (uint64_t)((ddi * 3 + dhi) * tap_step);
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) {
+                  umma_bf16(d_base + (uint32_t)(o * BN), adesc + 2 * k, bdesc + 2 * k, idesc,
+                            ((started >> o) & 1u) | (uint32_t)((dhi | k) != 0));
+                }
+              }
+            }
+            umma_commit(&p_empty[ps]);
+            if (pl == kTD + 1) {
+              umma_commit(&b_empty[bs]);
+              if (g == n_groups - 1) umma_commit(&tmem_full[acc]);
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int ddi = 0; ddi < 3; ++ddi) {   // warp-uniform bookkeeping of which accumulators have been started
+            const int o = pl - ddi;
+            if (o >= 0 && o < kTD) started |= 1u << o;
+          }
+          if (++ps == p.stages) { ps = 0; pphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;           // lane quarter == h-line within the tile
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int n = (int)(tile / tiles_per_n);
+      int t = (int)(tile % tiles_per_n);
+      const int w0 = (t % p.tiles_w) * kTW; t /= p.tiles_w;
+      const int h0 = (t % p.tiles_h) * kTH;
+      const int d0 = (t / p.tiles_h) * kTD;
+      const uint32_t acc = it & 1u;
+      const int w = w0 + lane, h = h0 + q;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
+      tc_fence_after();
+      for (int o = 0; o < kTD; ++o) {
+        const int d = d0 + o;
+        const bool valid = (w < p.W) && (h < p.H) && (d < p.D);
+        const size_t vox = (((size_t)n * p.D + d) * p.H + h) * p.W + w;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(o * BN);
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(p.y + vox * p.ldy + p.y_coff + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                f[e] = __uint_as_float(v[8 * j + e]);
+                if (p.relu) f[e] = fmaxf(f[e], 0.f);
+              }
+              uint4 ov;
+              ov.x = pack_bf16x2(f[0], f[1]);
+              ov.y = pack_bf16x2(f[2], f[3]);
+              ov.z = pack_bf16x2(f[4], f[5]);
+              ov.w = pack_bf16x2(f[6], f[7]);
+              dst[j] = ov;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// host: is the slab kernel applicable / worthwhile for this layer?
+bool slab_applicable(int N, int D, int H, int W, int Cin, int Cout, int y_is_fp32) {
+  if (y_is_fp32) return false;
+  if (!(Cout == 32 || Cout == 64)) return false;
+  if (!(Cin % 64 == 0 || Cin == 32)) return false;
+  const long long padded = (long long)ceil_div(W, kTW) * kTW * ceil_div(H, kTH) * kTH * ceil_div(D, kTD) * kTD;
+  if (padded * 100 > (long long)W * H * D * 112) return false;   // <= 12 % tile-quantisation waste
+  return true;
+}
+
+int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff, int N, int D,
+                int H, int W, int Cin, int Cout, int relu, cudaStream_t stream) {
+  SlabParams p;
+  p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  const int KC = (Cin % 64 == 0) ? 64 : 32;
+  p.n_chunks = Cin / KC;
+  p.tiles_w = ceil_div(W, kTW);
+  p.tiles_h = ceil_div(H, kTH);
+  p.tiles_d = ceil_div(D, kTD);
+  p.relu = relu;
+  p.ldy = ldy; p.y_coff = y_coff;
+  p.y = reinterpret_cast<__nv_bfloat16*>(y);
+  p.total_tiles = (long long)N * p.tiles_w * p.tiles_h * p.tiles_d;
+  const int plane_bytes = kPlaneRows * KC * 2;
+  const int b_bytes = 9 * Cout * KC * 2;
+  const int budget = 227 * 1024 - 1024 - 512;
+  p.stages = (budget - 2 * b_bytes) / plane_bytes;
+  p.stages = (p.stages / 3) * 3;
+  if (p.stages > 9) p.stages = 9;
+  B2_REQUIRE(p.stages >= 3, "conv3d_slab: tile does not fit shared memory");
+  CUtensorMap ta, tb;
+  int rc = make_act_tmap(&ta, x, N, D, H, W, Cin, ldx, x_coff, KC, kTW, kTH + 2, 1);
+  if (rc) return rc;
+  {
+    const uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)27 * Cout};
+    const uint64_t strides[1] = {(uint64_t)Cin * 2};
+    const uint32_t box[2] = {(uint32_t)KC, (uint32_t)Cout};
+    rc = encode_tmap_bf16(&tb, wpack, 2, dims, strides, box, KC * 2);
+    if (rc) return rc;
+  }
+  const size_t smem_bytes = 2 * (size_t)b_bytes + (size_t)p.stages * plane_bytes + 1024 + 512;
+  long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  if (KC == 64) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    conv3d_slab_kernel<64><<<(unsigned)grid, kSlabThreads, smem_bytes, stream>>>(ta, tb, p);
+  } else {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    conv3d_slab_kernel<32><<<(unsigned)grid, kSlabThreads, smem_bytes, stream>>>(ta, tb, p);
+  }
+  B2_CHECK_CUDA(cudaGetLastError());
+  return B2_OK;
+}
+
+}  // namespace b2

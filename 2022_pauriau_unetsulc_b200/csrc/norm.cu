@@ -134,32 +134,41 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ r, long long V, int C, float* 
 }
 
 // ------------------------------------------------------------------------------------------------- forward apply
+// grid = (blocks, N).  A thread keeps one channel octet (256 % C8 == 0) and walks voxels with pointer increments only
+// (no 64-bit divisions in the loop), two independent 16-byte loads in flight.
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ r, long long V, int C, const float* __restrict__ scale_shift,
-                __nv_bfloat16* __restrict__ y, int ldy, int y_coff, int N) {
-  const int C8 = C >> 3;  // C8 divides 256, so a thread keeps the same channel octet across the grid-stride loop
-  const long long total = (long long)N * V * C8;
-  const int oct = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % C8);
-  int cur_n = -1;
+                __nv_bfloat16* __restrict__ y, int ldy, int y_coff) {
+  const int C8 = C >> 3;
+  const int n = blockIdx.y;
+  const int oct = threadIdx.x % C8;
+  const int vpb = 256 / C8;                                   // voxels per block per sweep
+  const long long vstride = (long long)gridDim.x * vpb;
+  long long v = (long long)blockIdx.x * vpb + threadIdx.x / C8;
   float sc[8], sh[8];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long nv = i / C8;
-    const int n = (int)(nv / V);
-    if (n != cur_n) {
-      cur_n = n;
-      const float4* ss = reinterpret_cast<const float4*>(scale_shift + ((size_t)n * C + oct * 8) * 2);
+  const float4* ss = reinterpret_cast<const float4*>(scale_shift + ((size_t)n * C + oct * 8) * 2);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 t = __ldg(ss + k);
-        sc[2 * k] = t.x; sh[2 * k] = t.y; sc[2 * k + 1] = t.z; sh[2 * k + 1] = t.w;
-      }
-    }
-    const f8 x = unpack8(ldg16(r + nv * C + oct * 8));
+  for (int k = 0; k < 4; ++k) {
+    const float4 t = __ldg(ss + k);
+    sc[2 * k] = t.x; sh[2 * k] = t.y; sc[2 * k + 1] = t.z; sh[2 * k + 1] = t.w;
+  }
+  const __nv_bfloat16* rp = r + ((size_t)n * V) * C + oct * 8;
+  __nv_bfloat16* yp = y + ((size_t)n * V) * ldy + y_coff + oct * 8;
+  for (; v + vstride < V; v += 2 * vstride) {
+    const uint4 u0 = ldg16(rp + v * C), u1 = ldg16(rp + (v + vstride) * C);
+    const f8 x0 = unpack8(u0), x1 = unpack8(u1);
+    f8 o0, o1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { o0.v[k] = fmaf(x0.v[k], sc[k], sh[k]); o1.v[k] = fmaf(x1.v[k], sc[k], sh[k]); }
+    stg16(yp + v * ldy, pack8(o0));
+    stg16(yp + (v + vstride) * ldy, pack8(o1));
+  }
+  for (; v < V; v += vstride) {
+    const f8 x = unpack8(ldg16(rp + v * C));
     f8 o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.v[k] = fmaf(x.v[k], sc[k], sh[k]);
-    stg16(y + nv * ldy + y_coff + oct * 8, pack8(o));
+    stg16(yp + v * ldy, pack8(o));
   }
 }
 
@@ -321,37 +330,53 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
 
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff, const __nv_bfloat16* __restrict__ r,
-                    long long V, int C, int N, const float* __restrict__ mean_rstd, const float* __restrict__ coef,
+                    long long V, int C, const float* __restrict__ mean_rstd, const float* __restrict__ coef,
                     __nv_bfloat16* __restrict__ dr) {
   const int C8 = C >> 3;
-  const long long total = (long long)N * V * C8;
-  const int oct = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % C8);
-  int cur_n = -1;
-  float mu[8], rs[8], ca[8], cb[8], cc[8];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long nv = i / C8;
-    const int n = (int)(nv / V);
-    if (n != cur_n) {
-      cur_n = n;
+  const int n = blockIdx.y;
+  const int oct = threadIdx.x % C8;
+  const int vpb = 256 / C8;
+  const long long vstride = (long long)gridDim.x * vpb;
+  long long v = (long long)blockIdx.x * vpb + threadIdx.x / C8;
+  // dr = relu'(r) * (ca*dy + cb*xhat + cc) with xhat = (r - mu)*rs  ==  relu'(r) * (ca*dy + kb*r + kc)
+  float ca[8], kb[8], kc[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int c = oct * 8 + k;
-        const float2 mr = __ldg(reinterpret_cast<const float2*>(mean_rstd + ((size_t)n * C + c) * 2));
-        const float4 cf = __ldg(reinterpret_cast<const float4*>(coef + ((size_t)n * C + c) * 4));
-        mu[k] = mr.x; rs[k] = mr.y; ca[k] = cf.x; cb[k] = cf.y; cc[k] = cf.z;
-      }
+  for (int k = 0; k < 8; ++k) {
+    const int c = oct * 8 + k;
+    const float2 mr = __ldg(reinterpret_cast<const float2*>(mean_rstd + ((size_t)n * C + c) * 2));
+    const float4 cf = __ldg(reinterpret_cast<const float4*>(coef + ((size_t)n * C + c) * 4));
+    ca[k] = cf.x;
+    kb[k] = cf.y * mr.y;
+    kc[k] = cf.z - cf.y * mr.y * mr.x;
+  }
+  const __nv_bfloat16* rp = r + ((size_t)n * V) * C + oct * 8;
+  const __nv_bfloat16* gp = dy + ((size_t)n * V) * lddy + dy_coff + oct * 8;
+  __nv_bfloat16* op = dr + ((size_t)n * V) * C + oct * 8;
+  for (; v + vstride < V; v += 2 * vstride) {
+    const uint4 ux0 = ldg16(rp + v * C), ug0 = ldg16(gp + v * lddy);
+    const uint4 ux1 = ldg16(rp + (v + vstride) * C), ug1 = ldg16(gp + (v + vstride) * lddy);
+    const f8 x0 = unpack8(ux0), g0 = unpack8(ug0), x1 = unpack8(ux1), g1 = unpack8(ug1);
+    f8 o0, o1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float d0 = fmaf(ca[k], g0.v[k], fmaf(kb[k], x0.v[k], kc[k]));
+      const float d1 = fmaf(ca[k], g1.v[k], fmaf(kb[k], x1.v[k], kc[k]));
+      o0.v[k] = x0.v[k] > 0.f ? d0 : 0.f;
+      o1.v[k] = x1.v[k] > 0.f ? d1 : 0.f;
     }
-    const f8 x = unpack8(ldg16(r + nv * C + oct * 8));
-    const f8 g = unpack8(ldg16(dy + nv * lddy + dy_coff + oct * 8));
+    stg16(op + v * C, pack8(o0));
+    stg16(op + (v + vstride) * C, pack8(o1));
+  }
+  for (; v < V; v += vstride) {
+    const f8 x = unpack8(ldg16(rp + v * C));
+    const f8 g = unpack8(ldg16(gp + v * lddy));
     f8 o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float xh = (x.v[k] - mu[k]) * rs[k];
-      const float d = fmaf(ca[k], g.v[k], fmaf(cb[k], xh, cc[k]));
+      const float d = fmaf(ca[k], g.v[k], fmaf(kb[k], x.v[k], kc[k]));
       o.v[k] = x.v[k] > 0.f ? d : 0.f;
     }
-    stg16(dr + nv * C + oct * 8, pack8(o));
+    stg16(op + v * C, pack8(o));
   }
 }
 
@@ -420,9 +445,9 @@ extern "C" int b2_relu_gn_apply(const void* r, int N, int D, int H, int W, int C
         reinterpret_cast<const __nv_bfloat16*>(r), N, D, H, W, C, scale_shift, reinterpret_cast<__nv_bfloat16*>(y), ldy,
         y_coff, reinterpret_cast<__nv_bfloat16*>(pooled));
   } else {
-    const long long total = (long long)N * V * (C / 8);
-    gn_apply_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(r), V, C, scale_shift,
-                                                          reinterpret_cast<__nv_bfloat16*>(y), ldy, y_coff, N);
+    B2_REQUIRE(256 % (C / 8) == 0, "b2_relu_gn_apply: C=%d unsupported", C);
+    gn_apply_kernel<<<dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(r), V, C, scale_shift, reinterpret_cast<__nv_bfloat16*>(y), ldy, y_coff);
   }
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
@@ -448,10 +473,9 @@ extern "C" int b2_relu_gn_bwd(const void* dy, int lddy, int dy_coff, const void*
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
       mean_rstd, partial, counters, N, G, gamma, coef, dgb_n, dgamma, dbeta);
   B2_CHECK_CUDA(cudaGetLastError());
-  const long long total = (long long)N * V * (C / 8);
-  gn_bwd_apply_kernel<<<ew_blocks(total), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff,
-                                                            reinterpret_cast<const __nv_bfloat16*>(r), V, C, N,
-                                                            mean_rstd, coef, reinterpret_cast<__nv_bfloat16*>(dr));
+  gn_bwd_apply_kernel<<<dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
+      mean_rstd, coef, reinterpret_cast<__nv_bfloat16*>(dr));
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }

@@ -79,6 +79,45 @@ def test_conv_fprop(shape, fp32_out):
         assert err < 2e-3, "bf16-out conv rel-L2 %.3e" % err
 
 
+SLAB_SHAPES = [
+    # shapes the shared-memory tap-reuse kernel (conv_slab.cu) takes: Cout in {32, 64}, tile-aligned volumes
+    (1, 64, 64, 8, 12, 64),
+    (1, 32, 64, 8, 12, 64),      # KC = 32 planes
+    (1, 192, 64, 8, 8, 32),      # 3 channel chunks
+    (1, 64, 32, 8, 12, 64),      # N = 32 (dgrad of encoders.0.conv2)
+    (2, 64, 64, 8, 12, 60),      # ragged W edge (60 -> 64), batch 2
+    (1, 64, 64, 4, 4, 32),       # a single tile: every plane touches the volume border
+]
+
+
+@pytest.mark.parametrize("shape", SLAB_SHAPES)
+def test_conv_slab_kernel(shape):
+    ops = _ops()
+    N, Cin, Cout, D, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = bf16_round(torch.randn(N, Cin, D, H, W, device="cuda", generator=g))
+    w = bf16_round(torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=g) * (1.0 / (27 * Cin) ** 0.5))
+    wf, wd = ops.pack_conv_weights(w)
+    wide = torch.full((N, D, H, W, Cout + 16), 3.0, device="cuda", dtype=torch.bfloat16)
+    yv = ops.ActView(wide, N, D, H, W, Cout, ld=Cout + 16, coff=8)
+    ops.conv3d_igemm(ops.ActView(to_ndhwc(x), N, D, H, W, Cin), wf, yv, Cin, Cout, relu=True)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv3d(x, w, padding=1))
+    err = rel_l2(from_view(yv), ref)
+    assert err < 2e-3, "slab fprop rel-L2 %.3e" % err
+    assert bool((wide[..., :8] == 3.0).all()) and bool((wide[..., Cout + 8:] == 3.0).all())
+    # dgrad through the same kernel (roles of Cin / Cout swapped) when the output width allows it
+    if Cin in (32, 64):
+        dy = bf16_round(torch.randn(N, Cout, D, H, W, device="cuda", generator=g))
+        xq = torch.zeros(N, Cin, D, H, W, device="cuda", requires_grad=True)
+        F.conv3d(xq, w, padding=1).backward(dy)
+        dx = ops.ActView.alloc(N, D, H, W, Cin, "cuda", zero=True)
+        ops.conv3d_igemm(ops.ActView(to_ndhwc(dy), N, D, H, W, Cout), wd, dx, Cout, Cin, relu=False)
+        torch.cuda.synchronize()
+        err = rel_l2(from_view(dx), xq.grad)
+        assert err < 2e-3, "slab dgrad rel-L2 %.3e" % err
+
+
 def test_conv_fprop_channel_windows():
     """input read from / output written into channel windows of wider buffers (concat buffers)."""
     ops = _ops()
