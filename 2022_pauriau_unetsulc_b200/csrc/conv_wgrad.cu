@@ -251,6 +251,31 @@ wgrad_reduce_simple_kernel(const float* __restrict__ ws, float* __restrict__ dw,
   }
 }
 
+// roles swapped (see b2_conv3d_wgrad): ws[s][tap'][co][ci] with tap' = 26 - tap  ->  dW[co][ci][tap]
+__global__ void __launch_bounds__(256)
+wgrad_reduce_swapped_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int Cin, int Cout) {
+  const long long total = 27LL * Cin * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    int s = 0;
+    for (; s + 3 < splits; s += 4)
+      acc += (ws[(long long)s * total + i] + ws[(long long)(s + 1) * total + i]) +
+             (ws[(long long)(s + 2) * total + i] + ws[(long long)(s + 3) * total + i]);
+    for (; s < splits; ++s) acc += ws[(long long)s * total + i];
+    const int ci = (int)(i % Cin);
+    const long long r = i / Cin;
+    const int co = (int)(r % Cout);
+    const int tapf = (int)(r / Cout);
+    dw[((long long)co * Cin + ci) * 27 + (26 - tapf)] = acc;
+  }
+}
+
+// Which operand is shifted per tap?  The shifted operand is re-loaded for every tap, the other one once per
+// 128-voxel K-step, so shifting the NARROW one and keeping the wide one as the N dimension halves the TMA traffic
+// per tensor-cycle when Cout = 64 and Cin >= 128 (decoders.2.conv1: 133 -> 73 B/clk/SM).
+static bool wgrad_swap_roles(int Cin, int Cout) { return Cout == 64 && Cin >= 128 && Cin % 64 == 0; }
+
 static void choose_box_w(int W, int H, int D, int& bw, int& bh, int& bd) {
   long long best = -1;
   for (int lw = 0; lw <= 7; ++lw)
@@ -275,7 +300,7 @@ static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int C
   p.total_slots = 27 * p.n_cchunks;
   p.SPG = 128 / p.SWC;
   p.G = ceil_div(p.total_slots, p.SPG);
-  p.BN = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  p.BN = (Cout % 256 == 0) ? 256 : (Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : 64));
   p.n_cout_tiles = Cout / p.BN;
   const int P = 512 / p.BN;
   p.n_gchunks = ceil_div(p.G, P);
@@ -306,7 +331,8 @@ using namespace b2;
 extern "C" long long b2_conv3d_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout) {
   if (Cin % 32 != 0 || Cout % 64 != 0 || N <= 0 || D <= 0 || H <= 0 || W <= 0) return -1;
   WgradParams p;
-  if (plan_wgrad(p, N, D, H, W, Cin, Cout) != 0) return -1;
+  const bool swap = wgrad_swap_roles(Cin, Cout);
+  if (plan_wgrad(p, N, D, H, W, swap ? Cout : Cin, swap ? Cin : Cout) != 0) return -1;
   return (long long)p.splits * 27 * Cin * Cout * (long long)sizeof(float);
 }
 
@@ -320,15 +346,22 @@ extern "C" int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* d
   B2_REQUIRE(ldx % 8 == 0 && x_coff % 8 == 0 && ldy % 8 == 0 && y_coff % 8 == 0,
              "b2_conv3d_wgrad: channel strides/offsets must be multiples of 8");
   WgradParams p;
-  B2_REQUIRE(plan_wgrad(p, N, D, H, W, Cin, Cout) == 0, "b2_conv3d_wgrad: tile does not fit shared memory");
+  const bool swap = wgrad_swap_roles(Cin, Cout);
+  // kernel view: "shifted" operand (slots along M) and "fixed" operand (N); swapped roles shift dY by the flipped tap
+  const void* sh_ptr = swap ? dy : x;
+  const void* fx_ptr = swap ? x : dy;
+  const int sh_c = swap ? Cout : Cin, fx_c = swap ? Cin : Cout;
+  const int sh_ld = swap ? ldy : ldx, sh_off = swap ? y_coff : x_coff;
+  const int fx_ld = swap ? ldx : ldy, fx_off = swap ? x_coff : y_coff;
+  B2_REQUIRE(plan_wgrad(p, N, D, H, W, sh_c, fx_c) == 0, "b2_conv3d_wgrad: tile does not fit shared memory");
   const long long need = (long long)p.splits * 27 * Cin * Cout * (long long)sizeof(float);
   B2_REQUIRE(workspace_bytes >= need, "b2_conv3d_wgrad: workspace %lld < %lld bytes", workspace_bytes, need);
   p.ws = reinterpret_cast<float*>(workspace);
 
   CUtensorMap tx, ty;
-  int rc = make_act_tmap(&tx, x, N, D, H, W, Cin, ldx, x_coff, p.SWC, p.bw, p.bh, p.bd);
+  int rc = make_act_tmap(&tx, sh_ptr, N, D, H, W, sh_c, sh_ld, sh_off, p.SWC, p.bw, p.bh, p.bd);
   if (rc) return rc;
-  rc = make_act_tmap(&ty, dy, N, D, H, W, Cout, ldy, y_coff, 64, p.bw, p.bh, p.bd);
+  rc = make_act_tmap(&ty, fx_ptr, N, D, H, W, fx_c, fx_ld, fx_off, 64, p.bw, p.bh, p.bd);
   if (rc) return rc;
 
   const size_t smem_bytes = 2 * (size_t)p.b_bytes + (size_t)p.stages_a * p.a_bytes + 1024 + 512;
@@ -336,7 +369,10 @@ extern "C" int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* d
   dim3 grid((unsigned)(p.n_gchunks * p.n_cout_tiles), (unsigned)p.splits);
   conv3d_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tx, ty, p);
   B2_CHECK_CUDA(cudaGetLastError());
-  if ((Cout / 32) * (Cin / 8) >= 2 * num_sms()) {
+  if (swap) {
+    const long long total = 27LL * Cin * Cout;
+    wgrad_reduce_swapped_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p.ws, dw, p.splits, Cin, Cout);
+  } else if ((Cout / 32) * (Cin / 8) >= 2 * num_sms()) {
     wgrad_reduce_kernel<<<dim3(Cout / 32, Cin / 8), 256, 0, stream>>>(p.ws, dw, p.splits, Cin, Cout);
   } else {
     const long long total = 27LL * Cin * Cout;
