@@ -114,12 +114,17 @@ conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
       }
     }
   }
+  // deterministic block reduction: warps add their registers one after another (no float atomics)
+  for (int w = 0; w < warps_per_block; ++w) {
+    if ((int)(threadIdx.x >> 5) == w) {
 #pragma unroll
-  for (int tap = 0; tap < 27; ++tap) {
-    if (has0) atomicAdd(&red[tap][lane], acc0[tap]);
-    if (has1) atomicAdd(&red[tap][lane + 32], acc1[tap]);
+      for (int tap = 0; tap < 27; ++tap) {
+        if (has0) red[tap][lane] += acc0[tap];
+        if (has1) red[tap][lane + 32] += acc1[tap];
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (int i = threadIdx.x; i < 27 * Cout; i += blockDim.x)
     partial[(size_t)blockIdx.x * 27 * Cout + i] = red[i / Cout][i % Cout];
 }

@@ -33,6 +33,9 @@ struct IgemmParams {
   int ldy, y_coff;
   __nv_bfloat16* y;
   float* y32;          // optional fp32 output (same indexing, ld = ldy) instead of bf16
+  float* stat_partial; // optional [gridDim.x][Cout][2]: per-CTA sum / sum-of-squares of the
+                       // bf16-rounded outputs per channel (GroupNorm statistics fused into the epilogue; N == 1,
+                       // one N tile only)
   long long total_tiles;
 };
 
@@ -172,6 +175,9 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int lw = row % p.bw;
     const int lh = (row / p.bw) % p.bh;
     const int ld = row / (p.bw * p.bh);
+    float st_s[8], st_q[8];   // lane L: running sums of channel chunk*32 + L over this warp's rows, all tiles
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int n, d0, h0, w0, n0;
@@ -184,10 +190,28 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride;
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+#pragma unroll
+      for (int chunk = 0; chunk < 8; ++chunk) {
+        const int c0 = chunk * 32;
+        if (c0 >= p.BN) break;
         uint32_t v[32];
         tmem_ld32(t_addr + c0, v);
         tmem_ld_wait();
+        if (p.stat_partial != nullptr) {   // warp-uniform branch
+          float xs[32], xq[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float f = __uint_as_float(v[e]);
+            if (p.relu) f = fmaxf(f, 0.f);
+            f = valid ? __bfloat162float(__float2bfloat16_rn(f)) : 0.f;   // statistics of what is stored
+            xs[e] = f;
+            xq[e] = f * f;
+          }
+          warp_column_sums(xs, lane);
+          warp_column_sums(xq, lane);
+          st_s[chunk] += xs[0];
+          st_q[chunk] += xq[0];
+        }
         if (valid) {
           if (p.y32 != nullptr) {
             float4* dst = reinterpret_cast<float4*>(p.y32 + vox * p.ldy + p.y_coff + n0 + c0);
@@ -226,6 +250,19 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
+    if (p.stat_partial != nullptr) {
+      // combine the four epilogue warps through the (now idle) operand ring, one partial row per CTA
+      float2* sbuf = reinterpret_cast<float2*>(smem_a);   // [4][Cout]
+#pragma unroll
+      for (int chunk = 0; chunk < 8; ++chunk)
+        if (chunk * 32 < p.BN) sbuf[q * p.Cout + chunk * 32 + lane] = make_float2(st_s[chunk], st_q[chunk]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float2* dst = reinterpret_cast<float2*>(p.stat_partial) + (size_t)blockIdx.x * p.Cout;
+      for (int c = q * 32 + lane; c < p.Cout; c += 128) {
+        const float2 a = sbuf[c], b = sbuf[p.Cout + c], cc = sbuf[2 * p.Cout + c], d = sbuf[3 * p.Cout + c];
+        dst[c] = make_float2((a.x + b.x) + (cc.x + d.x), (a.y + b.y) + (cc.y + d.y));
+      }
+    }
   }
 
   tc_fence_before();
@@ -258,7 +295,7 @@ static void choose_box(int W, int H, int D, int& bw, int& bh, int& bd) {
 
 bool slab_applicable(int N, int D, int H, int W, int Cin, int Cout, int y_is_fp32);
 int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff, int N, int D,
-                int H, int W, int Cin, int Cout, int relu, cudaStream_t stream);
+                int H, int W, int Cin, int Cout, int relu, float* stat_partial, int* n_partials, cudaStream_t stream);
 
 int make_act_tmap(CUtensorMap* map, const void* base, int N, int D, int H, int W, int C, int ld, int coff,
                   int box_c, int bw, int bh, int bd) {
@@ -276,9 +313,9 @@ int make_act_tmap(CUtensorMap* map, const void* base, int N, int D, int H, int W
 using namespace b2;
 
 // See include/unetsulc_b200.h for the contract.
-extern "C" int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff,
-                               int y_is_fp32, int N, int D, int H, int W, int Cin, int Cout, int relu,
-                               cudaStream_t stream) {
+static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff,
+                             int y_is_fp32, int N, int D, int H, int W, int Cin, int Cout, int relu,
+                             float* stat_partial, int* n_partials, cudaStream_t stream) {
   B2_REQUIRE(x && wpack && y, "b2_conv3d_igemm: null pointer");
   B2_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "b2_conv3d_igemm: bad shape %dx%dx%dx%d", N, D, H, W);
   B2_REQUIRE(Cin % 32 == 0 && Cin >= 32, "b2_conv3d_igemm: Cin=%d must be a multiple of 32", Cin);
@@ -290,7 +327,8 @@ extern "C" int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* w
   // narrow-N layers at (almost) tile-aligned resolutions: shared-memory tap-reuse kernel (conv_slab.cu)
   static const bool no_slab = getenv("B2_NO_SLAB") != nullptr;
   if (!no_slab && slab_applicable(N, D, H, W, Cin, Cout, y_is_fp32))
-    return launch_slab(x, ldx, x_coff, wpack, y, ldy, y_coff, N, D, H, W, Cin, Cout, relu, stream);
+    return launch_slab(x, ldx, x_coff, wpack, y, ldy, y_coff, N, D, H, W, Cin, Cout, relu, stat_partial, n_partials,
+                       stream);
 
   IgemmParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
@@ -321,6 +359,11 @@ extern "C" int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* w
   p.y = y_is_fp32 ? nullptr : reinterpret_cast<__nv_bfloat16*>(y);
   p.y32 = y_is_fp32 ? reinterpret_cast<float*>(y) : nullptr;
   p.total_tiles = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles_n;
+  p.stat_partial = stat_partial;
+  if (stat_partial) {
+    B2_REQUIRE(N == 1 && p.n_tiles_n == 1 && !y_is_fp32,
+               "b2_conv3d_igemm_stats: fused statistics need batch 1, Cout <= 256 and a bf16 output");
+  }
 
   CUtensorMap ta, tb;
   int rc = make_act_tmap(&ta, x, N, D, H, W, Cin, ldx, x_coff, p.KC, p.bw, p.bh, p.bd);
@@ -342,6 +385,27 @@ extern "C" int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* w
     conv3d_igemm_kernel<32><<<(unsigned)grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
   }
   B2_CHECK_CUDA(cudaGetLastError());
+  if (n_partials) *n_partials = (int)grid;
   return B2_OK;
+}
+
+// See include/unetsulc_b200.h for the contract.
+extern "C" int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff,
+                               int y_is_fp32, int N, int D, int H, int W, int Cin, int Cout, int relu,
+                               cudaStream_t stream) {
+  return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, ldy, y_coff, y_is_fp32, N, D, H, W, Cin, Cout, relu, nullptr,
+                           nullptr, stream);
+}
+
+extern "C" int b2_conv3d_stats_max_partials(void) { return num_sms(); }
+
+// fprop with the GroupNorm statistics of the stored (bf16-rounded, post-ReLU) output fused into the epilogue.
+// stat_partial: fp32 [b2_conv3d_stats_max_partials()][Cout][2]; *n_partials (HOST) receives the rows written.
+extern "C" int b2_conv3d_igemm_stats(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy,
+                                     int y_coff, int N, int D, int H, int W, int Cin, int Cout, int relu,
+                                     float* stat_partial, int* n_partials, cudaStream_t stream) {
+  B2_REQUIRE(stat_partial && n_partials, "b2_conv3d_igemm_stats: null pointer");
+  return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, ldy, y_coff, 0, N, D, H, W, Cin, Cout, relu, stat_partial,
+                           n_partials, stream);
 }
 

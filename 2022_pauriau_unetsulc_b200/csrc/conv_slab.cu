@@ -8,6 +8,13 @@
 // dh*32) and the up-to-3 d-taps by accumulating into different output planes; the 9 weight tiles of that w-tap stay
 // resident (double-buffered) while the planes stream.  Traffic: (6*24 KB + 72 KB) per 144 MMAs = 47 B/clk/SM.
 //
+// SS-mode tcgen05.mma reads A (128 x 16 bf16 = 4 KB) from shared memory for every instruction; at N = 64 that is
+// 48 cycles of smem reads for 32 cycles of math (measured: 51 cycles per MMA issue, 67 % cap).  The accumulators of
+// the four output planes are adjacent in TMEM (64 columns each), and the d-taps of an input plane feed CONSECUTIVE
+// output planes, so one instruction with N = 64 * (number of valid d-taps) <= 192 updates up to three accumulators
+// from one A read: smem-read cycles == math cycles.  All MMAs accumulate; the epilogue zeroes each accumulator
+// (tcgen05.st) after reading it.
+//
 // Warp roles: 0 MMA issuer (+TMEM), 1-3 plane producers (ring stage s owned by producer s mod 3), 4-6 weight
 // producers (one d-tap row each), 7 idle, 8-11 epilogue.  Whole-warp uniform loops, elected-lane issue.
 #include "common.h"
@@ -27,6 +34,7 @@ struct SlabParams {
   int relu;
   int ldy, y_coff;
   __nv_bfloat16* y;
+  float* stat_partial;   // optional [gridDim.x][Cout][2] (see conv_igemm.cu)
   long long total_tiles;
 };
 
@@ -121,15 +129,16 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             mbar_arrive_expect_tx(&b_full[bs], (uint32_t)(3 * tap_bytes));
             for (int dhi = 0; dhi < 3; ++dhi) {
               const int tap = ddi * 9 + dhi * 3 + dwi;   // PyTorch tap order (kd, kh, kw)
-              tma_load_2d(smem_b + (size_t)bs * b_bytes + (size_t)(ddi * 3 + dhi) * tap_bytes, &tmap_b, &b_full[bs],
-                          ch * KC, tap * p.Cout);
+              // buffer layout [dh][dd = +1, 0, -1][co]: the d-taps of one h-tap are consecutive row blocks in the
+              // order of the output planes they feed
+              tma_load_2d(smem_b + (size_t)bs * b_bytes + (size_t)(dhi * 3 + (2 - ddi)) * tap_bytes, &tmap_b,
+                          &b_full[bs], ch * KC, tap * p.Cout);
             }
           }
           __syncwarp();
         }
   } else if (warp == 0) {
     // ---------------------------------------------------------------- MMA issuer
-    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)BN, 0, 0);
     constexpr uint32_t kLayout = (KC == 64) ? SWZ_128B : SWZ_64B;
     constexpr uint32_t kSbo = 8u * kRowBytes;
     const uint64_t desc_hi = make_smem_desc(0, 16, kSbo, kLayout);
@@ -137,14 +146,16 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     constexpr uint32_t kPlaneStep = kPlaneBytes >> 4;
     constexpr uint32_t kDhStep = (kTW * kRowBytes) >> 4;   // +32 rows
     const uint32_t tap_step = (uint32_t)tap_bytes >> 4, bbuf_step = (uint32_t)b_bytes >> 4;
+    const uint32_t idesc1 = make_idesc_bf16(128, (uint32_t)BN, 0, 0);
+    const uint32_t idesc2 = make_idesc_bf16(128, (uint32_t)(2 * BN), 0, 0);
+    const uint32_t idesc3 = make_idesc_bf16(128, (uint32_t)(3 * BN), 0, 0);
     int ps = 0;
     uint32_t pphase = 0, gb = 0, it = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1u;
-      mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1);
+      mbar_wait(&tmem_empty[acc], (it >> 1) & 1u);   // the epilogue has drained AND zeroed this accumulator set
       tc_fence_after();
       const uint32_t d_base = tmem_base + acc * 256u;
-      uint32_t started = 0;   // bit o: accumulator of output plane o has received its first MMA
       const int n_groups = p.n_chunks * 3;
       for (int g = 0; g < n_groups; ++g, ++gb) {
         const int bs = (int)(gb & 1u);
@@ -152,23 +163,22 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         for (int pl = 0; pl < kTD + 2; ++pl) {
           mbar_wait(&p_full[ps], pphase);
           tc_fence_after();
+          // input plane pl feeds output planes o = pl-2 (dd=+1), pl-1 (dd=0), pl (dd=-1), clipped to [0, kTD)
+          const int o_lo = pl - 2 < 0 ? 0 : pl - 2;
+          const int o_hi = pl > kTD - 1 ? kTD - 1 : pl;
+          const int nblk = o_hi - o_lo + 1;                 // 1..3 accumulators in one instruction
+          const int b_first = o_lo - (pl - 2);              // first row block (dd order +1, 0, -1) that is used
+          const uint32_t idesc = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
           if (elect_one()) {
             const uint64_t a_plane = desc_hi | (uint64_t)(p0 + (uint32_t)ps * kPlaneStep);
-            const uint64_t b_buf = desc_hi | (uint64_t)(b0 + (uint32_t)bs * bbuf_step);
+            const uint64_t b_buf = desc_hi | (uint64_t)(b0 + (uint32_t)bs * bbuf_step + (uint32_t)b_first * tap_step);
+            const uint32_t d_tmem = d_base + (uint32_t)(o_lo * BN);
 #pragma unroll
-            for (int ddi = 0; ddi < 3; ++ddi) {
-              const int o = pl - ddi;               // output plane: input plane pl = o + dd + 1
-              if (o < 0 || o >= kTD) continue;
+            for (int dhi = 0; dhi < 3; ++dhi) {
+              const uint64_t adesc = a_plane + (uint64_t)(dhi * kDhStep);
+              const uint64_t bdesc = b_buf + (uint64_t)(dhi * 3) * tap_step;
 #pragma unroll
-              for (int dhi = 0; dhi < 3; ++dhi) {
-                const uint64_t adesc = a_plane + (uint64_t)(dhi * kDhStep);
-                const uint64_t bdesc = b_buf + (uint64_t)((ddi * 3 + dhi) * tap_step);
-#pragma unroll
-                for (int k = 0; k < KC / 16; ++k) {
-                  umma_bf16(d_base + (uint32_t)(o * BN), adesc + 2 * k, bdesc + 2 * k, idesc,
-                            ((started >> o) & 1u) | (uint32_t)((dhi | k) != 0));
-                }
-              }
+              for (int k = 0; k < KC / 16; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
             }
             umma_commit(&p_empty[ps]);
             if (pl == kTD + 1) {
@@ -177,11 +187,6 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             }
           }
           __syncwarp();
-#pragma unroll
-          for (int ddi = 0; ddi < 3; ++ddi) {   // warp-uniform bookkeeping of which accumulators have been started
-            const int o = pl - ddi;
-            if (o >= 0 && o < kTD) started |= 1u << o;
-          }
           if (++ps == p.stages) { ps = 0; pphase ^= 1; }
         }
       }
@@ -189,6 +194,13 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   } else if (warp >= 8) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;           // lane quarter == h-line within the tile
+    float st_s[2] = {0.f, 0.f}, st_q[2] = {0.f, 0.f};
+    // every MMA accumulates: clear both accumulator sets once, then hand them to the MMA issuer
+    for (uint32_t c = 0; c < 512; c += 32) tmem_st32_zero(tmem_base + ((uint32_t)(q * 32) << 16) + c);
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(&tmem_empty[0]);
+    mbar_arrive(&tmem_empty[1]);
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int n = (int)(tile / tiles_per_n);
@@ -205,10 +217,29 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         const bool valid = (w < p.W) && (h < p.H) && (d < p.D);
         const size_t vox = (((size_t)n * p.D + d) * p.H + h) * p.W + w;
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(o * BN);
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+#pragma unroll
+        for (int chunk = 0; chunk < 2; ++chunk) {
+          const int c0 = chunk * 32;
+          if (c0 >= BN) break;
           uint32_t v[32];
           tmem_ld32(t_addr + c0, v);
           tmem_ld_wait();
+          tmem_st32_zero(t_addr + c0);   // ready for the next tile's always-accumulating MMAs
+          if (p.stat_partial != nullptr) {
+            float xs[32], xq[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              float f = __uint_as_float(v[e]);
+              if (p.relu) f = fmaxf(f, 0.f);
+              f = valid ? __bfloat162float(__float2bfloat16_rn(f)) : 0.f;
+              xs[e] = f;
+              xq[e] = f * f;
+            }
+            warp_column_sums(xs, lane);
+            warp_column_sums(xq, lane);
+            st_s[chunk] += xs[0];
+            st_q[chunk] += xq[0];
+          }
           if (valid) {
             uint4* dst = reinterpret_cast<uint4*>(p.y + vox * p.ldy + p.y_coff + c0);
 #pragma unroll
@@ -229,8 +260,21 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
         }
       }
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
+    }
+    if (p.stat_partial != nullptr) {
+      float2* sbuf = reinterpret_cast<float2*>(smem_p);   // [4][Cout] in the (now idle) plane ring
+#pragma unroll
+      for (int chunk = 0; chunk < 2; ++chunk)
+        if (chunk * 32 < BN) sbuf[q * BN + chunk * 32 + lane] = make_float2(st_s[chunk], st_q[chunk]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float2* dst = reinterpret_cast<float2*>(p.stat_partial) + (size_t)blockIdx.x * BN;
+      for (int c = q * 32 + lane; c < BN; c += 128) {
+        const float2 a = sbuf[c], b = sbuf[BN + c], cc = sbuf[2 * BN + c], d = sbuf[3 * BN + c];
+        dst[c] = make_float2((a.x + b.x) + (cc.x + d.x), (a.y + b.y) + (cc.y + d.y));
+      }
     }
   }
 
@@ -253,7 +297,7 @@ bool slab_applicable(int N, int D, int H, int W, int Cin, int Cout, int y_is_fp3
 }
 
 int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff, int N, int D,
-                int H, int W, int Cin, int Cout, int relu, cudaStream_t stream) {
+                int H, int W, int Cin, int Cout, int relu, float* stat_partial, int* n_partials, cudaStream_t stream) {
   SlabParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   const int KC = (Cin % 64 == 0) ? 64 : 32;
@@ -265,6 +309,8 @@ int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, 
   p.ldy = ldy; p.y_coff = y_coff;
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.total_tiles = (long long)N * p.tiles_w * p.tiles_h * p.tiles_d;
+  p.stat_partial = stat_partial;
+  if (stat_partial) B2_REQUIRE(N == 1, "b2_conv3d_igemm_stats: fused statistics need batch 1");
   const int plane_bytes = kPlaneRows * KC * 2;
   const int b_bytes = 9 * Cout * KC * 2;
   const int budget = 227 * 1024 - 1024 - 512;
@@ -292,6 +338,7 @@ int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, 
     conv3d_slab_kernel<32><<<(unsigned)grid, kSlabThreads, smem_bytes, stream>>>(ta, tb, p);
   }
   B2_CHECK_CUDA(cudaGetLastError());
+  if (n_partials) *n_partials = (int)grid;
   return B2_OK;
 }
 

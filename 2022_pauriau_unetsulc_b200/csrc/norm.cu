@@ -133,6 +133,35 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ r, long long V, int C, float* 
   if (threadIdx.x == 0) counters[n] = 0;   // self-resetting ticket
 }
 
+// statistics already reduced per (CTA, warp) by the conv epilogue: one block turns them into mean/rstd, scale/shift
+__global__ void __launch_bounds__(kStatThreads)
+gn_finalize_partials_kernel(const float* __restrict__ partial, int nblk, int C, int G, long long V, float eps,
+                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                            float* __restrict__ mean_rstd, float* __restrict__ scale_shift) {
+  extern __shared__ float sh[];
+  double* csum = reinterpret_cast<double*>(sh);
+  reduce_partials(partial, 0, nblk, C, csum);
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < cpg; ++k) { a += csum[2 * (g * cpg + k)]; b += csum[2 * (g * cpg + k) + 1]; }
+    const double m = (double)V * cpg;
+    const double mean = a / m;
+    double var = b / m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    for (int k = 0; k < cpg; ++k) {
+      const int c = g * cpg + k;
+      const float sc = rstd * gamma[c];
+      mean_rstd[c * 2 + 0] = (float)mean;
+      mean_rstd[c * 2 + 1] = rstd;
+      scale_shift[c * 2 + 0] = sc;
+      scale_shift[c * 2 + 1] = beta[c] - (float)mean * sc;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- forward apply
 // grid = (blocks, N).  A thread keeps one channel octet (256 % C8 == 0) and walks voxels with pointer increments only
 // (no 64-bit divisions in the loop), two independent 16-byte loads in flight.
@@ -429,6 +458,20 @@ extern "C" int b2_relu_gn_stats(const void* r, int N, long long V, int C, int G,
   gn_stats_kernel<<<dim3(nblk, N), kStatThreads, sh, stream>>>(reinterpret_cast<const __nv_bfloat16*>(r), V, C,
                                                                reinterpret_cast<float*>(workspace), counters, G, eps,
                                                                gamma, beta, mean_rstd, scale_shift);
+  B2_CHECK_CUDA(cudaGetLastError());
+  return B2_OK;
+}
+
+// GroupNorm statistics from the per-(CTA, warp) partial sums written by b2_conv3d_igemm_stats (batch 1).
+extern "C" int b2_relu_gn_finalize(const float* stat_partial, int n_partials, long long V, int C, int G, float eps,
+                                   const float* gamma, const float* beta, float* mean_rstd, float* scale_shift,
+                                   cudaStream_t stream) {
+  B2_REQUIRE(stat_partial && gamma && beta && mean_rstd && scale_shift && n_partials > 0,
+             "b2_relu_gn_finalize: null pointer");
+  int rc = check_gn_shape("b2_relu_gn_finalize", 1, V, C, G);
+  if (rc) return rc;
+  gn_finalize_partials_kernel<<<1, kStatThreads, (size_t)C * 2 * sizeof(double), stream>>>(
+      stat_partial, n_partials, C, G, V, eps, gamma, beta, mean_rstd, scale_shift);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }

@@ -144,6 +144,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// warp writes 32 consecutive fp32 columns of its 32 TMEM lanes (used to zero accumulators)
+__device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
@@ -175,6 +186,21 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_
   d |= ((N >> 3) & 0x3Fu) << 17;
   d |= ((M >> 4) & 0x1Fu) << 24;
   return d;
+}
+
+// Column sums of a 32 x 32 tile held as "lane = row, v[j] = column j": after the call v[0] of lane L holds the sum
+// over the 32 rows of column L.  Recursive halving, 31 shuffles (instead of 32 x 5 for per-column butterflies).
+__device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = upper ? v[j] : v[j + s];
+      const float keep = upper ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -192,12 +192,17 @@ class UNet3D(nn.Module):
             cin, cout = layer.cin, layer.cout
             d, h, w = (out_view.D, out_view.H, out_view.W)
             r = ActView.alloc(B, d, h, w, cout, dev)
+            gamma, beta = layer.norm.weight.detach(), layer.norm.bias.detach()
             if first:
                 ops.conv3d_first_fwd(xin, layer.conv.weight.detach(), r, relu=True)
+                mr, ss = ops.relu_gn_stats(r, G, layer.norm.eps, gamma, beta)
+            elif B == 1 and cout <= 256:
+                wf, _ = layer.packs()   # GroupNorm statistics come out of the conv epilogue
+                mr, ss = ops.conv3d_igemm_gn_stats(xin, wf, r, cin, cout, G, layer.norm.eps, gamma, beta)
             else:
                 wf, _ = layer.packs()
                 ops.conv3d_igemm(xin, wf, r, cin, cout, relu=True)
-            mr, ss = ops.relu_gn_stats(r, G, layer.norm.eps, layer.norm.weight.detach(), layer.norm.bias.detach())
+                mr, ss = ops.relu_gn_stats(r, G, layer.norm.eps, gamma, beta)
             ops.relu_gn_apply(r, ss, out_view, pooled)
             rec.append(dict(x=xin, r=r, mr=mr))
 

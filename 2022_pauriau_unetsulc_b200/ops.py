@@ -119,6 +119,27 @@ def conv3d_igemm(x, wpack, y, cin, cout, relu, y_fp32=False):
     _count(1)
 
 
+def conv3d_igemm_gn_stats(x, wpack, y, cin, cout, groups, eps, gamma, beta):
+    """fprop + ReLU with the GroupNorm statistics fused into the conv epilogue (batch 1, cout <= 256).
+    Returns (mean_rstd [1,C,2], scale_shift [1,C,2]) like relu_gn_stats, without re-reading the output tensor."""
+    lib = _lib.load()
+    _need_cuda(x.buf, wpack, y.buf, gamma, beta)
+    dev = x.buf.device
+    maxp = lib.b2_conv3d_stats_max_partials()
+    partial = Workspace.get(maxp * cout * 2 * 4, dev, "convstats")
+    n_partials = C.c_int(0)
+    with _Prof("conv3d_igemm", 2.0 * x.N * x.V * 27 * cin * cout):
+        _lib.check(lib.b2_conv3d_igemm_stats(_p(x.buf), x.ld, x.coff, _p(wpack), _p(y.buf), y.ld, y.coff, x.N, x.D,
+                                             x.H, x.W, cin, cout, 1, _p(partial), C.byref(n_partials), _s()),
+                   "b2_conv3d_igemm_stats")
+    mean_rstd = torch.empty((1, cout, 2), dtype=torch.float32, device=dev)
+    scale_shift = torch.empty((1, cout, 2), dtype=torch.float32, device=dev)
+    _lib.check(lib.b2_relu_gn_finalize(_p(partial), n_partials.value, x.V, cout, groups, float(eps), _p(gamma),
+                                       _p(beta), _p(mean_rstd), _p(scale_shift), _s()), "b2_relu_gn_finalize")
+    _count(2)
+    return mean_rstd, scale_shift
+
+
 def conv3d_wgrad(x, dy, cin, cout, out=None):
     """returns dW fp32 [cout, cin, 3, 3, 3] (written into `out` when given)"""
     lib = _lib.load()

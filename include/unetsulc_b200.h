@@ -32,6 +32,17 @@ const char* b2_last_error(void);
 int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff,
                     int y_is_fp32, int N, int D, int H, int W, int Cin, int Cout, int relu, cudaStream_t stream);
 
+/* fprop with the GroupNorm statistics of the stored (bf16, post-ReLU) output fused into the epilogue (batch 1, Cout
+ * <= 256).  stat_partial: fp32 [b2_conv3d_stats_max_partials()][Cout][2]; *n_partials (HOST int) = rows written;
+ * b2_relu_gn_finalize turns them into mean/rstd and scale/shift (replaces b2_relu_gn_stats, saves one tensor read). */
+int b2_conv3d_stats_max_partials(void);
+int b2_conv3d_igemm_stats(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff, int N,
+                          int D, int H, int W, int Cin, int Cout, int relu, float* stat_partial, int* n_partials,
+                          cudaStream_t stream);
+int b2_relu_gn_finalize(const float* stat_partial, int n_partials, long long V, int C, int G, float eps,
+                        const float* gamma, const float* beta, float* mean_rstd, float* scale_shift,
+                        cudaStream_t stream);
+
 /* dW[co][ci][3][3][3] (fp32, PyTorch layout) = sum_v dY[v,co] * X[v+off,ci]                                      */
 long long b2_conv3d_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout);
 int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* dy, int ldy, int y_coff, float* dw,

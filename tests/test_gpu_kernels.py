@@ -118,6 +118,34 @@ def test_conv_slab_kernel(shape):
         assert err < 2e-3, "slab dgrad rel-L2 %.3e" % err
 
 
+@pytest.mark.parametrize("shape", [(1, 64, 64, 8, 12, 64), (1, 128, 256, 6, 7, 6), (1, 64, 128, 5, 7, 9),
+                                   (1, 32, 64, 8, 12, 64), (1, 192, 64, 8, 8, 32)])
+def test_conv_epilogue_groupnorm_statistics(shape):
+    """GroupNorm statistics fused into the conv epilogue == statistics of a separate pass over the stored tensor."""
+    ops = _ops()
+    N, Cin, Cout, D, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(41)
+    x = bf16_round(torch.randn(N, Cin, D, H, W, device="cuda", generator=g))
+    w = bf16_round(torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=g) * (1.0 / (27 * Cin) ** 0.5))
+    gamma = torch.randn(Cout, device="cuda", generator=g) * 0.5 + 1.0
+    beta = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    wf, _ = ops.pack_conv_weights(w)
+    xv = ops.ActView(to_ndhwc(x), N, D, H, W, Cin)
+    r1 = ops.ActView.alloc(N, D, H, W, Cout, "cuda", zero=True)
+    mr1, ss1 = ops.conv3d_igemm_gn_stats(xv, wf, r1, Cin, Cout, 32, 1e-5, gamma, beta)
+    r2 = ops.ActView.alloc(N, D, H, W, Cout, "cuda", zero=True)
+    ops.conv3d_igemm(xv, wf, r2, Cin, Cout, relu=True)
+    mr2, ss2 = ops.relu_gn_stats(r2, 32, 1e-5, gamma, beta)
+    torch.cuda.synchronize()
+    assert torch.equal(r1.buf, r2.buf)
+    assert torch.allclose(mr1, mr2, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(ss1, ss2, rtol=1e-5, atol=1e-6)
+    ref = F.group_norm(from_view(r2), 32, gamma, beta, 1e-5)
+    y = ops.ActView.alloc(N, D, H, W, Cout, "cuda")
+    ops.relu_gn_apply(r1, ss1, y)
+    assert rel_l2(from_view(y), ref) < 4e-3
+
+
 def test_conv_fprop_channel_windows():
     """input read from / output written into channel windows of wider buffers (concat buffers)."""
     ops = _ops()
@@ -218,6 +246,39 @@ def test_conv_full_size_layers_deterministic_and_exact(cin, cout, dims):
     e = rel_l2(outs[0][2], wq.grad)
     print("full-size wgrad rel-L2 %.3e" % e)
     assert e < 2e-4
+
+
+@pytest.mark.parametrize("cin,cout,dims", [(64, 64, (32, 56, 96)), (192, 64, (16, 28, 96)), (32, 64, (32, 56, 96)),
+                                           (128, 128, (48, 56, 48)), (256, 512, (12, 14, 12))])
+def test_conv_pipelines_stress_bitwise(cin, cout, dims):
+    """30 back-to-back launches of fprop (+ fused GroupNorm statistics), dgrad and wgrad must be bit-identical:
+    a barrier-protocol race in the TMA / tcgen05 / TMEM pipelines would show up as run-to-run differences."""
+    ops = _ops()
+    D, H, W = dims
+    g = torch.Generator(device="cuda").manual_seed(51)
+    x = ops.ActView(torch.randn(1, D, H, W, cin, device="cuda", generator=g).to(torch.bfloat16), 1, D, H, W, cin)
+    dy = ops.ActView(torch.randn(1, D, H, W, cout, device="cuda", generator=g).to(torch.bfloat16), 1, D, H, W, cout)
+    w = torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) * 0.02
+    gamma = torch.ones(cout, device="cuda"); beta = torch.zeros(cout, device="cuda")
+    wf, wd = ops.pack_conv_weights(w)
+    first = None
+    for it in range(30):
+        y = ops.ActView.alloc(1, D, H, W, cout, "cuda")
+        if cout <= 256:
+            mr, _ = ops.conv3d_igemm_gn_stats(x, wf, y, cin, cout, 32, 1e-5, gamma, beta)
+        else:
+            ops.conv3d_igemm(x, wf, y, cin, cout, relu=True)
+            mr, _ = ops.relu_gn_stats(y, 32, 1e-5, gamma, beta)
+        dx = ops.ActView.alloc(1, D, H, W, cin, "cuda")
+        ops.conv3d_igemm(dy, wd, dx, cout, cin, relu=False)
+        dw = ops.conv3d_wgrad(x, dy, cin, cout)
+        cur = (y.buf, mr, dx.buf, dw)
+        if first is None:
+            first = tuple(t.clone() for t in cur)
+        else:
+            for name, a, b in zip(("fprop", "stats", "dgrad", "wgrad"), first, cur):
+                assert torch.equal(a, b), "%s differs at iteration %d" % (name, it)
+    torch.cuda.synchronize()
 
 
 def test_conv_first_layer():
