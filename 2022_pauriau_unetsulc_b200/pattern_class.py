@@ -312,19 +312,73 @@ class UnetPatternSulciLabelling(object):
             return dist.get_rank(), dist.get_world_size()
         return 0, 1
 
-    def train_step(self, inputs, labels, optimizer, reducer=None):
-        """One training step from HOST tensors (pinned memory recommended): H2D copy, fused forward + loss +
-        backward, gradient all-reduce when data parallel, fused SGD.  Returns the loss as a Python float (one D2H
-        read), i.e. what the reference's batch loop does per batch (training.py:198-215)."""
+    # -- CUDA-graph replay of the whole step ---------------------------------------------------------------------
+    # A step is ~125 kernel launches; enqueueing them from Python costs ~5 ms against ~8 ms of GPU time.  When the
+    # same volume shape comes back (fixed img_size, batch > 1 padding, benchmarks) the step is captured once into a
+    # CUDA graph and replayed: one launch per step.  Off by default for learning() because every subject of a real
+    # cohort has its own bounding box; `use_cuda_graph = True` turns it on (single-GPU only).
+    use_cuda_graph = False
+    _graph_cache_limit = 2
+
+    def _graph_key(self, shape, optimizer):
+        mask = tuple(bool(p.requires_grad) for p in self.model.ordered_parameters())
+        return (tuple(shape), id(optimizer), float(optimizer.param_groups[0]["lr"]), float(optimizer.momentum), mask)
+
+    def _graphed_step(self, x, y, optimizer):
+        """x, y: device tensors.  Returns the [2] loss tensor (mean, sum) of the step that was just enqueued."""
+        cache = self.__dict__.setdefault("_graphs", {})
+        seen = self.__dict__.setdefault("_graph_seen", set())
+        key = self._graph_key(x.shape, optimizer)
+        ent = cache.get(key)
+        if ent is None:
+            if key not in seen:          # first time: a real eager step (creates workspaces / momentum buffers)
+                seen.add(key)
+                loss, _, _, grads = self.model.forward_backward(x, y)
+                optimizer.step(grads=grads)
+                return loss
+            if len(cache) >= self._graph_cache_limit:
+                cache.pop(next(iter(cache)))
+            sx, sy = torch.empty_like(x), torch.empty_like(y)
+            sx.copy_(x)
+            sy.copy_(y)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):   # records, does not execute
+                loss, _, _, grads = self.model.forward_backward(sx, sy)
+                optimizer.step(grads=grads)
+            ent = cache[key] = (graph, sx, sy, loss)
+        else:
+            graph, sx, sy, loss = ent
+            sx.copy_(x, non_blocking=True)
+            sy.copy_(y, non_blocking=True)
+        ent[0].replay()
+        # the replayed SGD changed the fp32 masters behind PyTorch's back: bump their version counters so that eager
+        # paths (validation, labeling, state_dict consumers) re-pack the bf16 weights
+        for p in self.model.ordered_parameters():
+            if p.requires_grad:
+                torch.autograd.graph.increment_version(p)
+        return ent[3]
+
+    def train_step_device(self, x, y, optimizer, reducer=None):
+        """One training step on DEVICE tensors, no host synchronisation.  Returns the [2] loss tensor (mean, sum)."""
         self.model.train()
-        x = inputs.to(self.device, non_blocking=True)
-        y = labels.to(self.device, non_blocking=True)
+        if self.use_cuda_graph and reducer is None:
+            return self._graphed_step(x, y, optimizer)
         if reducer is not None:
             reducer.begin()
         loss, _, _, grads = self.model.forward_backward(x, y, outs=reducer.outs() if reducer is not None else None)
         if reducer is not None:
             grads = [g if n is not None else None for g, n in zip(reducer.finish(), grads)]
         optimizer.step(grads=grads)
+        return loss
+
+    def train_step(self, inputs, labels, optimizer, reducer=None):
+        """One training step from HOST tensors (pinned memory recommended): H2D copy, fused forward + loss +
+        backward, gradient all-reduce when data parallel, fused SGD.  Returns the loss as a Python float (one D2H
+        read), i.e. what the reference's batch loop does per batch (training.py:198-215)."""
+        x = inputs.to(self.device, non_blocking=True)
+        y = labels.to(self.device, non_blocking=True)
+        loss = self.train_step_device(x, y, optimizer, reducer)
         return float(loss[0].item())
 
     def _run_phase(self, phase, loader, optimizer, reducer, before_step=None):

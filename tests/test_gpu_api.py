@@ -128,3 +128,34 @@ def test_transfer_learning_two_phases(tmp_path):
     assert torch.equal(tl.model.decoders[2].double_conv.conv2.weight.detach().cpu(), dec_before)
     assert len(tl.results['epoch_loss_train'][0]) == 5
     assert tl.results['epoch_loss_train'][0][-1] < tl.results['epoch_loss_train'][0][0]
+
+
+def test_cuda_graph_step_matches_eager_step(tmp_path):
+    """train_step with use_cuda_graph replays the same kernels: identical losses and weights, step after step."""
+    from unetsulc_b200.training import UnetTrainingSulciLabelling
+    from unetsulc_b200.optim import SGD
+    from oracle.synth import synth_volume
+    sslist = ['S%02d_left' % i for i in range(8)]
+    data = []
+    for s in range(3):
+        x, l = synth_volume((16, 24, 32), 8, 100 + s, occupancy=0.06)
+        data.append((x.unsqueeze(0).pin_memory(), l.unsqueeze(0).pin_memory()))
+    results = []
+    for use_graph in (False, True):
+        torch.manual_seed(11)
+        with _quiet():
+            t = UnetTrainingSulciLabelling([], 'L', cuda=0, working_path=str(tmp_path), dict_model={'name': 'g'},
+                                           dict_names={}, dict_bck2={}, sulci_side_list=sslist)
+            t.load_network()
+        t.use_cuda_graph = use_graph
+        opt = SGD(t.model.ordered_parameters(), lr=1e-2, momentum=0.9)
+        losses = [t.train_step(*data[i % 3], opt) for i in range(6)]
+        # an eager evaluation after graph replays must see the updated weights
+        t.model.eval()
+        with torch.no_grad():
+            val, _ = t.model.loss_and_preds(data[0][0].cuda(), data[0][1].cuda())
+        results.append((losses, float(val), [p.detach().clone() for p in t.model.parameters()]))
+    assert results[0][0] == results[1][0], (results[0][0], results[1][0])
+    assert results[0][1] == results[1][1]
+    for a, b in zip(results[0][2], results[1][2]):
+        assert torch.equal(a, b)
