@@ -324,8 +324,18 @@ class UnetPatternSulciLabelling(object):
         mask = tuple(bool(p.requires_grad) for p in self.model.ordered_parameters())
         return (tuple(shape), id(optimizer), float(optimizer.param_groups[0]["lr"]), float(optimizer.momentum), mask)
 
-    def _graphed_step(self, x, y, optimizer):
-        """x, y: device tensors.  Returns the [2] loss tensor (mean, sum) of the step that was just enqueued."""
+    def _eager_step(self, x, y, optimizer, reducer):
+        if reducer is not None:
+            reducer.begin()
+        loss, _, _, grads = self.model.forward_backward(x, y, outs=reducer.outs() if reducer is not None else None)
+        if reducer is not None:
+            grads = [g if n is not None else None for g, n in zip(reducer.finish(), grads)]
+        optimizer.step(grads=grads)
+        return loss
+
+    def _graphed_step(self, x, y, optimizer, reducer=None):
+        """x, y: device tensors.  Returns the [2] loss tensor (mean, sum) of the step that was just enqueued.
+        With a reducer the bucketed NCCL all-reduces (side stream, fork/join by events) are captured too."""
         cache = self.__dict__.setdefault("_graphs", {})
         seen = self.__dict__.setdefault("_graph_seen", set())
         key = self._graph_key(x.shape, optimizer)
@@ -333,9 +343,7 @@ class UnetPatternSulciLabelling(object):
         if ent is None:
             if key not in seen:          # first time: a real eager step (creates workspaces / momentum buffers)
                 seen.add(key)
-                loss, _, _, grads = self.model.forward_backward(x, y)
-                optimizer.step(grads=grads)
-                return loss
+                return self._eager_step(x, y, optimizer, reducer)
             if len(cache) >= self._graph_cache_limit:
                 cache.pop(next(iter(cache)))
             sx, sy = torch.empty_like(x), torch.empty_like(y)
@@ -343,9 +351,13 @@ class UnetPatternSulciLabelling(object):
             sy.copy_(y)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):   # records, does not execute
-                loss, _, _, grads = self.model.forward_backward(sx, sy)
-                optimizer.step(grads=grads)
+            try:
+                with torch.cuda.graph(graph):   # records, does not execute
+                    loss = self._eager_step(sx, sy, optimizer, reducer)
+            except Exception as e:  # e.g. a collective that cannot be captured: stay eager from now on
+                print("unetsulc_b200: CUDA-graph capture failed (%s); continuing without graphs" % e)
+                self.use_cuda_graph = False
+                return self._eager_step(x, y, optimizer, reducer)
             ent = cache[key] = (graph, sx, sy, loss)
         else:
             graph, sx, sy, loss = ent
@@ -362,15 +374,11 @@ class UnetPatternSulciLabelling(object):
     def train_step_device(self, x, y, optimizer, reducer=None):
         """One training step on DEVICE tensors, no host synchronisation.  Returns the [2] loss tensor (mean, sum)."""
         self.model.train()
+        # graphs are used on a single GPU only: capturing the NCCL all-reduces (side-stream fork/join) dead-locked at
+        # replay on 2 x B200 (round 1), so data-parallel steps stay eager
         if self.use_cuda_graph and reducer is None:
-            return self._graphed_step(x, y, optimizer)
-        if reducer is not None:
-            reducer.begin()
-        loss, _, _, grads = self.model.forward_backward(x, y, outs=reducer.outs() if reducer is not None else None)
-        if reducer is not None:
-            grads = [g if n is not None else None for g, n in zip(reducer.finish(), grads)]
-        optimizer.step(grads=grads)
-        return loss
+            return self._graphed_step(x, y, optimizer, None)
+        return self._eager_step(x, y, optimizer, reducer)
 
     def train_step(self, inputs, labels, optimizer, reducer=None):
         """One training step from HOST tensors (pinned memory recommended): H2D copy, fused forward + loss +

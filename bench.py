@@ -291,7 +291,7 @@ def run_ours(args):
             "config": {"workload": "UNet3D(in=1,out=56,'crg',f=64) full training step (SGD lr 1e-2 momentum 0.9), "
                                    "synthetic 1x1x96x112x96 skeleton volumes, batch 1 per rank",
                        "parallelism": "dp%d over subjects" % world,
-                       "cuda_graph": bool(trainer.use_cuda_graph),
+                       "cuda_graph": bool(trainer.use_cuda_graph and world == 1),
                        "l2": "no explicit flush: a step streams ~2 GB of activations (>> 126 MB L2) and cycles "
                              "through %d distinct volumes" % n_data},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
