@@ -16,6 +16,9 @@ SIGNATURES = {
     "b2_conv3d_igemm": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b2_conv3d_stats_max_partials": (_i, []),
     "b2_conv3d_igemm_stats": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "b2_conv3d_igemm_bstats": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "b2_relu_gn_bwd_from_partials": (_i, [_vp, _i, _vp, _i, _i, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll,
+                                          _vp]),
     "b2_relu_gn_finalize": (_i, [_vp, _i, _ll, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "b2_conv3d_wgrad_workspace_bytes": (_ll, [_i, _i, _i, _i, _i, _i]),
     "b2_conv3d_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),

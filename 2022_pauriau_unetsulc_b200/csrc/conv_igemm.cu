@@ -36,6 +36,8 @@ struct IgemmParams {
   float* stat_partial; // optional [gridDim.x][Cout][2]: per-CTA sum / sum-of-squares of the
                        // bf16-rounded outputs per channel (GroupNorm statistics fused into the epilogue; N == 1,
                        // one N tile only)
+  const __nv_bfloat16* stat_r;  // when set, the statistics are (sum dy, sum dy*r) with r = this dense [V][Cout]
+                                // tensor: the two per-channel sums GroupNorm backward needs (dgrad launches)
   long long total_tiles;
 };
 
@@ -207,6 +209,20 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             xs[e] = f;
             xq[e] = f * f;
           }
+          if (p.stat_r != nullptr) {   // backward statistics: second sum is dy * r
+            const uint4* rp = reinterpret_cast<const uint4*>(p.stat_r + vox * p.Cout + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u = make_uint4(0, 0, 0, 0);
+              if (valid) u = __ldg(rp + j);
+              const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                xq[8 * j + 2 * e] = xs[8 * j + 2 * e] * __uint_as_float(wds[e] << 16);
+                xq[8 * j + 2 * e + 1] = xs[8 * j + 2 * e + 1] * __uint_as_float(wds[e] & 0xffff0000u);
+              }
+            }
+          }
           warp_column_sums(xs, lane);
           warp_column_sums(xq, lane);
           st_s[chunk] += xs[0];
@@ -295,7 +311,8 @@ static void choose_box(int W, int H, int D, int& bw, int& bh, int& bd) {
 
 bool slab_applicable(int N, int D, int H, int W, int Cin, int Cout, int y_is_fp32);
 int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff, int N, int D,
-                int H, int W, int Cin, int Cout, int relu, float* stat_partial, int* n_partials, cudaStream_t stream);
+                int H, int W, int Cin, int Cout, int relu, float* stat_partial, const void* stat_r, int* n_partials,
+                cudaStream_t stream);
 
 int make_act_tmap(CUtensorMap* map, const void* base, int N, int D, int H, int W, int C, int ld, int coff,
                   int box_c, int bw, int bh, int bd) {
@@ -315,7 +332,7 @@ using namespace b2;
 // See include/unetsulc_b200.h for the contract.
 static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff,
                              int y_is_fp32, int N, int D, int H, int W, int Cin, int Cout, int relu,
-                             float* stat_partial, int* n_partials, cudaStream_t stream) {
+                             float* stat_partial, const void* stat_r, int* n_partials, cudaStream_t stream) {
   B2_REQUIRE(x && wpack && y, "b2_conv3d_igemm: null pointer");
   B2_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "b2_conv3d_igemm: bad shape %dx%dx%dx%d", N, D, H, W);
   B2_REQUIRE(Cin % 32 == 0 && Cin >= 32, "b2_conv3d_igemm: Cin=%d must be a multiple of 32", Cin);
@@ -327,8 +344,8 @@ static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpa
   // narrow-N layers at (almost) tile-aligned resolutions: shared-memory tap-reuse kernel (conv_slab.cu)
   static const bool no_slab = getenv("B2_NO_SLAB") != nullptr;
   if (!no_slab && slab_applicable(N, D, H, W, Cin, Cout, y_is_fp32))
-    return launch_slab(x, ldx, x_coff, wpack, y, ldy, y_coff, N, D, H, W, Cin, Cout, relu, stat_partial, n_partials,
-                       stream);
+    return launch_slab(x, ldx, x_coff, wpack, y, ldy, y_coff, N, D, H, W, Cin, Cout, relu, stat_partial, stat_r,
+                       n_partials, stream);
 
   IgemmParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
@@ -360,6 +377,7 @@ static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpa
   p.y32 = y_is_fp32 ? reinterpret_cast<float*>(y) : nullptr;
   p.total_tiles = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles_n;
   p.stat_partial = stat_partial;
+  p.stat_r = reinterpret_cast<const __nv_bfloat16*>(stat_r);
   if (stat_partial) {
     B2_REQUIRE(N == 1 && p.n_tiles_n == 1 && !y_is_fp32,
                "b2_conv3d_igemm_stats: fused statistics need batch 1, Cout <= 256 and a bf16 output");
@@ -394,7 +412,7 @@ extern "C" int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* w
                                int y_is_fp32, int N, int D, int H, int W, int Cin, int Cout, int relu,
                                cudaStream_t stream) {
   return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, ldy, y_coff, y_is_fp32, N, D, H, W, Cin, Cout, relu, nullptr,
-                           nullptr, stream);
+                           nullptr, nullptr, stream);
 }
 
 extern "C" int b2_conv3d_stats_max_partials(void) { return num_sms(); }
@@ -406,6 +424,17 @@ extern "C" int b2_conv3d_igemm_stats(const void* x, int ldx, int x_coff, const v
                                      float* stat_partial, int* n_partials, cudaStream_t stream) {
   B2_REQUIRE(stat_partial && n_partials, "b2_conv3d_igemm_stats: null pointer");
   return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, ldy, y_coff, 0, N, D, H, W, Cin, Cout, relu, stat_partial,
+                           nullptr, n_partials, stream);
+}
+
+// dgrad (x = dY, wpack = dgrad pack, output dX written densely) with the GroupNorm-BACKWARD statistics of the layer
+// that produced dX's forward tensor fused into the epilogue: per channel sum(dX) and sum(dX * r), r = that layer's
+// stored relu(conv) (dense bf16 [V][Cout]).  Same partial layout / limits as b2_conv3d_igemm_stats.
+extern "C" int b2_conv3d_igemm_bstats(const void* x, int ldx, int x_coff, const void* wpack, void* y, int N, int D,
+                                      int H, int W, int Cin, int Cout, const void* r, float* stat_partial,
+                                      int* n_partials, cudaStream_t stream) {
+  B2_REQUIRE(stat_partial && n_partials && r, "b2_conv3d_igemm_bstats: null pointer");
+  return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, Cout, 0, 0, N, D, H, W, Cin, Cout, 0, stat_partial, r,
                            n_partials, stream);
 }
 

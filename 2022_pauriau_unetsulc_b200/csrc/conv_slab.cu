@@ -35,6 +35,7 @@ struct SlabParams {
   int ldy, y_coff;
   __nv_bfloat16* y;
   float* stat_partial;   // optional [gridDim.x][Cout][2] (see conv_igemm.cu)
+  const __nv_bfloat16* stat_r;   // optional: backward statistics (sum dy, sum dy*r)
   long long total_tiles;
 };
 
@@ -235,6 +236,20 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
               xs[e] = f;
               xq[e] = f * f;
             }
+            if (p.stat_r != nullptr) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.stat_r + vox * BN + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 u = make_uint4(0, 0, 0, 0);
+                if (valid) u = __ldg(rp + j);
+                const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  xq[8 * j + 2 * e] = xs[8 * j + 2 * e] * __uint_as_float(wds[e] << 16);
+                  xq[8 * j + 2 * e + 1] = xs[8 * j + 2 * e + 1] * __uint_as_float(wds[e] & 0xffff0000u);
+                }
+              }
+            }
             warp_column_sums(xs, lane);
             warp_column_sums(xq, lane);
             st_s[chunk] += xs[0];
@@ -297,7 +312,8 @@ bool slab_applicable(int N, int D, int H, int W, int Cin, int Cout, int y_is_fp3
 }
 
 int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff, int N, int D,
-                int H, int W, int Cin, int Cout, int relu, float* stat_partial, int* n_partials, cudaStream_t stream) {
+                int H, int W, int Cin, int Cout, int relu, float* stat_partial, const void* stat_r, int* n_partials,
+                cudaStream_t stream) {
   SlabParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   const int KC = (Cin % 64 == 0) ? 64 : 32;
@@ -310,6 +326,7 @@ int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, 
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.total_tiles = (long long)N * p.tiles_w * p.tiles_h * p.tiles_d;
   p.stat_partial = stat_partial;
+  p.stat_r = reinterpret_cast<const __nv_bfloat16*>(stat_r);
   if (stat_partial) B2_REQUIRE(N == 1, "b2_conv3d_igemm_stats: fused statistics need batch 1");
   const int plane_bytes = kPlaneRows * KC * 2;
   const int b_bytes = 9 * Cout * KC * 2;

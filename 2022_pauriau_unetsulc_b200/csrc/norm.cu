@@ -409,6 +409,46 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
   }
 }
 
+// backward statistics already reduced per CTA by the dgrad epilogue as (sum dy, sum dy*r): one block turns them into
+// the per-channel coefficients, d gamma and d beta (batch 1)
+__global__ void __launch_bounds__(kStatThreads)
+gn_bwd_finalize_partials_kernel(const float* __restrict__ partial, int nblk, int C, int G, long long V,
+                                const float* __restrict__ gamma, const float* __restrict__ mean_rstd,
+                                float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sh[];
+  double* csum = reinterpret_cast<double*>(sh);
+  reduce_partials(partial, 0, nblk, C, csum);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {   // (sum dy, sum dy*r) -> (sum dy, sum dy*xhat)
+    const double mu = (double)mean_rstd[c * 2], rs = (double)mean_rstd[c * 2 + 1];
+    const double sdy = csum[2 * c], sdyr = csum[2 * c + 1];
+    const double sdyx = rs * (sdyr - mu * sdy);
+    csum[2 * c + 1] = sdyx;
+    if (dgamma) dgamma[c] = (float)sdyx;
+    if (dbeta) dbeta[c] = (float)sdy;
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double S1 = 0.0, S2 = 0.0;
+    for (int k = 0; k < cpg; ++k) {
+      const double gm = (double)gamma[g * cpg + k];
+      S1 += gm * csum[2 * (g * cpg + k)];
+      S2 += gm * csum[2 * (g * cpg + k) + 1];
+    }
+    const double m = (double)V * cpg;
+    for (int k = 0; k < cpg; ++k) {
+      const int c = g * cpg + k;
+      const double rstd = (double)mean_rstd[c * 2 + 1];
+      float* o = coef + (size_t)c * 4;
+      o[0] = (float)(rstd * (double)gamma[c]);
+      o[1] = (float)(-rstd * S2 / m);
+      o[2] = (float)(-rstd * S1 / m);
+      o[3] = 0.f;
+    }
+  }
+}
+
 static inline int stat_blocks(long long V, int C) {
   long long nb = (V * C * 2) / 65536;   // at least 64 KB of the tensor per block
   if (nb > kStatBlocks) nb = kStatBlocks;
@@ -525,4 +565,27 @@ extern "C" int b2_relu_gn_bwd(const void* dy, int lddy, int dy_coff, const void*
 
 extern "C" long long b2_relu_gn_bwd_workspace_bytes(int N, int C) {
   return b2_gn_workspace_bytes(N, C) + (long long)N * C * 6 * (long long)sizeof(float);
+}
+
+// GroupNorm backward when the statistics come from b2_conv3d_igemm_bstats (batch 1): finalize + apply, no statistics
+// pass over dy and r.  workspace: >= C*4 floats.
+extern "C" int b2_relu_gn_bwd_from_partials(const float* stat_partial, int n_partials, const void* dy, int lddy,
+                                            int dy_coff, const void* r, long long V, int C, int G, const float* gamma,
+                                            const float* mean_rstd, void* dr, float* dgamma, float* dbeta,
+                                            void* workspace, long long workspace_bytes, cudaStream_t stream) {
+  B2_REQUIRE(stat_partial && dy && r && gamma && mean_rstd && dr && workspace && n_partials > 0,
+             "b2_relu_gn_bwd_from_partials: null pointer");
+  int rc = check_gn_shape("b2_relu_gn_bwd_from_partials", 1, V, C, G);
+  if (rc) return rc;
+  B2_REQUIRE(workspace_bytes >= (long long)C * 4 * (long long)sizeof(float),
+             "b2_relu_gn_bwd_from_partials: workspace too small");
+  float* coef = reinterpret_cast<float*>(workspace);
+  gn_bwd_finalize_partials_kernel<<<1, kStatThreads, (size_t)C * 2 * sizeof(double), stream>>>(
+      stat_partial, n_partials, C, G, V, gamma, mean_rstd, coef, dgamma, dbeta);
+  B2_CHECK_CUDA(cudaGetLastError());
+  gn_bwd_apply_kernel<<<dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
+      mean_rstd, coef, reinterpret_cast<__nv_bfloat16*>(dr));
+  B2_CHECK_CUDA(cudaGetLastError());
+  return B2_OK;
 }

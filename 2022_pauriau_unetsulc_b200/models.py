@@ -261,12 +261,20 @@ class UNet3D(nn.Module):
         if outs is None:
             outs = [None] * 42
 
-        def layer_bwd(i, dy):
-            """dy: gradient w.r.t. the GN output of layer i.  Returns gradient w.r.t. the layer input (or None)."""
+        B = save.x.shape[0]
+
+        def layer_bwd(i, dy, dy_stats=None):
+            """dy: gradient w.r.t. the GN output of layer i (dy_stats: GroupNorm-backward statistics of dy when the
+            dgrad that produced it fused them).  Returns gradient w.r.t. the layer input (or None); for the second
+            conv of a block the return value is (dx, stats) so that the first conv's GroupNorm skips its pass."""
             layer, rc = L[i], rec[i]
             want_gb = needs[3 * i + 1] or needs[3 * i + 2]
-            dr, dg, db = ops.relu_gn_bwd(dy, rc["r"], G, layer.norm.weight.detach(), rc["mr"], want_gb,
-                                         outs[3 * i + 1] if want_gb else None, outs[3 * i + 2] if want_gb else None)
+            go, bo = (outs[3 * i + 1] if want_gb else None), (outs[3 * i + 2] if want_gb else None)
+            if dy_stats is not None:
+                dr, dg, db = ops.relu_gn_bwd_from_stats(dy_stats, dy, rc["r"], G, layer.norm.weight.detach(),
+                                                        rc["mr"], want_gb, go, bo)
+            else:
+                dr, dg, db = ops.relu_gn_bwd(dy, rc["r"], G, layer.norm.weight.detach(), rc["mr"], want_gb, go, bo)
             if needs[3 * i + 1]:
                 grads[3 * i + 1] = dg
             if needs[3 * i + 2]:
@@ -283,6 +291,10 @@ class UNet3D(nn.Module):
             xin = rc["x"]
             dx = ActView.alloc(xin.N, xin.D, xin.H, xin.W, layer.cin, dr.buf.device)
             _, wd = layer.packs()
+            if i % 2 == 1 and B == 1 and layer.cin <= 256:
+                # conv2 of a block: dx IS the gradient at conv1's GroupNorm output -> fuse its backward statistics
+                stats = ops.conv3d_dgrad_gn_bstats(dr, wd, dx, layer.cout, layer.cin, rec[i - 1]["r"])
+                return dx, stats
             ops.conv3d_igemm(dr, wd, dx, layer.cout, layer.cin, relu=False)
             return dx
 
@@ -290,12 +302,15 @@ class UNet3D(nn.Module):
         dcat = [None, None, None]
         # decoders: layers 13,12 (lvl 0), 11,10 (lvl 1), 9,8 (lvl 2)
         li = 13
+        def split(res):
+            return res if isinstance(res, tuple) else (res, None)
+
         for lvl in (0, 1, 2):
-            dy = layer_bwd(li, dy)
+            dy, st = split(layer_bwd(li, dy))
             li -= 1
             if dy is None:
                 return grads
-            dc = layer_bwd(li, dy)
+            dc = layer_bwd(li, dy, st)
             li -= 1
             if dc is None:
                 return grads
@@ -306,11 +321,11 @@ class UNet3D(nn.Module):
             if lvl < 3:
                 ywin = cats[lvl].window(0, skip_c[lvl])
                 dy = ops.maxpool3d_bwd_add(ywin, dcat[lvl].window(0, skip_c[lvl]), dy)
-            dy = layer_bwd(li, dy)
+            dy, st = split(layer_bwd(li, dy))
             li -= 1
             if dy is None:
                 return grads
-            dy = layer_bwd(li, dy)
+            dy = layer_bwd(li, dy, st)
             li -= 1
             if dy is None:
                 return grads

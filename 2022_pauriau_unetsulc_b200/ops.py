@@ -140,6 +140,43 @@ def conv3d_igemm_gn_stats(x, wpack, y, cin, cout, groups, eps, gamma, beta):
     return mean_rstd, scale_shift
 
 
+def conv3d_dgrad_gn_bstats(dy, wd, dx, cin, cout, r):
+    """dgrad (dy: gradient w.r.t. the conv output with `cin` channels -> dx with `cout` channels, dense) with the
+    GroupNorm-backward statistics of the layer that produced dx's forward tensor fused into the epilogue.
+    r: that layer's stored relu(conv) (dense ActView, `cout` channels).  Returns an opaque stats handle."""
+    lib = _lib.load()
+    dev = dy.buf.device
+    maxp = lib.b2_conv3d_stats_max_partials()
+    partial = Workspace.get(maxp * cout * 2 * 4, dev, "convbstats")
+    n_partials = C.c_int(0)
+    with _Prof("conv3d_igemm", 2.0 * dy.N * dy.V * 27 * cin * cout):
+        _lib.check(lib.b2_conv3d_igemm_bstats(_p(dy.buf), dy.ld, dy.coff, _p(wd), _p(dx.buf), dy.N, dy.D, dy.H, dy.W,
+                                              cin, cout, _p(r.buf), _p(partial), C.byref(n_partials), _s()),
+                   "b2_conv3d_igemm_bstats")
+    _count(1)
+    return (partial, n_partials.value)
+
+
+def relu_gn_bwd_from_stats(stats, dy, r, groups, gamma, mean_rstd, want_param_grads=True, dgamma_out=None,
+                           dbeta_out=None):
+    """GroupNorm backward using the statistics fused into the dgrad that produced `dy` (batch 1)."""
+    lib = _lib.load()
+    dev = r.buf.device
+    partial, n_partials = stats
+    dr = ActView.alloc(r.N, r.D, r.H, r.W, r.C, dev)
+    dgamma = dgamma_out if dgamma_out is not None else (
+        torch.empty(r.C, dtype=torch.float32, device=dev) if want_param_grads else None)
+    dbeta = dbeta_out if dbeta_out is not None else (
+        torch.empty(r.C, dtype=torch.float32, device=dev) if want_param_grads else None)
+    ws = Workspace.get(r.C * 16, dev, "gncoef")
+    _lib.check(lib.b2_relu_gn_bwd_from_partials(_p(partial), n_partials, _p(dy.buf), dy.ld, dy.coff, _p(r.buf), r.V,
+                                                r.C, groups, _p(gamma), _p(mean_rstd), _p(dr.buf), _p(dgamma),
+                                                _p(dbeta), _p(ws), ws.numel(), _s()),
+               "b2_relu_gn_bwd_from_partials")
+    _count(2)
+    return dr, dgamma, dbeta
+
+
 def conv3d_wgrad(x, dy, cin, cout, out=None):
     """returns dW fp32 [cout, cin, 3, 3, 3] (written into `out` when given)"""
     lib = _lib.load()

@@ -275,6 +275,36 @@ def run_ours(args):
     e2e = {"value": world * args.steps / e_secs, "unit": "volumes/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 4, "ms_per_step": e_secs / args.steps * 1e3}
 
+    # secondary metric of BASELINE.json: inference ms per hemisphere = eval forward + Softmax scores gathered at the
+    # skeleton voxels + the cutting / fold-vote pass for thresholds [50, 100, 150] (pattern_class.py:177-245), device
+    # resident, CUDA events, rank 0 only
+    inference = None
+    if rank == 0:
+        from oracle.synth import synth_folds
+        from unetsulc_b200 import cutting as cut_mod
+        model.eval()
+        xi = xs_d[0]
+        idx = torch.nonzero(xi.reshape(-1) > 0).reshape(-1)
+        coords = torch.nonzero(xi[0, 0] > 0).cpu().numpy()
+        vert = synth_folds(coords, (12, 14, 12))
+        import numpy as _np
+        _, inv = _np.unique(vert, return_inverse=True)
+        fold = torch.from_numpy(inv.astype(_np.int32)).to(dev)
+        nf = int(inv.max()) + 1
+
+        def infer(_i):
+            with torch.no_grad():
+                scores, preds = model.scores_at(xi, idx)
+                return ops.fold_vote(scores, fold, nf, [50, 100, 150])
+
+        for i in range(3):
+            infer(i)
+        isecs, _ = timed(infer, 10)
+        inference = {"ms_per_hemi": isecs / 10 * 1e3, "voxels": int(idx.numel()), "folds": nf,
+                     "what": "eval forward + softmax gather at skeleton voxels + fold vote for 3 thresholds, "
+                             "inputs resident in HBM"}
+        model.train()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = (48, 56, 48)
@@ -295,7 +325,7 @@ def run_ours(args):
                        "l2": "no explicit flush: a step streams ~2 GB of activations (>> 126 MB L2) and cycles "
                              "through %d distinct volumes" % n_data},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "wall_s_timed_region": wall,
+            "wall_s_timed_region": wall, "inference": inference,
         }
         print(json.dumps(line))
     if world > 1:

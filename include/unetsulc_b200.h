@@ -39,6 +39,16 @@ int b2_conv3d_stats_max_partials(void);
 int b2_conv3d_igemm_stats(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff, int N,
                           int D, int H, int W, int Cin, int Cout, int relu, float* stat_partial, int* n_partials,
                           cudaStream_t stream);
+/* dgrad with the GroupNorm-BACKWARD statistics (sum dX, sum dX*r per channel) of the producing layer fused into the
+ * epilogue; r = that layer's stored relu(conv), dense bf16 [V][Cout]; dX is written densely (ld = Cout).
+ * b2_relu_gn_bwd_from_partials then runs finalize + apply without a statistics pass (workspace >= Cout*16 bytes).  */
+int b2_conv3d_igemm_bstats(const void* x, int ldx, int x_coff, const void* wpack, void* y, int N, int D, int H, int W,
+                           int Cin, int Cout, const void* r, float* stat_partial, int* n_partials,
+                           cudaStream_t stream);
+int b2_relu_gn_bwd_from_partials(const float* stat_partial, int n_partials, const void* dy, int lddy, int dy_coff,
+                                 const void* r, long long V, int C, int G, const float* gamma,
+                                 const float* mean_rstd, void* dr, float* dgamma, float* dbeta, void* workspace,
+                                 long long workspace_bytes, cudaStream_t stream);
 int b2_relu_gn_finalize(const float* stat_partial, int n_partials, long long V, int C, int G, float eps,
                         const float* gamma, const float* beta, float* mean_rstd, float* scale_shift,
                         cudaStream_t stream);
