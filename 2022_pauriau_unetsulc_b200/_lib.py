@@ -33,6 +33,8 @@ SIGNATURES = {
     "b2_maxpool3d_bwd_add": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b2_upcat_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "b2_upcat_bwd": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
+    "b2_upcat_bwd_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
+    "b2_upcat_bwd_separable": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _ll, _vp]),
     "b2_head_workspace_bytes": (_ll, [_i]),
     "b2_head_ce": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _f, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
     "b2_head_gather": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -32,9 +32,10 @@ __device__ __forceinline__ bool last_block_done(int* counter, int total) {
 // L = 256/C lanes cooperate per channel (independent loads in flight), combined in a fixed order.
 __device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int n, int nblk, int C,
                                                 double* csum) {
-  const int L = (C >= kStatThreads) ? 1 : kStatThreads / C;     // power of two (C is a power-of-two multiple of 8)
+  const int nthr = blockDim.x;
+  const int L = (C >= nthr) ? 1 : (nthr / C > 32 ? 32 : nthr / C);   // lanes per channel: power of two <= 32
   const int sub = threadIdx.x % L;
-  for (int c = threadIdx.x / L; c < C; c += kStatThreads / L) {
+  for (int c = threadIdx.x / L; c < C; c += nthr / L) {
     double a = 0.0, b = 0.0;
     const float* base = partial + ((size_t)n * nblk * C + c) * 2;
     int blk = sub;
@@ -134,7 +135,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ r, long long V, int C, float* 
 }
 
 // statistics already reduced per (CTA, warp) by the conv epilogue: one block turns them into mean/rstd, scale/shift
-__global__ void __launch_bounds__(kStatThreads)
+__global__ void __launch_bounds__(1024)
 gn_finalize_partials_kernel(const float* __restrict__ partial, int nblk, int C, int G, long long V, float eps,
                             const float* __restrict__ gamma, const float* __restrict__ beta,
                             float* __restrict__ mean_rstd, float* __restrict__ scale_shift) {
@@ -411,7 +412,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
 
 // backward statistics already reduced per CTA by the dgrad epilogue as (sum dy, sum dy*r): one block turns them into
 // the per-channel coefficients, d gamma and d beta (batch 1)
-__global__ void __launch_bounds__(kStatThreads)
+__global__ void __launch_bounds__(1024)
 gn_bwd_finalize_partials_kernel(const float* __restrict__ partial, int nblk, int C, int G, long long V,
                                 const float* __restrict__ gamma, const float* __restrict__ mean_rstd,
                                 float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -450,7 +451,7 @@ gn_bwd_finalize_partials_kernel(const float* __restrict__ partial, int nblk, int
 }
 
 static inline int stat_blocks(long long V, int C) {
-  long long nb = (V * C * 2) / 65536;   // at least 64 KB of the tensor per block
+  long long nb = (V * C * 2) / 262144;  // at least 256 KB of the tensor per block (few partials for the last block)
   if (nb > kStatBlocks) nb = kStatBlocks;
   if (nb < 1) nb = 1;
   return (int)nb;
@@ -510,7 +511,7 @@ extern "C" int b2_relu_gn_finalize(const float* stat_partial, int n_partials, lo
              "b2_relu_gn_finalize: null pointer");
   int rc = check_gn_shape("b2_relu_gn_finalize", 1, V, C, G);
   if (rc) return rc;
-  gn_finalize_partials_kernel<<<1, kStatThreads, (size_t)C * 2 * sizeof(double), stream>>>(
+  gn_finalize_partials_kernel<<<1, 1024, (size_t)C * 2 * sizeof(double), stream>>>(
       stat_partial, n_partials, C, G, V, eps, gamma, beta, mean_rstd, scale_shift);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
@@ -580,7 +581,7 @@ extern "C" int b2_relu_gn_bwd_from_partials(const float* stat_partial, int n_par
   B2_REQUIRE(workspace_bytes >= (long long)C * 4 * (long long)sizeof(float),
              "b2_relu_gn_bwd_from_partials: workspace too small");
   float* coef = reinterpret_cast<float*>(workspace);
-  gn_bwd_finalize_partials_kernel<<<1, kStatThreads, (size_t)C * 2 * sizeof(double), stream>>>(
+  gn_bwd_finalize_partials_kernel<<<1, 1024, (size_t)C * 2 * sizeof(double), stream>>>(
       stat_partial, n_partials, C, G, V, gamma, mean_rstd, coef, dgamma, dbeta);
   B2_CHECK_CUDA(cudaGetLastError());
   gn_bwd_apply_kernel<<<dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream>>>(

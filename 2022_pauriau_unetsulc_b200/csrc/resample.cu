@@ -202,6 +202,77 @@ upsample_cat_bwd_kernel(const __nv_bfloat16* __restrict__ dcat, int ldc, int cof
   }
 }
 
+// Separable adjoint, pass 1 (W): t[n, od, oh, wc, c] = sum_ow ww(wc, ow) * dcat[n, od, oh, ow, c]   (bf16 out)
+// one block per fine row (n, od, oh); instruction-light streaming pass over the big tensor.
+__global__ void __launch_bounds__(256)
+upsample_bwd_w_kernel(const __nv_bfloat16* __restrict__ dcat, int ldc, int coff, int Wo, __nv_bfloat16* __restrict__ t,
+                      int Wi, int C) {
+  __shared__ int s_cnt[kMaxUpW];
+  __shared__ int s_idx[kMaxUpW][kMaxTouch];
+  __shared__ float s_wt[kMaxUpW][kMaxTouch];
+  const int C8 = C >> 3;
+  const float sw = (float)Wi / (float)Wo;
+  for (int w = threadIdx.x; w < Wi; w += blockDim.x) {
+    int idx[kMaxTouch]; float wt[kMaxTouch];
+    const int c = touch_list(w, sw, Wi, Wo, idx, wt);
+    s_cnt[w] = c;
+    for (int k = 0; k < c; ++k) { s_idx[w][k] = idx[k] * ldc; s_wt[w][k] = wt[k]; }
+  }
+  __syncthreads();
+  const __nv_bfloat16* rp = dcat + (size_t)blockIdx.x * Wo * ldc + coff;
+  __nv_bfloat16* out = t + (size_t)blockIdx.x * Wi * C;
+  const int total = Wi * C8;
+  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+    const int w = e / C8, oc = (e - w * C8) * 8;
+    const int nw = s_cnt[w];
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int c = 0; c < nw; ++c) {
+      const float wgt = s_wt[w][c];
+      const f8 g = unpack8(ldg16(rp + s_idx[w][c] + oc));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, g.v[k], acc[k]);
+    }
+    f8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = acc[k];
+    stg16(out + (size_t)w * C + oc, pack8(o));
+  }
+}
+
+// pass 2 (H, D): dx[n, d, h, w, c] = sum_{od, oh} wd * wh * t[n, od, oh, w, c]; one block per coarse row (n, d, h)
+__global__ void __launch_bounds__(256)
+upsample_bwd_hd_kernel(const __nv_bfloat16* __restrict__ t, int Do, int Ho, __nv_bfloat16* __restrict__ dx, int Di,
+                       int Hi, int Wi, int C) {
+  const int row = blockIdx.x;
+  const int h = row % Hi, d = (row / Hi) % Di, n = row / (Hi * Di);
+  const float sd = (float)Di / (float)Do, shh = (float)Hi / (float)Ho;
+  int didx[kMaxTouch], hidx[kMaxTouch];
+  float dwt[kMaxTouch], hwt[kMaxTouch];
+  const int nd = touch_list(d, sd, Di, Do, didx, dwt);
+  const int nh = touch_list(h, shh, Hi, Ho, hidx, hwt);
+  const int rowlen = Wi * C;           // elements per (od, oh) row of t
+  const __nv_bfloat16* tb = t + (size_t)n * Do * Ho * rowlen;
+  __nv_bfloat16* out = dx + (size_t)row * rowlen;
+  for (int e = threadIdx.x * 8; e < rowlen; e += blockDim.x * 8) {
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int a = 0; a < nd; ++a)
+      for (int b = 0; b < nh; ++b) {
+        const float wgt = dwt[a] * hwt[b];
+        const f8 g = unpack8(ldg16(tb + ((size_t)didx[a] * Ho + hidx[b]) * rowlen + e));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, g.v[k], acc[k]);
+      }
+    f8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = acc[k];
+    stg16(out + e, pack8(o));
+  }
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -229,6 +300,30 @@ extern "C" int b2_upcat_fwd(const void* x, int N, int Di, int Hi, int Wi, int C,
   upsample_cat_fwd_kernel<<<(unsigned)(N * Do * Ho), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, Di, Hi,
                                                                 Wi, C, reinterpret_cast<__nv_bfloat16*>(cat), ldc, coff,
                                                                 Do, Ho, Wo);
+  B2_CHECK_CUDA(cudaGetLastError());
+  return B2_OK;
+}
+
+extern "C" long long b2_upcat_bwd_workspace_bytes(int N, int Do, int Ho, int Wi, int C) {
+  return (long long)N * Do * Ho * Wi * C * 2;
+}
+
+// separable variant: W pass into `workspace` (bf16 [N][Do][Ho][Wi][C]), then the H/D pass
+extern "C" int b2_upcat_bwd_separable(const void* dcat, int ldc, int coff, int N, int Do, int Ho, int Wo, void* dx,
+                                      int Di, int Hi, int Wi, int C, void* workspace, long long workspace_bytes,
+                                      cudaStream_t stream) {
+  B2_REQUIRE(dcat && dx && workspace, "b2_upcat_bwd_separable: null pointer");
+  B2_REQUIRE(C % 8 == 0 && ldc % 8 == 0 && coff % 8 == 0, "b2_upcat_bwd_separable: channel counts must be multiples of 8");
+  B2_REQUIRE(Wo <= kMaxUpW && Wi <= kMaxUpW, "b2_upcat_bwd_separable: row width %d > %d", Wo, kMaxUpW);
+  B2_REQUIRE(2 * Do <= 7 * Di && 2 * Ho <= 7 * Hi && 2 * Wo <= 7 * Wi, "b2_upcat_bwd_separable: ratio > 3.5 unsupported");
+  B2_REQUIRE((long long)Wo * ldc < (1LL << 31) && (long long)Wi * C < (1LL << 31), "b2_upcat_bwd_separable: row too large");
+  B2_REQUIRE(workspace_bytes >= b2_upcat_bwd_workspace_bytes(N, Do, Ho, Wi, C), "b2_upcat_bwd_separable: workspace too small");
+  __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(workspace);
+  upsample_bwd_w_kernel<<<(unsigned)(N * Do * Ho), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dcat), ldc,
+                                                                      coff, Wo, t, Wi, C);
+  B2_CHECK_CUDA(cudaGetLastError());
+  upsample_bwd_hd_kernel<<<(unsigned)(N * Di * Hi), 256, 0, stream>>>(t, Do, Ho, reinterpret_cast<__nv_bfloat16*>(dx),
+                                                                      Di, Hi, Wi, C);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }

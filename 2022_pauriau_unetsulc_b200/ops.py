@@ -275,13 +275,19 @@ def upcat_fwd(x, cat_window):
     _count(1)
 
 
-def upcat_bwd(dcat_window, Di, Hi, Wi):
+def upcat_bwd(dcat_window, Di, Hi, Wi, separable=True):
     lib = _lib.load()
     c = dcat_window
     dx = ActView.alloc(c.N, Di, Hi, Wi, c.C, c.buf.device)
-    _lib.check(lib.b2_upcat_bwd(_p(c.buf), c.ld, c.coff, c.N, c.D, c.H, c.W, _p(dx.buf), Di, Hi, Wi, c.C, _s()),
-               "b2_upcat_bwd")
-    _count(1)
+    if separable:
+        ws = Workspace.get(lib.b2_upcat_bwd_workspace_bytes(c.N, c.D, c.H, Wi, c.C), c.buf.device, "upbwd")
+        _lib.check(lib.b2_upcat_bwd_separable(_p(c.buf), c.ld, c.coff, c.N, c.D, c.H, c.W, _p(dx.buf), Di, Hi, Wi,
+                                              c.C, _p(ws), ws.numel(), _s()), "b2_upcat_bwd_separable")
+        _count(2)
+    else:
+        _lib.check(lib.b2_upcat_bwd(_p(c.buf), c.ld, c.coff, c.N, c.D, c.H, c.W, _p(dx.buf), Di, Hi, Wi, c.C, _s()),
+                   "b2_upcat_bwd")
+        _count(1)
     return dx
 
 

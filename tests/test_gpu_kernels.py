@@ -372,9 +372,10 @@ def test_upsample_concat_fwd_bwd(din, dout):
     assert bool((cat[..., :Cs] == 0).all())
     dcat = bf16_round(torch.randn(N, Cs + C, *dout, device="cuda", generator=g))
     ref.backward(dcat[:, Cs:])
-    dx = ops.upcat_bwd(ops.ActView(to_ndhwc(dcat), N, *dout, C, ld=Cs + C, coff=Cs), *din)
-    torch.cuda.synchronize()
-    assert rel_l2(from_view(dx), x.grad) < 4e-3
+    for separable in (False, True):
+        dx = ops.upcat_bwd(ops.ActView(to_ndhwc(dcat), N, *dout, C, ld=Cs + C, coff=Cs), *din, separable=separable)
+        torch.cuda.synchronize()
+        assert rel_l2(from_view(dx), x.grad) < 4e-3, separable
 
 
 def _head_inputs(seed, N=1, D=6, H=7, W=8, Cin=64, Cout=56, frac=0.2):
