@@ -39,6 +39,10 @@ struct IgemmParams {
   const __nv_bfloat16* stat_r;  // when set, the statistics are (sum dy, sum dy*r) with r = this dense [V][Cout]
                                 // tensor: the two per-channel sums GroupNorm backward needs (dgrad launches)
   long long total_tiles;
+  // split-K over the 27 taps for layers with fewer tiles than SMs (12x14x12 level): work item = (split, tile);
+  // every split writes an fp32 partial tile to y32 + split * split_stride, reduced by conv_splitk_reduce_kernel
+  int splits;
+  long long split_stride;
 };
 
 static constexpr int kProducerPairs = 4;
@@ -109,10 +113,12 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int me = (warp - 1) >> 1;
     const bool loads_a = ((warp - 1) & 1) == 0;
     uint32_t gs = 0;  // global stage counter, identical in every producer and in the MMA issuer
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (long long work = blockIdx.x; work < p.total_tiles * p.splits; work += gridDim.x) {
       int n, d0, h0, w0, n0;
-      decode_tile(tile, p, n, d0, h0, w0, n0);
-      for (int tap = 0; tap < 27; ++tap) {
+      decode_tile(work % p.total_tiles, p, n, d0, h0, w0, n0);
+      const int split = (int)(work / p.total_tiles);
+      const int tap_end = 27 * (split + 1) / p.splits;
+      for (int tap = 27 * split / p.splits; tap < tap_end; ++tap) {
         const int dd = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
         for (int ch = 0; ch < p.n_chunks; ++ch, ++gs) {
           if ((int)(gs % kProducerPairs) != me) continue;
@@ -141,11 +147,12 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint64_t desc_hi = make_smem_desc(0, 16, kSbo, kLayout);           // everything but the start address
     const uint32_t a0 = smem_u32(smem_a) >> 4, b0 = smem_u32(smem_b) >> 4;   // encoded start addresses of stage 0
     const uint32_t a_step = kABytes >> 4, b_step = (uint32_t)p.b_bytes >> 4;
-    const int n_stage_per_tile = 27 * p.n_chunks;
     int stage = 0;
     uint32_t phase = 0;
     uint32_t it = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (long long work = blockIdx.x; work < p.total_tiles * p.splits; work += gridDim.x, ++it) {
+      const int split = (int)(work / p.total_tiles);
+      const int n_stage_per_tile = (27 * (split + 1) / p.splits - 27 * split / p.splits) * p.n_chunks;
       const uint32_t acc = it & 1u;
       const uint32_t acc_phase = (it >> 1) & 1u;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -181,9 +188,10 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
     for (int i = 0; i < 8; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
     uint32_t it = 0;
-    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (long long work = blockIdx.x; work < p.total_tiles * p.splits; work += gridDim.x, ++it) {
       int n, d0, h0, w0, n0;
-      decode_tile(tile, p, n, d0, h0, w0, n0);
+      decode_tile(work % p.total_tiles, p, n, d0, h0, w0, n0);
+      float* y32 = p.y32 ? p.y32 + (work / p.total_tiles) * p.split_stride : nullptr;
       const uint32_t acc = it & 1u;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int w = w0 + lw, h = h0 + lh, d = d0 + ld;
@@ -229,8 +237,8 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           st_q[chunk] += xq[0];
         }
         if (valid) {
-          if (p.y32 != nullptr) {
-            float4* dst = reinterpret_cast<float4*>(p.y32 + vox * p.ldy + p.y_coff + n0 + c0);
+          if (y32 != nullptr) {
+            float4* dst = reinterpret_cast<float4*>(y32 + vox * p.ldy + p.y_coff + n0 + c0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 o;
@@ -289,6 +297,29 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
+// out[v, c] = (relu)(sum_s partial[s][v][c]) -> bf16 channel window
+__global__ void __launch_bounds__(256)
+conv_splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long split_stride, long long NV, int C,
+                          int relu, __nv_bfloat16* __restrict__ y, int ldy, int y_coff) {
+  const int C4 = C >> 2;
+  const long long total = NV * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i / C4;
+    const int c = (int)(i % C4) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 t = *reinterpret_cast<const float4*>(partial + s * split_stride + v * C + c);
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    uint2 o;
+    o.x = pack_bf16x2(a.x, a.y);
+    o.y = pack_bf16x2(a.z, a.w);
+    *reinterpret_cast<uint2*>(y + v * ldy + y_coff + c) = o;
+  }
+}
+
 // choose the (bw, bh, bd) box with bw*bh*bd == 128 that wastes the fewest padded voxels
 static void choose_box(int W, int H, int D, int& bw, int& bh, int& bd) {
   long long best = -1;
@@ -332,7 +363,8 @@ using namespace b2;
 // See include/unetsulc_b200.h for the contract.
 static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff,
                              int y_is_fp32, int N, int D, int H, int W, int Cin, int Cout, int relu,
-                             float* stat_partial, const void* stat_r, int* n_partials, cudaStream_t stream) {
+                             float* stat_partial, const void* stat_r, int* n_partials, void* splitk_workspace,
+                             long long splitk_workspace_bytes, cudaStream_t stream) {
   B2_REQUIRE(x && wpack && y, "b2_conv3d_igemm: null pointer");
   B2_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "b2_conv3d_igemm: bad shape %dx%dx%dx%d", N, D, H, W);
   B2_REQUIRE(Cin % 32 == 0 && Cin >= 32, "b2_conv3d_igemm: Cin=%d must be a multiple of 32", Cin);
@@ -375,7 +407,22 @@ static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpa
   p.ldy = ldy; p.y_coff = y_coff;
   p.y = y_is_fp32 ? nullptr : reinterpret_cast<__nv_bfloat16*>(y);
   p.y32 = y_is_fp32 ? reinterpret_cast<float*>(y) : nullptr;
+  const int user_ldy = ldy, user_coff = y_coff, user_relu = relu;
   p.total_tiles = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles_n;
+  p.splits = 1;
+  p.split_stride = 0;
+  // split-K over taps when the layer has too few tiles to fill the machine (needs a caller-provided fp32 workspace)
+  float* splitk_ws = nullptr;
+  if (!y_is_fp32 && !stat_partial && splitk_workspace && p.total_tiles * 2 <= num_sms()) {
+    int sp = (int)(num_sms() / p.total_tiles);
+    if (sp > 9) sp = 9;
+    const long long need = (long long)sp * N * D * H * W * Cout * (long long)sizeof(float);
+    if (sp >= 2 && need <= splitk_workspace_bytes) {
+      p.splits = sp;
+      p.split_stride = (long long)N * D * H * W * Cout;
+      splitk_ws = reinterpret_cast<float*>(splitk_workspace);
+    }
+  }
   p.stat_partial = stat_partial;
   p.stat_r = reinterpret_cast<const __nv_bfloat16*>(stat_r);
   if (stat_partial) {
@@ -394,7 +441,15 @@ static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpa
     if (rc) return rc;
   }
   const size_t smem_bytes = (size_t)p.stages * (p.a_bytes + p.b_bytes) + 1024 + 512;
-  long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  if (p.splits > 1) {   // partial tiles: dense fp32 [split][voxel][Cout], no ReLU before the reduction
+    p.y = nullptr;
+    p.y32 = splitk_ws;
+    p.ldy = Cout;
+    p.y_coff = 0;
+    p.relu = 0;
+  }
+  const long long work_items = p.total_tiles * p.splits;
+  long long grid = work_items < num_sms() ? work_items : num_sms();
   if (p.KC == 64) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     conv3d_igemm_kernel<64><<<(unsigned)grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
@@ -403,6 +458,15 @@ static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpa
     conv3d_igemm_kernel<32><<<(unsigned)grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
   }
   B2_CHECK_CUDA(cudaGetLastError());
+  if (p.splits > 1) {
+    const long long NV = (long long)N * D * H * W;
+    long long rb = (NV * (Cout / 4) + 255) / 256;
+    if (rb > num_sms() * 8) rb = num_sms() * 8;
+    conv_splitk_reduce_kernel<<<(unsigned)rb, 256, 0, stream>>>(splitk_ws, p.splits, p.split_stride, NV, Cout,
+                                                                user_relu, reinterpret_cast<__nv_bfloat16*>(y),
+                                                                user_ldy, user_coff);
+    B2_CHECK_CUDA(cudaGetLastError());
+  }
   if (n_partials) *n_partials = (int)grid;
   return B2_OK;
 }
@@ -412,7 +476,19 @@ extern "C" int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* w
                                int y_is_fp32, int N, int D, int H, int W, int Cin, int Cout, int relu,
                                cudaStream_t stream) {
   return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, ldy, y_coff, y_is_fp32, N, D, H, W, Cin, Cout, relu, nullptr,
-                           nullptr, nullptr, stream);
+                           nullptr, nullptr, nullptr, 0, stream);
+}
+
+// Same as b2_conv3d_igemm with an optional fp32 workspace: layers with fewer than num_SMs/2 output tiles are split
+// over the 27 taps (split-K, up to 9 ways) into the workspace and reduced (+ReLU, bf16) by a second kernel.
+extern "C" long long b2_conv3d_splitk_workspace_bytes(int N, int D, int H, int W, int Cout) {
+  return 9LL * N * D * H * W * Cout * (long long)sizeof(float);
+}
+extern "C" int b2_conv3d_igemm_splitk(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy,
+                                      int y_coff, int N, int D, int H, int W, int Cin, int Cout, int relu,
+                                      void* workspace, long long workspace_bytes, cudaStream_t stream) {
+  return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, ldy, y_coff, 0, N, D, H, W, Cin, Cout, relu, nullptr, nullptr,
+                           nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" int b2_conv3d_stats_max_partials(void) { return num_sms(); }
@@ -424,7 +500,7 @@ extern "C" int b2_conv3d_igemm_stats(const void* x, int ldx, int x_coff, const v
                                      float* stat_partial, int* n_partials, cudaStream_t stream) {
   B2_REQUIRE(stat_partial && n_partials, "b2_conv3d_igemm_stats: null pointer");
   return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, ldy, y_coff, 0, N, D, H, W, Cin, Cout, relu, stat_partial,
-                           nullptr, n_partials, stream);
+                           nullptr, n_partials, nullptr, 0, stream);
 }
 
 // dgrad (x = dY, wpack = dgrad pack, output dX written densely) with the GroupNorm-BACKWARD statistics of the layer
@@ -435,6 +511,6 @@ extern "C" int b2_conv3d_igemm_bstats(const void* x, int ldx, int x_coff, const 
                                       int* n_partials, cudaStream_t stream) {
   B2_REQUIRE(stat_partial && n_partials && r, "b2_conv3d_igemm_bstats: null pointer");
   return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, Cout, 0, 0, N, D, H, W, Cin, Cout, 0, stat_partial, r,
-                           n_partials, stream);
+                           n_partials, nullptr, 0, stream);
 }
 

@@ -94,7 +94,7 @@ __device__ __forceinline__ void load_head_weights(const float* __restrict__ W, c
 }
 
 // ------------------------------------------------------------------------------------------------- fused head + CE
-// partial layout per block: [Cout*Cin dW][kMaxCo db][loss]
+// partial layout per block: [Cin][kMaxCo] dW (transposed, bank-conflict-free) | [kMaxCo] db | loss
 template <int CIN>
 __global__ void __launch_bounds__(kCeThreads)
 head_ce_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ labels, long long NV,
@@ -186,9 +186,9 @@ head_ce_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict_
     if (warp == w) {
       if (compute_grad) {
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
-          red[lane * CIN + ci] += accW0[ci];
-          red[(lane + 32) * CIN + ci] += accW1[ci];
+        for (int ci = 0; ci < CIN; ++ci) {   // [ci][co] layout: lanes hit consecutive banks
+          red[ci * kMaxCo + lane] += accW0[ci];
+          red[ci * kMaxCo + lane + 32] += accW1[ci];
         }
         red[kMaxCo * CIN + lane] += accb0;
         red[kMaxCo * CIN + lane + 32] += accb1;
@@ -210,7 +210,8 @@ __global__ void head_ce_finalize_kernel(const float* __restrict__ partial, int n
   double acc = 0.0;
   for (int bidx = 0; bidx < nblocks; ++bidx) acc += (double)partial[(size_t)bidx * stride + i];
   if (i < kMaxCo * Cin) {
-    if (dW && i < Cout * Cin) dW[i] = (float)acc;
+    const int ci = i / kMaxCo, co = i % kMaxCo;   // partials are laid out [ci][co]
+    if (dW && co < Cout) dW[co * Cin + ci] = (float)acc;
   } else if (i < kMaxCo * Cin + kMaxCo) {
     const int co = i - kMaxCo * Cin;
     if (db && co < Cout) db[co] = (float)acc;

@@ -196,12 +196,12 @@ class UNet3D(nn.Module):
             if first:
                 ops.conv3d_first_fwd(xin, layer.conv.weight.detach(), r, relu=True)
                 mr, ss = ops.relu_gn_stats(r, G, layer.norm.eps, gamma, beta)
-            elif B == 1 and cout <= 256:
+            elif B == 1 and cout <= 256 and B * d * h * w > ops.SPLITK_MAX_VOXELS:
                 wf, _ = layer.packs()   # GroupNorm statistics come out of the conv epilogue
                 mr, ss = ops.conv3d_igemm_gn_stats(xin, wf, r, cin, cout, G, layer.norm.eps, gamma, beta)
             else:
                 wf, _ = layer.packs()
-                ops.conv3d_igemm(xin, wf, r, cin, cout, relu=True)
+                ops.conv3d_igemm_auto(xin, wf, r, cin, cout, relu=True)   # split-K when the volume is tiny
                 mr, ss = ops.relu_gn_stats(r, G, layer.norm.eps, gamma, beta)
             ops.relu_gn_apply(r, ss, out_view, pooled)
             rec.append(dict(x=xin, r=r, mr=mr))
@@ -291,11 +291,11 @@ class UNet3D(nn.Module):
             xin = rc["x"]
             dx = ActView.alloc(xin.N, xin.D, xin.H, xin.W, layer.cin, dr.buf.device)
             _, wd = layer.packs()
-            if i % 2 == 1 and B == 1 and layer.cin <= 256:
+            if i % 2 == 1 and B == 1 and layer.cin <= 256 and xin.N * xin.V > ops.SPLITK_MAX_VOXELS:
                 # conv2 of a block: dx IS the gradient at conv1's GroupNorm output -> fuse its backward statistics
                 stats = ops.conv3d_dgrad_gn_bstats(dr, wd, dx, layer.cout, layer.cin, rec[i - 1]["r"])
                 return dx, stats
-            ops.conv3d_igemm(dr, wd, dx, layer.cout, layer.cin, relu=False)
+            ops.conv3d_igemm_auto(dr, wd, dx, layer.cout, layer.cin, relu=False)
             return dx
 
         dy = dfeat

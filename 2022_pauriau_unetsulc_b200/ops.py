@@ -119,6 +119,23 @@ def conv3d_igemm(x, wpack, y, cin, cout, relu, y_fp32=False):
     _count(1)
 
 
+SPLITK_MAX_VOXELS = 8192   # below this the layer cannot fill 148 SMs with 128-voxel tiles
+
+
+def conv3d_igemm_auto(x, wpack, y, cin, cout, relu):
+    """conv3d_igemm that switches to the split-K path for very small volumes (the 12x14x12 level)."""
+    if x.N * x.V > SPLITK_MAX_VOXELS:
+        return conv3d_igemm(x, wpack, y, cin, cout, relu)
+    lib = _lib.load()
+    _need_cuda(x.buf, wpack, y.buf)
+    ws = Workspace.get(lib.b2_conv3d_splitk_workspace_bytes(x.N, x.D, x.H, x.W, cout), x.buf.device, "splitk")
+    with _Prof("conv3d_igemm", 2.0 * x.N * x.V * 27 * cin * cout):
+        _lib.check(lib.b2_conv3d_igemm_splitk(_p(x.buf), x.ld, x.coff, _p(wpack), _p(y.buf), y.ld, y.coff, x.N, x.D,
+                                              x.H, x.W, cin, cout, int(relu), _p(ws), ws.numel(), _s()),
+                   "b2_conv3d_igemm_splitk")
+    _count(2)
+
+
 def conv3d_igemm_gn_stats(x, wpack, y, cin, cout, groups, eps, gamma, beta):
     """fprop + ReLU with the GroupNorm statistics fused into the conv epilogue (batch 1, cout <= 256).
     Returns (mean_rstd [1,C,2], scale_shift [1,C,2]) like relu_gn_stats, without re-reading the output tensor."""

@@ -32,6 +32,13 @@ const char* b2_last_error(void);
 int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff,
                     int y_is_fp32, int N, int D, int H, int W, int Cin, int Cout, int relu, cudaStream_t stream);
 
+/* b2_conv3d_igemm with an fp32 workspace: layers with fewer output tiles than half the SMs (12x14x12 level) are split
+ * over the 27 taps (split-K) into the workspace and reduced (+ReLU, bf16) by a second kernel.                      */
+long long b2_conv3d_splitk_workspace_bytes(int N, int D, int H, int W, int Cout);
+int b2_conv3d_igemm_splitk(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff, int N,
+                           int D, int H, int W, int Cin, int Cout, int relu, void* workspace,
+                           long long workspace_bytes, cudaStream_t stream);
+
 /* fprop with the GroupNorm statistics of the stored (bf16, post-ReLU) output fused into the epilogue (batch 1, Cout
  * <= 256).  stat_partial: fp32 [b2_conv3d_stats_max_partials()][Cout][2]; *n_partials (HOST int) = rows written;
  * b2_relu_gn_finalize turns them into mean/rstd and scale/shift (replaces b2_relu_gn_stats, saves one tensor read). */

@@ -146,6 +146,32 @@ def test_conv_epilogue_groupnorm_statistics(shape):
     assert rel_l2(from_view(y), ref) < 4e-3
 
 
+@pytest.mark.parametrize("shape", [(1, 256, 512, 12, 14, 12), (1, 256, 256, 6, 7, 6), (1, 64, 128, 5, 7, 9),
+                                   (1, 128, 64, 3, 4, 5)])
+def test_conv_splitk_small_volumes(shape):
+    """fewer output tiles than half the SMs: split-K over the 27 taps + fp32 reduce (+ReLU) kernel."""
+    ops = _ops()
+    N, Cin, Cout, D, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(61)
+    x = bf16_round(torch.randn(N, Cin, D, H, W, device="cuda", generator=g))
+    w = bf16_round(torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=g) * (1.0 / (27 * Cin) ** 0.5))
+    wf, wd = ops.pack_conv_weights(w)
+    wide = torch.full((N, D, H, W, Cout + 16), 5.0, device="cuda", dtype=torch.bfloat16)
+    yv = ops.ActView(wide, N, D, H, W, Cout, ld=Cout + 16, coff=8)
+    ops.conv3d_igemm_auto(ops.ActView(to_ndhwc(x), N, D, H, W, Cin), wf, yv, Cin, Cout, relu=True)
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv3d(x, w, padding=1))
+    assert rel_l2(from_view(yv), ref) < 2e-3
+    assert bool((wide[..., :8] == 5.0).all()) and bool((wide[..., Cout + 8:] == 5.0).all())
+    dy = bf16_round(torch.randn(N, Cout, D, H, W, device="cuda", generator=g))
+    xq = torch.zeros(N, Cin, D, H, W, device="cuda", requires_grad=True)
+    F.conv3d(xq, w, padding=1).backward(dy)
+    dx = ops.ActView.alloc(N, D, H, W, Cin, "cuda", zero=True)
+    ops.conv3d_igemm_auto(ops.ActView(to_ndhwc(dy), N, D, H, W, Cout), wd, dx, Cout, Cin, relu=False)
+    torch.cuda.synchronize()
+    assert rel_l2(from_view(dx), xq.grad) < 2e-3
+
+
 def test_conv_fprop_channel_windows():
     """input read from / output written into channel windows of wider buffers (concat buffers)."""
     ops = _ops()
