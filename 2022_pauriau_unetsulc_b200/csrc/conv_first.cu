@@ -88,15 +88,21 @@ conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
       r /= H;
       const int dq = (int)(r % D);
       const long long nbase = (r / D) * (long long)D * H * W;
+      // issue all 27 row loads first (independent, predicated), then accumulate: the loop is latency-bound otherwise
+      float g0[27], g1[27];
 #pragma unroll
       for (int tap = 0; tap < 27; ++tap) {
         // output voxel v with v + off(tap) = u
         const int d = dq - (tap / 9 - 1), h = hq - ((tap / 3) % 3 - 1), ww = wq - (tap % 3 - 1);
-        if ((unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)ww < (unsigned)W) {   // warp-uniform
-          const __nv_bfloat16* row = dyc + (nbase + ((long long)d * H + h) * W + ww) * lddy;
-          if (has0) acc0[tap] = fmaf(xv, __bfloat162float(row[lane]), acc0[tap]);
-          if (has1) acc1[tap] = fmaf(xv, __bfloat162float(row[lane + 32]), acc1[tap]);
-        }
+        const bool ok = (unsigned)d < (unsigned)D && (unsigned)h < (unsigned)H && (unsigned)ww < (unsigned)W;
+        const __nv_bfloat16* row = dyc + (nbase + ((long long)(ok ? d : dq) * H + (ok ? h : hq)) * W + (ok ? ww : wq)) * lddy;
+        g0[tap] = (ok && has0) ? __bfloat162float(row[lane]) : 0.f;
+        g1[tap] = (ok && has1) ? __bfloat162float(row[lane + 32]) : 0.f;
+      }
+#pragma unroll
+      for (int tap = 0; tap < 27; ++tap) {
+        acc0[tap] = fmaf(xv, g0[tap], acc0[tap]);
+        acc1[tap] = fmaf(xv, g1[tap], acc1[tap]);
       }
     }
   }
