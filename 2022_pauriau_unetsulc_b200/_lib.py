@@ -25,6 +25,8 @@ SIGNATURES = {
     "b2_conv3d_wgrad_workspace_bytes": (_ll, [_i, _i, _i, _i, _i, _i]),
     "b2_conv3d_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
     "b2_conv3d_first_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b2_conv3d_first_stats_max_partials": (_i, []),
+    "b2_conv3d_first_fwd_stats": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b2_conv3d_first_wgrad_workspace_bytes": (_ll, [_i]),
     "b2_conv3d_first_wgrad": (_i, [_vp, _vp, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     "b2_gn_workspace_bytes": (_ll, [_i, _i]),

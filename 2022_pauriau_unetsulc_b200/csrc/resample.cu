@@ -135,6 +135,98 @@ upsample_cat_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int Di, int 
   }
 }
 
+// Exact 2x upsampling (every level of a volume whose sides are multiples of 8): src = dst/2 - 0.25, so the fine
+// samples 2j+1 and 2j+2 both interpolate between the coarse samples j and j+1 with weights (.75,.25) / (.25,.75).
+// One thread per CELL (jd, jh, jw) in [-1, Di-1] x [-1, Hi-1] x [-1, Wi-1] and channel octet: 8 coarse loads feed
+// 8 fine stores (the generic kernel needs 8 loads per store).  Edge cells clamp the coarse index exactly like
+// src_index does (fine 0 = coarse 0 with weights (1,0); the last fine sample = .75*a + .25*a of the last coarse one).
+struct Cell2x {
+  int c0, c1;      // coarse indices
+  int f[2];        // fine indices (2j+1, 2j+2), -1 when outside
+  float l0[2], l1[2];
+};
+__device__ __forceinline__ Cell2x cell2x(int j, int n_in) {
+  Cell2x c;
+  c.c0 = j < 0 ? 0 : j;
+  c.c1 = (j + 1 > n_in - 1) ? n_in - 1 : j + 1;
+  c.f[0] = j >= 0 ? 2 * j + 1 : -1;
+  c.f[1] = (j + 1 <= n_in - 1) ? 2 * j + 2 : -1;
+  c.l0[0] = 0.75f; c.l1[0] = 0.25f;
+  c.l0[1] = j < 0 ? 1.f : 0.25f;
+  c.l1[1] = j < 0 ? 0.f : 0.75f;
+  return c;
+}
+
+__global__ void __launch_bounds__(256)
+upsample2x_cat_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int Di, int Hi, int Wi, int C,
+                          __nv_bfloat16* __restrict__ cat, int ldc, int coff) {
+  const int C8 = C >> 3;
+  const int Do = 2 * Di, Ho = 2 * Hi, Wo = 2 * Wi;
+  const long long total = (long long)N * (Di + 1) * (Hi + 1) * (Wi + 1) * C8;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int oc = (int)(i % C8) * 8;
+  long long t = i / C8;
+  const int jw = (int)(t % (Wi + 1)) - 1; t /= (Wi + 1);
+  const int jh = (int)(t % (Hi + 1)) - 1; t /= (Hi + 1);
+  const int jd = (int)(t % (Di + 1)) - 1;
+  const int n = (int)(t / (Di + 1));
+  const Cell2x cd = cell2x(jd, Di), ch = cell2x(jh, Hi), cw = cell2x(jw, Wi);
+  const __nv_bfloat16* xb = x + (size_t)n * Di * Hi * Wi * C + oc;
+  uint4 a[2][2][2];
+#pragma unroll
+  for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+    for (int hz = 0; hz < 2; ++hz)
+#pragma unroll
+      for (int wz = 0; wz < 2; ++wz)
+        a[dz][hz][wz] = ldg16(xb + (((size_t)(dz ? cd.c1 : cd.c0) * Hi + (hz ? ch.c1 : ch.c0)) * Wi +
+                                    (wz ? cw.c1 : cw.c0)) * C);
+  uint32_t o[2][2][2][4];   // [fd][fh][fw][channel pair]
+#pragma unroll
+  for (int cp = 0; cp < 4; ++cp) {
+    float lo[2][2][2], hi[2][2][2];
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int hz = 0; hz < 2; ++hz)
+#pragma unroll
+        for (int wz = 0; wz < 2; ++wz) {
+          const uint4& u = a[dz][hz][wz];
+          const uint32_t wd = cp == 0 ? u.x : (cp == 1 ? u.y : (cp == 2 ? u.z : u.w));
+          lo[dz][hz][wz] = __uint_as_float(wd << 16);
+          hi[dz][hz][wz] = __uint_as_float(wd & 0xffff0000u);
+        }
+#pragma unroll
+    for (int fd = 0; fd < 2; ++fd)
+#pragma unroll
+      for (int fh = 0; fh < 2; ++fh)
+#pragma unroll
+        for (int fw = 0; fw < 2; ++fw) {
+          const float lw0 = cw.l0[fw], lw1 = cw.l1[fw], lh0 = ch.l0[fh], lh1 = ch.l1[fh];
+          const float ld0 = cd.l0[fd], ld1 = cd.l1[fd];
+          // same association order as ATen's upsample_trilinear3d kernel (and upsample_cat_fwd_kernel)
+          const float vl = ld0 * (lh0 * (lw0 * lo[0][0][0] + lw1 * lo[0][0][1]) + lh1 * (lw0 * lo[0][1][0] + lw1 * lo[0][1][1])) +
+                           ld1 * (lh0 * (lw0 * lo[1][0][0] + lw1 * lo[1][0][1]) + lh1 * (lw0 * lo[1][1][0] + lw1 * lo[1][1][1]));
+          const float vh = ld0 * (lh0 * (lw0 * hi[0][0][0] + lw1 * hi[0][0][1]) + lh1 * (lw0 * hi[0][1][0] + lw1 * hi[0][1][1])) +
+                           ld1 * (lh0 * (lw0 * hi[1][0][0] + lw1 * hi[1][0][1]) + lh1 * (lw0 * hi[1][1][0] + lw1 * hi[1][1][1]));
+          __nv_bfloat162 pk = __floats2bfloat162_rn(vl, vh);
+          o[fd][fh][fw][cp] = *reinterpret_cast<uint32_t*>(&pk);
+        }
+  }
+  __nv_bfloat16* ob = cat + (size_t)n * Do * Ho * Wo * ldc + coff + oc;
+#pragma unroll
+  for (int fd = 0; fd < 2; ++fd)
+#pragma unroll
+    for (int fh = 0; fh < 2; ++fh)
+#pragma unroll
+      for (int fw = 0; fw < 2; ++fw) {
+        if (cd.f[fd] < 0 || ch.f[fh] < 0 || cw.f[fw] < 0) continue;
+        const size_t v = ((size_t)cd.f[fd] * Ho + ch.f[fh]) * Wo + cw.f[fw];
+        stg16(ob + v * ldc, make_uint4(o[fd][fh][fw][0], o[fd][fh][fw][1], o[fd][fh][fw][2], o[fd][fh][fw][3]));
+      }
+}
+
 // fine samples whose interpolation touches coarse index i, with their weights (exact: same src_index as forward)
 __device__ __forceinline__ int touch_list(int i, float scale, int in_size, int out_size, int* idx, float* wt) {
   const float a = ((float)i - 0.5f) / scale - 0.5f;
@@ -297,6 +389,13 @@ extern "C" int b2_upcat_fwd(const void* x, int N, int Di, int Hi, int Wi, int C,
   B2_REQUIRE(C % 8 == 0 && ldc % 8 == 0 && coff % 8 == 0, "b2_upcat_fwd: channel counts must be multiples of 8");
   B2_REQUIRE(Wo <= kMaxUpW && Wi <= kMaxUpW, "b2_upcat_fwd: row width %d > %d", Wo, kMaxUpW);
   B2_REQUIRE((long long)Wi * C < (1LL << 31) && (long long)Wo * ldc < (1LL << 31), "b2_upcat_fwd: row too large");
+  if (Do == 2 * Di && Ho == 2 * Hi && Wo == 2 * Wi) {
+    const long long total = (long long)N * (Di + 1) * (Hi + 1) * (Wi + 1) * (C / 8);
+    upsample2x_cat_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), N, Di, Hi, Wi, C, reinterpret_cast<__nv_bfloat16*>(cat), ldc, coff);
+    B2_CHECK_CUDA(cudaGetLastError());
+    return B2_OK;
+  }
   upsample_cat_fwd_kernel<<<(unsigned)(N * Do * Ho), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, Di, Hi,
                                                                 Wi, C, reinterpret_cast<__nv_bfloat16*>(cat), ldc, coff,
                                                                 Do, Ho, Wo);

@@ -193,7 +193,10 @@ class UNet3D(nn.Module):
             d, h, w = (out_view.D, out_view.H, out_view.W)
             r = ActView.alloc(B, d, h, w, cout, dev)
             gamma, beta = layer.norm.weight.detach(), layer.norm.bias.detach()
-            if first:
+            if first and B == 1:
+                mr, ss = ops.conv3d_first_fwd_gn_stats(xin, layer.conv.weight.detach(), r, G, layer.norm.eps, gamma,
+                                                       beta)
+            elif first:
                 ops.conv3d_first_fwd(xin, layer.conv.weight.detach(), r, relu=True)
                 mr, ss = ops.relu_gn_stats(r, G, layer.norm.eps, gamma, beta)
             elif B == 1 and cout <= 256 and B * d * h * w > ops.SPLITK_MAX_VOXELS:

@@ -219,6 +219,24 @@ def conv3d_first_fwd(x, w, y, relu=True):
     _count(1)
 
 
+def conv3d_first_fwd_gn_stats(x, w, y, groups, eps, gamma, beta):
+    """first conv + ReLU with the GroupNorm statistics fused in (batch 1).  Returns (mean_rstd, scale_shift)."""
+    lib = _lib.load()
+    _need_cuda(x, w, y.buf, gamma, beta)
+    dev = x.device
+    cout = w.shape[0]
+    partial = Workspace.get(lib.b2_conv3d_first_stats_max_partials() * cout * 2 * 4, dev, "convstats")
+    n_partials = C.c_int(0)
+    _lib.check(lib.b2_conv3d_first_fwd_stats(_p(x), _p(w), _p(y.buf), y.ld, y.coff, y.N, y.D, y.H, y.W, cout, 1,
+                                             _p(partial), C.byref(n_partials), _s()), "b2_conv3d_first_fwd_stats")
+    mean_rstd = torch.empty((1, cout, 2), dtype=torch.float32, device=dev)
+    scale_shift = torch.empty((1, cout, 2), dtype=torch.float32, device=dev)
+    _lib.check(lib.b2_relu_gn_finalize(_p(partial), n_partials.value, y.V, cout, groups, float(eps), _p(gamma),
+                                       _p(beta), _p(mean_rstd), _p(scale_shift), _s()), "b2_relu_gn_finalize")
+    _count(2)
+    return mean_rstd, scale_shift
+
+
 def conv3d_first_wgrad(x, dy, cout, out=None):
     lib = _lib.load()
     _need_cuda(x, dy.buf)

@@ -51,6 +51,11 @@ class BucketedGradReducer(object):
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self._pending = []
         self._needed_last = dict(_LAST_LAYER_OF_BUCKET)
+        # CUDA-graph capture of a data-parallel step (pattern_class._graphed_step): NCCL is never captured; while
+        # `segment_cb` is set, a bucket launch / the final wait only report where the step has to be cut into graph
+        # segments, and the collectives are enqueued eagerly between the replays of those segments.
+        self.segment_cb = None
+        self.force_segments = False   # tests: cut the step at the bucket boundaries even on one rank
         model.grad_ready_hook = self._on_layer_ready
 
     def outs(self):
@@ -74,11 +79,16 @@ class BucketedGradReducer(object):
 
     def _on_layer_ready(self, layer, grads):
         b = self._close_at.get(layer)
-        if b is None or self.world == 1:
+        if b is None or (self.world == 1 and not self.force_segments):
             return
         self._launch(b)
 
     def _launch(self, b):
+        if self.segment_cb is not None:            # capturing: cut the graph here, the all-reduce runs at replay
+            self.segment_cb(("reduce", b))
+            return
+        if self.world == 1:                        # force_segments on a single rank: nothing to exchange
+            return
         if self.comm_stream is None:               # CPU tensors (gloo tests)
             dist.all_reduce(self.flat[b], group=self.group)
             if self.average:
@@ -98,6 +108,9 @@ class BucketedGradReducer(object):
 
     def finish(self):
         """compute stream waits for every outstanding all-reduce; returns the reduced gradient views"""
+        if self.segment_cb is not None:
+            self.segment_cb(("finish", None))
+            return self.views
         for ev in self._pending:
             torch.cuda.current_stream().wait_event(ev)
         self._pending = []

@@ -314,9 +314,14 @@ class UnetPatternSulciLabelling(object):
 
     # -- CUDA-graph replay of the whole step ---------------------------------------------------------------------
     # A step is ~125 kernel launches; enqueueing them from Python costs ~5 ms against ~8 ms of GPU time.  When the
-    # same volume shape comes back (fixed img_size, batch > 1 padding, benchmarks) the step is captured once into a
-    # CUDA graph and replayed: one launch per step.  Off by default for learning() because every subject of a real
-    # cohort has its own bounding box; `use_cuda_graph = True` turns it on (single-GPU only).
+    # same volume shape comes back (fixed img_size, batch > 1 padding, benchmarks) the step is captured once into
+    # CUDA graphs and replayed.  Off by default for learning() because every subject of a real cohort has its own
+    # bounding box; `use_cuda_graph = True` turns it on.
+    # Data parallel: NCCL is NOT captured (capturing the side-stream all-reduces dead-locked at replay on 2 x B200).
+    # The step is cut into graph segments at the points where a gradient bucket closes; between the replays of two
+    # segments the bucket's all-reduce is enqueued eagerly on the communication stream, so it still overlaps the
+    # rest of the backward pass; the last segment (fused SGD) is replayed after the compute stream has waited for
+    # every all-reduce.  One rank: a single segment.
     use_cuda_graph = False
     _graph_cache_limit = 2
 
@@ -333,12 +338,49 @@ class UnetPatternSulciLabelling(object):
         optimizer.step(grads=grads)
         return loss
 
+    def _capture_segments(self, sx, sy, optimizer, reducer):
+        """Records one eager step into a list of (CUDAGraph, action) segments; action is None, ("reduce", bucket)
+        or ("finish", None) = what has to be enqueued eagerly after that segment's replay."""
+        import gc
+        segs, cur = [], []
+        pool = torch.cuda.graph_pool_handle()
+        side = torch.cuda.Stream(device=sx.device)
+
+        def begin():
+            g = torch.cuda.CUDAGraph()
+            # thread_local: the NCCL watchdog thread may query events while this thread captures
+            g.capture_begin(pool=pool, capture_error_mode="thread_local")
+            cur.append(g)
+
+        def cut(action):
+            g = cur.pop()
+            g.capture_end()
+            segs.append((g, action))
+            begin()
+
+        gc.collect()
+        torch.cuda.synchronize()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            if reducer is not None:
+                reducer.segment_cb = cut
+            begin()
+            try:
+                loss = self._eager_step(sx, sy, optimizer, reducer)
+            finally:
+                if reducer is not None:
+                    reducer.segment_cb = None
+                g = cur.pop()
+                g.capture_end()
+            segs.append((g, None))
+        torch.cuda.current_stream().wait_stream(side)
+        return segs, loss
+
     def _graphed_step(self, x, y, optimizer, reducer=None):
-        """x, y: device tensors.  Returns the [2] loss tensor (mean, sum) of the step that was just enqueued.
-        With a reducer the bucketed NCCL all-reduces (side stream, fork/join by events) are captured too."""
+        """x, y: device tensors.  Returns the [2] loss tensor (mean, sum) of the step that was just enqueued."""
         cache = self.__dict__.setdefault("_graphs", {})
         seen = self.__dict__.setdefault("_graph_seen", set())
-        key = self._graph_key(x.shape, optimizer)
+        key = self._graph_key(x.shape, optimizer) + (id(reducer),)
         ent = cache.get(key)
         if ent is None:
             if key not in seen:          # first time: a real eager step (creates workspaces / momentum buffers)
@@ -349,21 +391,25 @@ class UnetPatternSulciLabelling(object):
             sx, sy = torch.empty_like(x), torch.empty_like(y)
             sx.copy_(x)
             sy.copy_(y)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
             try:
-                with torch.cuda.graph(graph):   # records, does not execute
-                    loss = self._eager_step(sx, sy, optimizer, reducer)
-            except Exception as e:  # e.g. a collective that cannot be captured: stay eager from now on
+                segs, loss = self._capture_segments(sx, sy, optimizer, reducer)   # records, does not execute
+            except Exception as e:
                 print("unetsulc_b200: CUDA-graph capture failed (%s); continuing without graphs" % e)
                 self.use_cuda_graph = False
                 return self._eager_step(x, y, optimizer, reducer)
-            ent = cache[key] = (graph, sx, sy, loss)
+            ent = cache[key] = (segs, sx, sy, loss)
         else:
-            graph, sx, sy, loss = ent
+            segs, sx, sy, loss = ent
             sx.copy_(x, non_blocking=True)
             sy.copy_(y, non_blocking=True)
-        ent[0].replay()
+        for g, action in ent[0]:
+            g.replay()
+            if action is None:
+                continue
+            if action[0] == "reduce":
+                reducer._launch(action[1])
+            else:
+                reducer.finish()
         # the replayed SGD changed the fp32 masters behind PyTorch's back: bump their version counters so that eager
         # paths (validation, labeling, state_dict consumers) re-pack the bf16 weights
         for p in self.model.ordered_parameters():
@@ -374,10 +420,8 @@ class UnetPatternSulciLabelling(object):
     def train_step_device(self, x, y, optimizer, reducer=None):
         """One training step on DEVICE tensors, no host synchronisation.  Returns the [2] loss tensor (mean, sum)."""
         self.model.train()
-        # graphs are used on a single GPU only: capturing the NCCL all-reduces (side-stream fork/join) dead-locked at
-        # replay on 2 x B200 (round 1), so data-parallel steps stay eager
-        if self.use_cuda_graph and reducer is None:
-            return self._graphed_step(x, y, optimizer, None)
+        if self.use_cuda_graph:
+            return self._graphed_step(x, y, optimizer, reducer)
         return self._eager_step(x, y, optimizer, reducer)
 
     def train_step(self, inputs, labels, optimizer, reducer=None):

@@ -37,6 +37,20 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/): the
+    newest profiles/r*_traffic.json.  Returns (bytes_per_launch or None, source)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not files:
+        return None, None
+    try:
+        d = json.load(open(files[-1]))
+        return float(d["dram_bytes_per_launch"]), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return None, None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -193,7 +207,9 @@ def run_ours(args):
     ls_d = [l.to(dev) for l in ls_h]
     h2d = xs_h[0].numel() * 4 + ls_h[0].numel() * 8
 
-    trainer.use_cuda_graph = (world == 1) and not args.no_cuda_graph   # whole step replayed as one CUDA graph
+    # the step is replayed from CUDA graphs (one graph on one rank; under data parallelism one graph segment per
+    # gradient bucket with the NCCL all-reduces enqueued eagerly in between)
+    trainer.use_cuda_graph = not args.no_cuda_graph
 
     def step_resident(i):
         return trainer.train_step_device(xs_d[i % n_data], ls_d[i % n_data], opt, reducer)
@@ -253,9 +269,11 @@ def run_ours(args):
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     wg = prof.get("conv3d_wgrad", [])
     wg_ms = sum(a.elapsed_time(b) for a, b, _ in wg)
+    traffic, traffic_src = load_traffic()
     roofline = {
         "bound": "tensor", "kernel": "conv3d_igemm_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src + " sustained bf16",
+        "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": peak_src + " sustained bf16",
         "launches_per_step": len(ig) / max(prof_steps, 1), "avg_launch_ms": ig_ms / max(len(ig), 1),
         "share_of_step": ig_ms * 1e-3 / prof_secs if prof_secs > 0 else None,
         "wgrad_kernel_tflops": (sum(w for _, _, w in wg) / (wg_ms * 1e-3) / 1e12) if wg_ms > 0 else None,
@@ -321,7 +339,7 @@ def run_ours(args):
             "config": {"workload": "UNet3D(in=1,out=56,'crg',f=64) full training step (SGD lr 1e-2 momentum 0.9), "
                                    "synthetic 1x1x96x112x96 skeleton volumes, batch 1 per rank",
                        "parallelism": "dp%d over subjects" % world,
-                       "cuda_graph": bool(trainer.use_cuda_graph and world == 1),
+                       "cuda_graph": bool(trainer.use_cuda_graph),
                        "l2": "no explicit flush: a step streams ~2 GB of activations (>> 126 MB L2) and cycles "
                              "through %d distinct volumes" % n_data},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

@@ -69,6 +69,11 @@ int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* dy, int ldy,
 /* encoders.0.conv1 (Cin = 1): direct convolution on the fp32 [N,D,H,W] skeleton volume (dataset.py:78-80)        */
 int b2_conv3d_first_fwd(const float* x, const float* w, void* y, int ldy, int y_coff, int N, int D, int H, int W,
                         int Cout, int relu, cudaStream_t stream);
+/* same, with the GroupNorm statistics of the stored output fused in (batch 1): stat_partial fp32
+ * [b2_conv3d_first_stats_max_partials()][Cout][2], finalised by b2_relu_gn_finalize; *n_partials is a HOST int.     */
+int b2_conv3d_first_stats_max_partials(void);
+int b2_conv3d_first_fwd_stats(const float* x, const float* w, void* y, int ldy, int y_coff, int N, int D, int H, int W,
+                              int Cout, int relu, float* stat_partial, int* n_partials, cudaStream_t stream);
 long long b2_conv3d_first_wgrad_workspace_bytes(int Cout);
 int b2_conv3d_first_wgrad(const float* x, const void* dy, int lddy, int dy_coff, float* dw, void* workspace,
                           long long workspace_bytes, int N, int D, int H, int W, int Cout, cudaStream_t stream);

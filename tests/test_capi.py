@@ -32,7 +32,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     # size queries are host-only arithmetic: callable without a GPU
     assert lib.b2_gn_workspace_bytes(1, 64) == 296 * 64 * 2 * 4
     assert lib.b2_relu_gn_bwd_workspace_bytes(2, 64) == 2 * 296 * 64 * 2 * 4 + 2 * 64 * 6 * 4
-    assert lib.b2_conv3d_first_wgrad_workspace_bytes(32) == 296 * 27 * 32 * 4
+    assert lib.b2_conv3d_first_wgrad_workspace_bytes(32) == 592 * 27 * 32 * 4
     assert lib.b2_head_workspace_bytes(64) > 0
     assert lib.b2_fold_vote_workspace_bytes(100, 56, 7, 3) > 0
 

@@ -130,8 +130,12 @@ def test_transfer_learning_two_phases(tmp_path):
     assert tl.results['epoch_loss_train'][0][-1] < tl.results['epoch_loss_train'][0][0]
 
 
-def test_cuda_graph_step_matches_eager_step(tmp_path):
-    """train_step with use_cuda_graph replays the same kernels: identical losses and weights, step after step."""
+@pytest.mark.parametrize("segmented", [False, True])
+def test_cuda_graph_step_matches_eager_step(tmp_path, segmented):
+    """train_step with use_cuda_graph replays the same kernels: identical losses and weights, step after step.
+    segmented: the data-parallel form of the replay (graph cut where a gradient bucket closes, gradients written
+    into the flat buckets, collectives enqueued between the segments) forced on one rank."""
+    from unetsulc_b200 import parallel
     from unetsulc_b200.training import UnetTrainingSulciLabelling
     from unetsulc_b200.optim import SGD
     from oracle.synth import synth_volume
@@ -149,7 +153,14 @@ def test_cuda_graph_step_matches_eager_step(tmp_path):
             t.load_network()
         t.use_cuda_graph = use_graph
         opt = SGD(t.model.ordered_parameters(), lr=1e-2, momentum=0.9)
-        losses = [t.train_step(*data[i % 3], opt) for i in range(6)]
+        red = None
+        if segmented:
+            red = parallel.BucketedGradReducer(t.model)
+            red.force_segments = True
+        losses = [t.train_step(*data[i % 3], opt, red) for i in range(6)]
+        if segmented and use_graph:
+            segs = next(iter(t._graphs.values()))[0]
+            assert [a[0] if a else None for _, a in segs] == ["reduce"] * 4 + ["finish", None]
         # an eager evaluation after graph replays must see the updated weights
         t.model.eval()
         with torch.no_grad():

@@ -325,6 +325,28 @@ def test_conv_first_layer():
     assert rel_l2(got, wp.grad) < 1e-5
 
 
+def test_conv_first_layer_fused_gn_stats():
+    """first conv with the GroupNorm statistics fused in == first conv followed by the statistics kernel"""
+    ops = _ops()
+    Cout, D, H, W, G = 32, 19, 21, 37, 32
+    g = torch.Generator(device="cuda").manual_seed(15)
+    x = (torch.rand(1, 1, D, H, W, device="cuda", generator=g) < 0.05).float()
+    w = torch.randn(Cout, 1, 3, 3, 3, device="cuda", generator=g) * 0.2
+    gamma = torch.randn(Cout, device="cuda", generator=g) * 0.5 + 1.0
+    beta = torch.randn(Cout, device="cuda", generator=g) * 0.1
+    y0 = ops.ActView.alloc(1, D, H, W, Cout, "cuda")
+    ops.conv3d_first_fwd(x, w, y0, relu=True)
+    mr0, ss0 = ops.relu_gn_stats(y0, G, 1e-5, gamma, beta)
+    y1 = ops.ActView.alloc(1, D, H, W, Cout, "cuda")
+    mr1, ss1 = ops.conv3d_first_fwd_gn_stats(x, w, y1, G, 1e-5, gamma, beta)
+    torch.cuda.synchronize()
+    assert torch.equal(y0.buf, y1.buf)
+    assert torch.allclose(mr0, mr1, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(ss0, ss1, rtol=1e-5, atol=1e-6)
+    ref = F.relu(F.conv3d(x, w, padding=1))
+    assert rel_l2(from_view(y1), ref) < 2e-3
+
+
 @pytest.mark.parametrize("C,D,H,W,N", [(32, 8, 10, 12, 1), (64, 9, 11, 13, 2), (256, 4, 6, 6, 1), (512, 3, 4, 5, 1)])
 def test_relu_groupnorm_fwd_bwd(C, D, H, W, N):
     ops = _ops()
