@@ -94,111 +94,231 @@ __device__ __forceinline__ void load_head_weights(const float* __restrict__ W, c
 }
 
 // ------------------------------------------------------------------------------------------------- fused head + CE
-// partial layout per block: [Cin][kMaxCo] dW (transposed, bank-conflict-free) | [kMaxCo] db | loss
+// Every block owns a contiguous range of voxels.  Per 2048-voxel sub-chunk it compacts the LABELLED voxels (2-4 %)
+// into shared memory (ballot + prefix: ascending order, deterministic), then works through them 64 at a time:
+//   * four adjacent lanes per voxel: lane q computes the logits of output channels [q*Cout/4, (q+1)*Cout/4) from the
+//     voxel's 64-channel row held in registers (weights: conflict-free broadcast float4 reads, rows padded by 4),
+//     softmax / argmax / loss combine over the 4 lanes by shuffles, d(logits) goes to shared memory;
+//   * the same four lanes compute the voxel's dX row (lane q owns channels 16m + 4q .. +3);
+//   * dW / db: all 256 threads as a [64 x CIN] register tile (thread = (co, CIN/4 channels)) accumulate
+//     d(logits)^T . x over the 64 staged voxels — the accumulators live for the whole kernel, no atomics.
+// The round-1 kernel gave each labelled voxel to a whole warp, one after another (128 accumulator registers per lane,
+// 8 warps per SM): latency-bound at 0.19 ms for 31 k voxels.
+// partial layout per block: [Cin][kMaxCo] dW (transposed) | [kMaxCo] db | loss
+static constexpr int kCeChunk = 2048;
+static constexpr int kCeGroup = 64;
+
 template <int CIN>
-__global__ void __launch_bounds__(kCeThreads)
+__global__ void __launch_bounds__(kCeThreads, 2)
 head_ce_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ labels, long long NV,
                const float* __restrict__ W, const float* __restrict__ b, int Cout, const int* __restrict__ count,
                float grad_scale, const float* __restrict__ grad_scale_dev, int compute_grad, int eval_softmax,
-               int* __restrict__ preds, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial) {
+               int* __restrict__ preds, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial,
+               long long per_block) {
+  constexpr int WS = CIN + 4;        // padded row strides (floats)
+  constexpr int DS = kMaxCo + 1;
+  constexpr int CPT = CIN / 4;       // channels per thread in the dX and dW phases
   extern __shared__ float shm[];
-  float* Wt = shm;                       // [CIN][kMaxCo]
-  float* Ws = Wt + CIN * kMaxCo;         // [kMaxCo][CIN]
-  float* bs = Ws + kMaxCo * CIN;         // [kMaxCo]
-  float* red = bs + kMaxCo;              // [kMaxCo*CIN + kMaxCo + 1]
-  load_head_weights(W, b, CIN, Cout, Wt, Ws, bs);
-  for (int i = threadIdx.x; i < kMaxCo * CIN + kMaxCo + 1; i += blockDim.x) red[i] = 0.f;
+  float* Ws = shm;                            // [kMaxCo][WS]
+  float* bs = Ws + kMaxCo * WS;               // [kMaxCo]
+  float* ds = bs + kMaxCo;                    // [kCeGroup][DS]  logits, then d(logits)
+  float* xs = ds + kCeGroup * DS;             // [kCeGroup][WS]  x rows (fp32)
+  float* lossv = xs + kCeGroup * WS;          // [kCeGroup]
+  int* s_u = reinterpret_cast<int*>(lossv + kCeGroup);   // [kCeChunk] voxel offsets relative to r_begin
+  int* s_lab = s_u + kCeChunk;                           // [kCeChunk]
+  int* s_cnt = s_lab + kCeChunk;                         // [kCeChunk / 32 + 1]
+  for (int i = threadIdx.x; i < kMaxCo * WS; i += blockDim.x) {
+    const int co = i / WS, ci = i % WS;
+    Ws[i] = (co < Cout && ci < CIN) ? W[co * CIN + ci] : 0.f;
+  }
+  for (int i = threadIdx.x; i < kMaxCo; i += blockDim.x) bs[i] = (i < Cout && b) ? b[i] : 0.f;
+  for (int i = threadIdx.x; i < kCeGroup * DS; i += blockDim.x) ds[i] = 0.f;   // columns >= Cout stay zero
   __syncthreads();
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const int cnt = *count;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = threadIdx.x >> 2, q = threadIdx.x & 3;   // voxel slot in the group, quarter
+  const int cpq = (Cout + 3) >> 2;
+  const int co_begin = q * cpq, co_end = min(Cout, co_begin + cpq);
+  const int cnt_all = *count;
   const float gsc = grad_scale_dev ? grad_scale * (*grad_scale_dev) : grad_scale;
-  const float gs = (cnt > 0) ? gsc / (float)cnt : 0.f;
-  float accW0[CIN], accW1[CIN];
-  float accb0 = 0.f, accb1 = 0.f, loss = 0.f;
+  const float gs = (cnt_all > 0) ? gsc / (float)cnt_all : 0.f;
+  const int wco = threadIdx.x >> 2, wcb = (threadIdx.x & 3) * CPT;   // dW tile of this thread
+  float accW[CPT];
 #pragma unroll
-  for (int i = 0; i < CIN; ++i) { accW0[i] = 0.f; accW1[i] = 0.f; }
+  for (int i = 0; i < CPT; ++i) accW[i] = 0.f;
+  float accb = 0.f, block_loss = 0.f;
 
-  const long long gw = (long long)blockIdx.x * nwarp + warp, nw = (long long)gridDim.x * nwarp;
-  for (long long base = gw * 32; base < NV; base += nw * 32) {
-    const long long v = base + lane;
-    const long long lab = (v < NV) ? labels[v] : -1;
-    unsigned any = __ballot_sync(0xffffffffu, lab >= 0);
-    while (any) {
-      const int src = __ffs(any) - 1;
-      any &= any - 1;
-      const long long vv = base + src;
-      const int label = (int)__shfl_sync(0xffffffffu, (int)lab, src);
-      uint32_t xp = 0;
-      if (lane < CIN / 2) xp = __ldg(reinterpret_cast<const uint32_t*>(x + vv * CIN) + lane);
-      WarpHead h = warp_logits<CIN>(xp, Wt, bs, lane);
-      float p0, p1, lse;
-      warp_softmax(h.l0, h.l1, Cout, lane, p0, p1, lse);
-      const int am = warp_argmax(h.l0, h.l1, Cout, lane);
-      float lv;
-      if (eval_softmax) {  // reference val phase: CrossEntropyLoss applied to Softmax outputs (training.py:189,205-208)
-        float q0, q1, lse2;
-        warp_softmax(p0, p1, Cout, lane, q0, q1, lse2);
-        const float pl = __shfl_sync(0xffffffffu, (label < 32) ? p0 : p1, label & 31);
-        lv = lse2 - pl;
-      } else {
-        const float ll = __shfl_sync(0xffffffffu, (label < 32) ? h.l0 : h.l1, label & 31);
-        lv = lse - ll;
-      }
-      if (lane == 0) {
-        loss += lv;
-        if (preds) preds[vv] = am;
-      }
-      if (compute_grad) {
-        const float d0 = (lane < Cout) ? (p0 - ((lane == label) ? 1.f : 0.f)) * gs : 0.f;
-        const float d1 = (lane + 32 < Cout) ? (p1 - ((lane + 32 == label) ? 1.f : 0.f)) * gs : 0.f;
-        accb0 += d0;
-        accb1 += d1;
+  const long long r_begin = (long long)blockIdx.x * per_block;
+  const long long r_end = (r_begin + per_block < NV) ? r_begin + per_block : NV;
+  for (long long c0 = r_begin; c0 < r_end; c0 += kCeChunk) {
+    // ---- compaction of the labelled voxels of [c0, c0 + kCeChunk)
+    int lab[kCeChunk / kCeThreads];
+    unsigned bal[kCeChunk / kCeThreads];
 #pragma unroll
-        for (int ci = 0; ci < CIN; ci += 2) {
-          const uint32_t p = __shfl_sync(0xffffffffu, xp, ci >> 1);
-          const float xa = __uint_as_float(p << 16), xb = __uint_as_float(p & 0xffff0000u);
-          accW0[ci] = fmaf(d0, xa, accW0[ci]);
-          accW1[ci] = fmaf(d1, xa, accW1[ci]);
-          accW0[ci + 1] = fmaf(d0, xb, accW0[ci + 1]);
-          accW1[ci + 1] = fmaf(d1, xb, accW1[ci + 1]);
-        }
-        if (dx) {
-          float g0 = 0.f, g1 = 0.f;  // dX for channels 2*lane, 2*lane+1
-          for (int co = 0; co < Cout; ++co) {
-            const float dc = __shfl_sync(0xffffffffu, (co < 32) ? d0 : d1, co & 31);
-            if (lane < CIN / 2) {
-              const float2 w2 = *reinterpret_cast<const float2*>(Ws + co * CIN + 2 * lane);
-              g0 = fmaf(dc, w2.x, g0);
-              g1 = fmaf(dc, w2.y, g1);
-            }
-          }
-          if (lane < CIN / 2) {
-            __nv_bfloat162 o = __floats2bfloat162_rn(g0, g1);
-            reinterpret_cast<__nv_bfloat162*>(dx + vv * CIN)[lane] = o;
-          }
-        }
-      }
-    }
-  }
-  // deterministic block reduction: warps add their registers into smem one after another
-  for (int w = 0; w < nwarp; ++w) {
-    if (warp == w) {
-      if (compute_grad) {
-#pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {   // [ci][co] layout: lanes hit consecutive banks
-          red[ci * kMaxCo + lane] += accW0[ci];
-          red[ci * kMaxCo + lane + 32] += accW1[ci];
-        }
-        red[kMaxCo * CIN + lane] += accb0;
-        red[kMaxCo * CIN + lane + 32] += accb1;
-      }
-      if (lane == 0) red[kMaxCo * CIN + kMaxCo] += loss;
+    for (int k = 0; k < kCeChunk / kCeThreads; ++k) {
+      const long long u = c0 + k * kCeThreads + threadIdx.x;
+      const long long l = (u < r_end) ? labels[u] : -1;
+      lab[k] = (l >= 0) ? (int)l : -1;
+      bal[k] = __ballot_sync(0xffffffffu, lab[k] >= 0);
+      if (lane == 0) s_cnt[k * 8 + warp] = __popc(bal[k]);
     }
     __syncthreads();
+    if (warp == 0) {   // exclusive prefix over the 64 (k, warp) counts
+      const int a = s_cnt[lane], bb = s_cnt[lane + 32];
+      int ia = a, ib = bb;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ta; ib += tb; }
+      }
+      const int tot_a = __shfl_sync(0xffffffffu, ia, 31);
+      s_cnt[lane] = ia - a;
+      s_cnt[lane + 32] = tot_a + ib - bb;
+      if (lane == 31) s_cnt[64] = tot_a + ib;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kCeChunk / kCeThreads; ++k) {
+      if (lab[k] >= 0) {
+        const int pos = s_cnt[k * 8 + warp] + __popc(bal[k] & ((1u << lane) - 1u));
+        s_u[pos] = (int)(c0 - r_begin) + k * kCeThreads + threadIdx.x;
+        s_lab[pos] = lab[k];
+      }
+    }
+    __syncthreads();
+    const int cnt = s_cnt[64];
+
+    for (int g0 = 0; g0 < cnt; g0 += kCeGroup) {
+      const int nj = min(kCeGroup, cnt - g0);
+      const bool live = j < nj;
+      const long long vv = r_begin + (live ? s_u[g0 + j] : s_u[g0]);
+      const int label = live ? s_lab[g0 + j] : 0;
+      // ---- logits of this lane's output channels
+      float xr[CIN];
+#pragma unroll
+      for (int i8 = 0; i8 < CIN / 8; ++i8) {
+        const f8 t = unpack8(ldg16(x + vv * CIN + i8 * 8));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xr[i8 * 8 + k] = t.v[k];
+      }
+      // this lane's quarter of the row, staged for the dW tile (re-loaded: indexing xr[] by q would spill it)
+#pragma unroll
+      for (int i8 = 0; i8 < CPT / 8; ++i8) {
+        const f8 t = unpack8(ldg16(x + vv * CIN + q * CPT + i8 * 8));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xs[j * WS + q * CPT + i8 * 8 + k] = live ? t.v[k] : 0.f;
+      }
+      float m = -INFINITY;
+      int am = 0;
+      for (int co = co_begin; co < co_end; ++co) {
+        float a0 = bs[co], a1 = 0.f;
+        const float4* wr = reinterpret_cast<const float4*>(Ws + co * WS);
+#pragma unroll
+        for (int c4 = 0; c4 < CIN / 4; c4 += 2) {
+          const float4 w0 = wr[c4], w1 = wr[c4 + 1];
+          a0 = fmaf(xr[4 * c4 + 0], w0.x, a0); a0 = fmaf(xr[4 * c4 + 1], w0.y, a0);
+          a0 = fmaf(xr[4 * c4 + 2], w0.z, a0); a0 = fmaf(xr[4 * c4 + 3], w0.w, a0);
+          a1 = fmaf(xr[4 * c4 + 4], w1.x, a1); a1 = fmaf(xr[4 * c4 + 5], w1.y, a1);
+          a1 = fmaf(xr[4 * c4 + 6], w1.z, a1); a1 = fmaf(xr[4 * c4 + 7], w1.w, a1);
+        }
+        const float l = a0 + a1;
+        ds[j * DS + co] = l;
+        if (l > m) { m = l; am = co; }   // first maximum wins inside the ascending range
+      }
+      // combine max / argmax over the 4 lanes of the voxel (ties -> lowest index, torch.max semantics)
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+        if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+      }
+      float se = 0.f;
+      for (int co = co_begin; co < co_end; ++co) se += expf(ds[j * DS + co] - m);
+      se += __shfl_xor_sync(0xffffffffu, se, 1);
+      se += __shfl_xor_sync(0xffffffffu, se, 2);
+      const float lse = m + logf(se);
+      __syncwarp();
+      float lv;
+      if (eval_softmax) {  // reference val phase: CrossEntropyLoss applied to Softmax outputs (training.py:189,205-208)
+        float m2 = -INFINITY;
+        for (int co = co_begin; co < co_end; ++co) m2 = fmaxf(m2, expf(ds[j * DS + co] - m) / se);
+        m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 1));
+        m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, 2));
+        float s2 = 0.f;
+        for (int co = co_begin; co < co_end; ++co) s2 += expf(expf(ds[j * DS + co] - m) / se - m2);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+        lv = (m2 + logf(s2)) - expf(ds[j * DS + label] - m) / se;
+      } else {
+        lv = lse - ds[j * DS + label];
+      }
+      if (q == 0) {
+        lossv[j] = live ? lv : 0.f;
+        if (live && preds) preds[vv] = am;
+      }
+      __syncwarp();
+      if (compute_grad) {
+        for (int co = co_begin; co < co_end; ++co) {
+          const float pco = expf(ds[j * DS + co] - m) / se;
+          ds[j * DS + co] = live ? (pco - ((co == label) ? 1.f : 0.f)) * gs : 0.f;
+        }
+        __syncwarp();
+        if (dx != nullptr && live) {
+          float g[CPT];   // channels 16m + 4q + e
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) g[i] = 0.f;
+          for (int co = 0; co < Cout; ++co) {
+            const float dco = ds[j * DS + co];
+#pragma unroll
+            for (int mm = 0; mm < CPT / 4; ++mm) {
+              const float4 w4 = *reinterpret_cast<const float4*>(Ws + co * WS + 16 * mm + 4 * q);
+              g[4 * mm + 0] = fmaf(dco, w4.x, g[4 * mm + 0]);
+              g[4 * mm + 1] = fmaf(dco, w4.y, g[4 * mm + 1]);
+              g[4 * mm + 2] = fmaf(dco, w4.z, g[4 * mm + 2]);
+              g[4 * mm + 3] = fmaf(dco, w4.w, g[4 * mm + 3]);
+            }
+          }
+#pragma unroll
+          for (int mm = 0; mm < CPT / 4; ++mm) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(g[4 * mm + 0], g[4 * mm + 1]);
+            __nv_bfloat162 hi = __floats2bfloat162_rn(g[4 * mm + 2], g[4 * mm + 3]);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&lo);
+            o.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(dx + vv * CIN + 16 * mm + 4 * q) = o;
+          }
+        }
+      }
+      __syncthreads();
+      // ---- dW / db register tile over the staged voxels; loss in a fixed order
+      if (compute_grad) {
+        for (int jv = 0; jv < nj; ++jv) {
+          const float dco = ds[jv * DS + wco];
+          const float4* xr4 = reinterpret_cast<const float4*>(xs + jv * WS + wcb);
+#pragma unroll
+          for (int i4 = 0; i4 < CPT / 4; ++i4) {
+            const float4 xv = xr4[i4];
+            accW[4 * i4 + 0] = fmaf(dco, xv.x, accW[4 * i4 + 0]);
+            accW[4 * i4 + 1] = fmaf(dco, xv.y, accW[4 * i4 + 1]);
+            accW[4 * i4 + 2] = fmaf(dco, xv.z, accW[4 * i4 + 2]);
+            accW[4 * i4 + 3] = fmaf(dco, xv.w, accW[4 * i4 + 3]);
+          }
+          if ((threadIdx.x & 3) == 0) accb += dco;
+        }
+      }
+      if (warp == 0) {
+        float v = lossv[lane] + lossv[lane + 32];
+        v = warp_sum(v);
+        block_loss += v;
+      }
+      __syncthreads();
+    }
   }
   float* dst = partial + (size_t)blockIdx.x * (kMaxCo * CIN + kMaxCo + 1);
-  for (int i = threadIdx.x; i < kMaxCo * CIN + kMaxCo + 1; i += blockDim.x) dst[i] = red[i];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) dst[(wcb + i) * kMaxCo + wco] = accW[i];
+  if ((threadIdx.x & 3) == 0) dst[kMaxCo * CIN + wco] = accb;
+  if (threadIdx.x == 0) dst[kMaxCo * CIN + kMaxCo] = block_loss;
 }
 
 __global__ void head_ce_finalize_kernel(const float* __restrict__ partial, int nblocks, int Cin, int Cout,
@@ -439,19 +559,24 @@ extern "C" int b2_head_ce(const void* x, const long long* labels, long long NV, 
   if (cblocks > num_sms() * 8) cblocks = num_sms() * 8;
   count_labelled_kernel<<<cblocks, 256, 0, stream>>>(labels, NV, count_out);
   B2_CHECK_CUDA(cudaGetLastError());
-  const size_t sh = (size_t)(2 * kMaxCo * Cin + kMaxCo + kMaxCo * Cin + kMaxCo + 1) * sizeof(float);
+  B2_REQUIRE(NV < (1LL << 31), "b2_head_ce: %lld voxels unsupported", NV);
+  const size_t sh = (size_t)(kMaxCo * (Cin + 4) + kMaxCo + kCeGroup * (kMaxCo + 1) + kCeGroup * (Cin + 4) + kCeGroup) *
+                        sizeof(float) +
+                    (size_t)(2 * kCeChunk + kCeChunk / 32 + 1) * sizeof(int);
+  long long per_block = (NV + kCeBlocks - 1) / kCeBlocks;
+  per_block = (per_block + kCeThreads - 1) / kCeThreads * kCeThreads;
   auto* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   auto* dxb = reinterpret_cast<__nv_bfloat16*>(dx);
   if (Cin == 64) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(head_ce_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     head_ce_kernel<64><<<kCeBlocks, kCeThreads, sh, stream>>>(xb, labels, NV, W, b, Cout, count_out, grad_scale,
                                                               grad_scale_dev, compute_grad, eval_softmax, preds, dxb,
-                                                              partial);
+                                                              partial, per_block);
   } else {
     B2_CHECK_CUDA(cudaFuncSetAttribute(head_ce_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     head_ce_kernel<32><<<kCeBlocks, kCeThreads, sh, stream>>>(xb, labels, NV, W, b, Cout, count_out, grad_scale,
                                                               grad_scale_dev, compute_grad, eval_softmax, preds, dxb,
-                                                              partial);
+                                                              partial, per_block);
   }
   B2_CHECK_CUDA(cudaGetLastError());
   const int stride = kMaxCo * Cin + kMaxCo + 1;
