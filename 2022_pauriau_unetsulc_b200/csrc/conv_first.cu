@@ -110,37 +110,47 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /
 
 // dw[co][tap] = sum_u x[u] * dy[u - off(tap), co] over the NON-ZERO input voxels u (~3 % of a skeleton volume).
 // Every block owns a contiguous range of input voxels: it first compacts the non-zero ones of a 2048-voxel
-// sub-chunk into shared memory (ballot + prefix: ascending voxel order, deterministic), then warp w accumulates taps
-// w, w+8, w+16, w+24 over that list (lane = output channel, 64-byte coalesced dy rows, four voxels x four taps of
-// independent loads in flight).  The round-1 kernel scanned and gathered one voxel at a time per warp and was
-// latency-bound (0.18 ms for 31 k voxels).  No atomics: a (tap, channel) sum lives in one lane's register.
+// sub-chunk into shared memory (ballot + prefix: ascending voxel order, deterministic).  Warp w then takes the
+// voxels w, w+8, ... of that list; for one voxel a single 16-byte load instruction fetches 32/LPR different TAP rows
+// at once (lane = (tap slot, channel octet), LPR = Cout/8 lanes per dy row), so the 27 taps cost ceil(27*LPR/32)
+// load instructions instead of 27 (ncu, round 1: the one-row-per-instruction form executed 36 M warp instructions
+// for 31 k voxels and sat at 25 % issue utilisation behind long-scoreboard stalls).  A lane owns its (tap, 8
+// channels) sums; the 8 warps are combined through shared memory in warp order: no atomics, deterministic.
 static constexpr int kFwChunk = 2048;
 
+template <int COUT>
 __global__ void __launch_bounds__(256)
 conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
-                        float* __restrict__ partial /*[grid][27][Cout]*/, int N, int D, int H, int W, int Cout,
+                        float* __restrict__ partial /*[grid][27][COUT]*/, int N, int D, int H, int W,
                         long long per_block) {
+  constexpr int LPR = COUT / 8;              // lanes per dy row
+  constexpr int PPL = 32 / LPR;              // (voxel, tap) rows fetched by one load instruction
+  constexpr int ROUNDS = (27 + PPL - 1) / PPL;
   __shared__ int s_u[kFwChunk];
   __shared__ uint32_t s_dhw[kFwChunk];
   __shared__ float s_x[kFwChunk];
   __shared__ int s_cnt[kFwChunk / 32 + 1];
+  __shared__ float red[27 * COUT];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = lane / LPR, cq = lane % LPR;
   const long long V = (long long)N * D * H * W;
   const long long r_begin = (long long)blockIdx.x * per_block;
   const long long r_end = (r_begin + per_block < V) ? r_begin + per_block : V;
-  const bool has0 = lane < Cout, has1 = (lane + 32) < Cout;
-  const __nv_bfloat16* dyc = dy + dy_coff;
-  float acc0[4], acc1[4];
+  const __nv_bfloat16* dyc = dy + dy_coff + cq * 8;
+  float acc[ROUNDS][8];
+  int tdd[ROUNDS], tdh[ROUNDS], tdw[ROUNDS], toff[ROUNDS];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) { acc0[t] = 0.f; acc1[t] = 0.f; }
-  // this warp's taps and their (dd, dh, dw)
-  int tdd[4], tdh[4], tdw[4], toff[4];
+  for (int k = 0; k < ROUNDS; ++k) {
+    const int tap = slot + PPL * k;
+    tdd[k] = tap < 27 ? tap / 9 - 1 : 4096;   // 4096: never in bounds
+    tdh[k] = (tap / 3) % 3 - 1;
+    tdw[k] = tap % 3 - 1;
+    toff[k] = tap < 27 ? (tdd[k] * H + tdh[k]) * W + tdw[k] : 0;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int tap = warp + 8 * t;
-    tdd[t] = tap / 9 - 1; tdh[t] = (tap / 3) % 3 - 1; tdw[t] = tap % 3 - 1;
-    toff[t] = (tdd[t] * H + tdh[t]) * W + tdw[t];
+    for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
   }
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
   for (long long c0 = r_begin; c0 < r_end; c0 += kFwChunk) {
     // ---- compaction of the non-zero voxels of [c0, c0 + kFwChunk) in ascending order
     float xv[kFwChunk / 256];
@@ -184,54 +194,81 @@ conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
     }
     __syncthreads();
     const int cnt = s_cnt[64];
-    // ---- gather: 4 voxels x (up to) 4 taps of loads in flight per warp
-    for (int j0 = 0; j0 < cnt; j0 += 4) {
-      float g0[4][4], g1[4][4], xs[4];
+    // ---- gather: two voxels x ROUNDS 16-byte loads in flight per lane
+    for (int j0 = warp; j0 < cnt; j0 += 16) {
+      uint4 g[2][ROUNDS];
+      float xs[2];
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = (j0 + jj < cnt) ? j0 + jj : cnt - 1;
-        const bool live = j0 + jj < cnt;
-        const int u = s_u[j];
-        const uint32_t c = s_dhw[j];
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = j0 + 8 * jj;
+        const bool live = j < cnt;
+        const int js = live ? j : j0;
+        const int u = s_u[js];
+        const uint32_t c = s_dhw[js];
         const int dq = (int)(c >> 20), hq = (int)((c >> 10) & 1023u), wq = (int)(c & 1023u);
-        xs[jj] = live ? s_x[j] : 0.f;
+        xs[jj] = live ? s_x[js] : 0.f;
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int k = 0; k < ROUNDS; ++k) {
           // output voxel v with v + off(tap) = u
-          const bool ok = live && (warp + 8 * t < 27) && (unsigned)(dq - tdd[t]) < (unsigned)D &&
-                          (unsigned)(hq - tdh[t]) < (unsigned)H && (unsigned)(wq - tdw[t]) < (unsigned)W;
-          const __nv_bfloat16* row = dyc + (long long)(ok ? u - toff[t] : u) * lddy;
-          g0[jj][t] = (ok && has0) ? __bfloat162float(row[lane]) : 0.f;
-          g1[jj][t] = (ok && has1) ? __bfloat162float(row[lane + 32]) : 0.f;
+          const bool ok = live && (unsigned)(dq - tdd[k]) < (unsigned)D && (unsigned)(hq - tdh[k]) < (unsigned)H &&
+                          (unsigned)(wq - tdw[k]) < (unsigned)W;
+          g[jj][k] = make_uint4(0u, 0u, 0u, 0u);
+          if (ok) g[jj][k] = __ldg(reinterpret_cast<const uint4*>(dyc + (long long)(u - toff[k]) * lddy));
         }
       }
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj)
+      for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          acc0[t] = fmaf(xs[jj], g0[jj][t], acc0[t]);
-          acc1[t] = fmaf(xs[jj], g1[jj][t], acc1[t]);
+        for (int k = 0; k < ROUNDS; ++k) {
+          const uint32_t wd[4] = {g[jj][k].x, g[jj][k].y, g[jj][k].z, g[jj][k].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc[k][2 * e] = fmaf(xs[jj], __uint_as_float(wd[e] << 16), acc[k][2 * e]);
+            acc[k][2 * e + 1] = fmaf(xs[jj], __uint_as_float(wd[e] & 0xffff0000u), acc[k][2 * e + 1]);
+          }
         }
     }
     __syncthreads();   // the list is rebuilt by the next sub-chunk
   }
+  // deterministic block reduction: warps add their registers one after another (no float atomics)
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int tap = warp + 8 * t;
-    if (tap < 27) {
-      float* dst = partial + ((size_t)blockIdx.x * 27 + tap) * Cout;
-      if (has0) dst[lane] = acc0[t];
-      if (has1) dst[lane + 32] = acc1[t];
+      for (int k = 0; k < ROUNDS; ++k) {
+        const int tap = slot + PPL * k;
+        if (tap < 27) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) red[tap * COUT + cq * 8 + e] += acc[k][e];
+        }
+      }
     }
+    __syncthreads();
   }
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) partial[(size_t)blockIdx.x * 27 * COUT + i] = red[i];
 }
 
-__global__ void conv_first_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nblocks,
-                                               int Cout) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // i = tap*Cout + co
-  if (i >= 27 * Cout) return;
+// fixed-order sum of the per-block partials: block = 32 outputs x 8 row groups, fp64
+__global__ void __launch_bounds__(256)
+conv_first_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nblocks, int Cout) {
+  __shared__ double red[8][32];
+  const int o = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + o;  // i = tap*Cout + co
+  const int total = 27 * Cout;
   double acc = 0.0;
-  for (int b = 0; b < nblocks; ++b) acc += (double)partial[(size_t)b * 27 * Cout + i];
+  if (i < total) {
+    int r = rg;
+    for (; r + 24 < nblocks; r += 32) {
+      const float a0 = partial[(size_t)r * total + i], a1 = partial[(size_t)(r + 8) * total + i];
+      const float a2 = partial[(size_t)(r + 16) * total + i], a3 = partial[(size_t)(r + 24) * total + i];
+      acc += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+    }
+    for (; r < nblocks; r += 8) acc += (double)partial[(size_t)r * total + i];
+  }
+  red[rg][o] = acc;
+  __syncthreads();
+  if (rg != 0 || i >= total) return;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) acc += red[k][o];
   const int tap = i / Cout, co = i % Cout;
   dw[co * 27 + tap] = (float)acc;
 }
@@ -288,7 +325,7 @@ extern "C" int b2_conv3d_first_wgrad(const float* x, const void* dy, int lddy, i
                                      long long workspace_bytes, int N, int D, int H, int W, int Cout,
                                      cudaStream_t stream) {
   B2_REQUIRE(x && dy && dw && workspace, "b2_conv3d_first_wgrad: null pointer");
-  B2_REQUIRE(Cout >= 1 && Cout <= kMaxC1, "b2_conv3d_first_wgrad: Cout=%d unsupported (<= 64)", Cout);
+  B2_REQUIRE(Cout == 32 || Cout == 64, "b2_conv3d_first_wgrad: Cout=%d unsupported (32 or 64)", Cout);
   B2_REQUIRE(workspace_bytes >= b2_conv3d_first_wgrad_workspace_bytes(Cout), "b2_conv3d_first_wgrad: workspace too small");
   B2_REQUIRE(D < 1024 && H < 1024 && W < 1024 && (long long)N * D * H * W < (1LL << 31),
              "b2_conv3d_first_wgrad: volume %dx%dx%dx%d too large", N, D, H, W);
@@ -297,10 +334,14 @@ extern "C" int b2_conv3d_first_wgrad(const float* x, const void* dy, int lddy, i
   long long per_block = (V + kFirstWgradBlocks - 1) / kFirstWgradBlocks;
   per_block = (per_block + 255) / 256 * 256;
   const int blocks = (int)((V + per_block - 1) / per_block);
-  conv_first_wgrad_kernel<<<blocks, 256, 0, stream>>>(x, reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff,
-                                                     partial, N, D, H, W, Cout, per_block);
+  B2_REQUIRE(lddy % 8 == 0 && dy_coff % 8 == 0, "b2_conv3d_first_wgrad: lddy/dy_coff must be multiples of 8");
+  auto* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+  if (Cout == 32)
+    conv_first_wgrad_kernel<32><<<blocks, 256, 0, stream>>>(x, dyb, lddy, dy_coff, partial, N, D, H, W, per_block);
+  else
+    conv_first_wgrad_kernel<64><<<blocks, 256, 0, stream>>>(x, dyb, lddy, dy_coff, partial, N, D, H, W, per_block);
   B2_CHECK_CUDA(cudaGetLastError());
-  conv_first_wgrad_reduce_kernel<<<(27 * Cout + 63) / 64, 64, 0, stream>>>(partial, dw, blocks, Cout);
+  conv_first_wgrad_reduce_kernel<<<(27 * Cout + 31) / 32, 256, 0, stream>>>(partial, dw, blocks, Cout);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }

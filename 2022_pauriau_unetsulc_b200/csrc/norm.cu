@@ -39,6 +39,13 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
     double a = 0.0, b = 0.0;
     const float* base = partial + ((size_t)n * nblk * C + c) * 2;
     int blk = sub;
+    for (; blk + 7 * L < nblk; blk += 8 * L) {   // 8 independent loads in flight
+      float2 pp[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pp[k] = __ldcg(reinterpret_cast<const float2*>(base + (size_t)(blk + k * L) * C * 2));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a += (double)pp[k].x; b += (double)pp[k].y; }
+    }
     for (; blk + 3 * L < nblk; blk += 4 * L) {
       const float2 p0 = __ldcg(reinterpret_cast<const float2*>(base + (size_t)blk * C * 2));
       const float2 p1 = __ldcg(reinterpret_cast<const float2*>(base + (size_t)(blk + L) * C * 2));
@@ -451,7 +458,11 @@ gn_bwd_finalize_partials_kernel(const float* __restrict__ partial, int nblk, int
 }
 
 static inline int stat_blocks(long long V, int C) {
-  long long nb = (V * C * 2) / 262144;  // at least 256 KB of the tensor per block (few partials for the last block)
+  // >= 16 KB of the tensor per block (round 1: 256 KB per block left the 12x14x12 and 24x28x24 levels with 3..31
+  // blocks and 35 us of pure latency per launch), and at most ~16 k partial pairs for the finalising block to sum
+  long long nb = (V * C * 2) / 16384;
+  const long long by_partials = 16384 / C;
+  if (nb > by_partials) nb = by_partials;
   if (nb > kStatBlocks) nb = kStatBlocks;
   if (nb < 1) nb = 1;
   return (int)nb;

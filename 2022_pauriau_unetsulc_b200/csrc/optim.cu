@@ -39,10 +39,12 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(const SgdArgs a) {
 }
 
 // Multi-layer weight pack, one launch for every conv layer whose fp32 master changed.
-//   role 0 (fprop):  block = (co, 64-wide ci tile): reads W[co][ci0..][27] (contiguous), writes Wf[tap][co][ci0..]
-//   role 1 (dgrad):  block = (ci, 64-wide co tile): reads W[co0..][ci][27] (108-byte runs), writes Wd[26-tap][ci][co0..]
-// Both directions go through a shared-memory transpose so that global reads and writes are contiguous runs.
+// Block = (16 output channels x 64 input channels) of one layer: the fp32 master is read ONCE (16 contiguous runs of
+// 64*27 floats), rounded to bf16 into shared memory, and written out twice: Wf[tap][co][ci0..] in 128-byte runs and
+// Wd[26-tap][ci][co0..] in 32-byte runs.  (Round 1 used one 64x27 tile per block and per pack: 18 912 blocks, two
+// reads of the master, 102 us.)
 static constexpr int kMaxPackLayers = 16;
+static constexpr int kPkCo = 16, kPkCi = 64;
 struct PackArgs {
   const float* w[kMaxPackLayers];
   __nv_bfloat16* wf[kMaxPackLayers];
@@ -53,40 +55,36 @@ struct PackArgs {
 };
 
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackArgs a) {
-  __shared__ float tile[64][28];
+  extern __shared__ __align__(16) uint8_t pack_smem[];
+  auto tile = reinterpret_cast<__nv_bfloat16(*)[kPkCi * 27 + 2]>(pack_smem);   // [kPkCo][..], odd word stride
   int l = 0;
   while (l + 1 < a.count && (int)blockIdx.x >= a.first_block[l + 1]) ++l;
   const int Cout = a.cout[l], Cin = a.cin[l];
   const float* __restrict__ w = a.w[l];
-  int b = blockIdx.x - a.first_block[l];
-  const int ci_tiles = (Cin + 63) / 64, co_tiles = (Cout + 63) / 64;
-  const int n_f = Cout * ci_tiles;
-  if (b < n_f) {
-    if (a.wf[l] == nullptr) return;
-    const int co = b / ci_tiles, ci0 = (b % ci_tiles) * 64;
-    const int tw = min(64, Cin - ci0);
-    const float* src = w + ((size_t)co * Cin + ci0) * 27;
-    for (int e = threadIdx.x; e < tw * 27; e += 256) tile[e / 27][e % 27] = src[e];
-    __syncthreads();
+  const int b = blockIdx.x - a.first_block[l];
+  const int ci_tiles = (Cin + kPkCi - 1) / kPkCi;
+  const int co0 = (b / ci_tiles) * kPkCo, ci0 = (b % ci_tiles) * kPkCi;
+  const int th = min(kPkCo, Cout - co0), tw = min(kPkCi, Cin - ci0);
+  const int run = tw * 27;
+  for (int e = threadIdx.x; e < th * run; e += 256) {
+    const int j = e / run, r = e - j * run;   // r = ci*27 + tap
+    tile[j][r] = __float2bfloat16_rn(w[((size_t)(co0 + j) * Cin + ci0) * 27 + r]);
+  }
+  __syncthreads();
+  if (a.wf[l] != nullptr) {
     __nv_bfloat16* dst = a.wf[l];
-    for (int e = threadIdx.x; e < 27 * tw; e += 256) {
-      const int tap = e / tw, ci = e % tw;
-      dst[((size_t)tap * Cout + co) * Cin + ci0 + ci] = __float2bfloat16_rn(tile[ci][tap]);
+    for (int e = threadIdx.x; e < 27 * th * tw; e += 256) {
+      const int ci = e % tw, t2 = e / tw;
+      const int j = t2 % th, tap = t2 / th;
+      dst[((size_t)tap * Cout + co0 + j) * Cin + ci0 + ci] = tile[j][ci * 27 + tap];
     }
-  } else {
-    if (a.wd[l] == nullptr) return;
-    b -= n_f;
-    const int ci = b / co_tiles, co0 = (b % co_tiles) * 64;
-    const int tw = min(64, Cout - co0);
-    for (int e = threadIdx.x; e < tw * 27; e += 256) {
-      const int j = e / 27, tap = e % 27;
-      tile[j][tap] = w[((size_t)(co0 + j) * Cin + ci) * 27 + tap];
-    }
-    __syncthreads();
+  }
+  if (a.wd[l] != nullptr) {
     __nv_bfloat16* dst = a.wd[l];
-    for (int e = threadIdx.x; e < 27 * tw; e += 256) {
-      const int tap = e / tw, j = e % tw;
-      dst[((size_t)(26 - tap) * Cin + ci) * Cout + co0 + j] = __float2bfloat16_rn(tile[j][tap]);
+    for (int e = threadIdx.x; e < 27 * tw * th; e += 256) {
+      const int j = e % th, t2 = e / th;
+      const int ci = t2 % tw, tap = t2 / tw;
+      dst[((size_t)(26 - tap) * Cin + ci0 + ci) * Cout + co0 + j] = tile[j][ci * 27 + tap];
     }
   }
 }
@@ -146,13 +144,15 @@ extern "C" int b2_pack_conv_weights_multi(const float* const* w, void* const* wf
       a.cout[k] = cout[i];
       a.cin[k] = cin[i];
       a.first_block[k] = blocks;
-      blocks += cout[i] * ((cin[i] + 63) / 64) + cin[i] * ((cout[i] + 63) / 64);
+      blocks += ((cout[i] + kPkCo - 1) / kPkCo) * ((cin[i] + kPkCi - 1) / kPkCi);
       ++k;
     }
     a.first_block[k] = blocks;
     a.count = k;
     if (blocks > 0) {
-      pack_weights_multi_kernel<<<blocks, 256, 0, stream>>>(a);
+      const int sh = kPkCo * (kPkCi * 27 + 2) * 2;
+      B2_CHECK_CUDA(cudaFuncSetAttribute(pack_weights_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh));
+      pack_weights_multi_kernel<<<blocks, 256, sh, stream>>>(a);
       B2_CHECK_CUDA(cudaGetLastError());
     }
     done += k;
