@@ -1,4 +1,5 @@
 #include "common.h"
+#include <stdlib.h>
 
 #include <stdarg.h>
 #include <string.h>
@@ -82,6 +83,11 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("B2_PDL") != nullptr;   // opt-in: measured slower on B200 (see common.h)
+  return on;
 }
 
 }  // namespace b2

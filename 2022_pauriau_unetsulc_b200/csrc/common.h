@@ -35,4 +35,41 @@ int num_sms();
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// A training step is ~130 short kernels in one stream; the dependency gap between two of them (drain, launch, first
+// wave) costs microseconds each.  Every kernel of this library starts with pdl_prologue(): griddepcontrol.wait (all
+// memory operations of the preceding grid are complete and visible — nothing is read or written before it) followed
+// by griddepcontrol.launch_dependents (the NEXT kernel's blocks may be scheduled as soon as every block of this grid
+// has started, so its launch latency and prologue overlap this grid's tail).  Launches go through launch_pdl(), which
+// sets cudaLaunchAttributeProgrammaticStreamSerialization (captured as programmatic edges in CUDA graphs).
+// MEASURED (round 1, 1 x B200, CUDA-graph replay of the training step): 7.37 ms/step with the attribute, 7.19 ms
+// without — the early-scheduled dependent blocks cost more than the launch gaps they hide.  The attribute is therefore
+// OFF by default (plain stream order; griddepcontrol.* are no-ops then) and B2_PDL=1 in the environment turns it on.
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define B2_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (void)::b2::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
+#endif
+
 }  // namespace b2

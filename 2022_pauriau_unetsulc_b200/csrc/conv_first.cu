@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(128)
 conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*[COUT][27]*/,
                       __nv_bfloat16* __restrict__ y, int N, int D, int H, int W, int ldy, int y_coff, int relu,
                       float* __restrict__ stat_partial) {
+  pdl_prologue();
   __shared__ __align__(16) float ws[27][COUT];
   __shared__ float2 sred[4][COUT];
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) ws[i % 27][i / 27] = w[i];  // w[co*27+tap]
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(256)
 conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
                         float* __restrict__ partial /*[grid][27][COUT]*/, int N, int D, int H, int W,
                         long long per_block) {
+  pdl_prologue();
   constexpr int LPR = COUT / 8;              // lanes per dy row
   constexpr int PPL = 32 / LPR;              // (voxel, tap) rows fetched by one load instruction
   constexpr int ROUNDS = (27 + PPL - 1) / PPL;
@@ -250,6 +252,7 @@ conv_first_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __rest
 // fixed-order sum of the per-block partials: block = 32 outputs x 8 row groups, fp64
 __global__ void __launch_bounds__(256)
 conv_first_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nblocks, int Cout) {
+  pdl_prologue();
   __shared__ double red[8][32];
   const int o = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + o;  // i = tap*Cout + co
@@ -290,8 +293,8 @@ static int conv_first_fwd_impl(const float* x, const float* w, void* y, int ldy,
   if (blocks > cap) blocks = cap;
   __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
   switch (Cout) {
-    case 32: conv_first_fwd_kernel<32><<<(unsigned)blocks, 128, 0, stream>>>(x, w, yy, N, D, H, W, ldy, y_coff, relu, stat_partial); break;
-    case 64: conv_first_fwd_kernel<64><<<(unsigned)blocks, 128, 0, stream>>>(x, w, yy, N, D, H, W, ldy, y_coff, relu, stat_partial); break;
+    case 32: B2_LAUNCH(conv_first_fwd_kernel<32>, (unsigned)blocks, 128, 0, stream, x, w, yy, N, D, H, W, ldy, y_coff, relu, stat_partial); break;
+    case 64: B2_LAUNCH(conv_first_fwd_kernel<64>, (unsigned)blocks, 128, 0, stream, x, w, yy, N, D, H, W, ldy, y_coff, relu, stat_partial); break;
     default:
       set_error("b2_conv3d_first_fwd: Cout=%d unsupported (32 or 64)", Cout);
       return B2_ERR_UNSUPPORTED;
@@ -337,11 +340,11 @@ extern "C" int b2_conv3d_first_wgrad(const float* x, const void* dy, int lddy, i
   B2_REQUIRE(lddy % 8 == 0 && dy_coff % 8 == 0, "b2_conv3d_first_wgrad: lddy/dy_coff must be multiples of 8");
   auto* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
   if (Cout == 32)
-    conv_first_wgrad_kernel<32><<<blocks, 256, 0, stream>>>(x, dyb, lddy, dy_coff, partial, N, D, H, W, per_block);
+    B2_LAUNCH(conv_first_wgrad_kernel<32>, blocks, 256, 0, stream, x, dyb, lddy, dy_coff, partial, N, D, H, W, per_block);
   else
-    conv_first_wgrad_kernel<64><<<blocks, 256, 0, stream>>>(x, dyb, lddy, dy_coff, partial, N, D, H, W, per_block);
+    B2_LAUNCH(conv_first_wgrad_kernel<64>, blocks, 256, 0, stream, x, dyb, lddy, dy_coff, partial, N, D, H, W, per_block);
   B2_CHECK_CUDA(cudaGetLastError());
-  conv_first_wgrad_reduce_kernel<<<(27 * Cout + 31) / 32, 256, 0, stream>>>(partial, dw, blocks, Cout);
+  B2_LAUNCH(conv_first_wgrad_reduce_kernel, (27 * Cout + 31) / 32, 256, 0, stream, partial, dw, blocks, Cout);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }

@@ -74,6 +74,7 @@ template <int KC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const IgemmParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kABytes = 128 * KC * 2;
@@ -301,6 +302,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 __global__ void __launch_bounds__(256)
 conv_splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long split_stride, long long NV, int C,
                           int relu, __nv_bfloat16* __restrict__ y, int ldy, int y_coff) {
+  pdl_prologue();
   const int C4 = C >> 2;
   const long long total = NV * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -452,17 +454,17 @@ static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpa
   long long grid = work_items < num_sms() ? work_items : num_sms();
   if (p.KC == 64) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    conv3d_igemm_kernel<64><<<(unsigned)grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+    B2_LAUNCH(conv3d_igemm_kernel<64>, (unsigned)grid, kThreads, smem_bytes, stream, ta, tb, p);
   } else {
     B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    conv3d_igemm_kernel<32><<<(unsigned)grid, kThreads, smem_bytes, stream>>>(ta, tb, p);
+    B2_LAUNCH(conv3d_igemm_kernel<32>, (unsigned)grid, kThreads, smem_bytes, stream, ta, tb, p);
   }
   B2_CHECK_CUDA(cudaGetLastError());
   if (p.splits > 1) {
     const long long NV = (long long)N * D * H * W;
     long long rb = (NV * (Cout / 4) + 255) / 256;
     if (rb > num_sms() * 8) rb = num_sms() * 8;
-    conv_splitk_reduce_kernel<<<(unsigned)rb, 256, 0, stream>>>(splitk_ws, p.splits, p.split_stride, NV, Cout,
+    B2_LAUNCH(conv_splitk_reduce_kernel, (unsigned)rb, 256, 0, stream, splitk_ws, p.splits, p.split_stride, NV, Cout,
                                                                 user_relu, reinterpret_cast<__nv_bfloat16*>(y),
                                                                 user_ldy, user_coff);
     B2_CHECK_CUDA(cudaGetLastError());

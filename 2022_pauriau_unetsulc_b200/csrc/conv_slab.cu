@@ -47,6 +47,7 @@ template <int KC>
 __global__ void __launch_bounds__(kSlabThreads, 1)
 conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const SlabParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kRowBytes = KC * 2;
@@ -349,10 +350,10 @@ int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, 
   long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   if (KC == 64) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    conv3d_slab_kernel<64><<<(unsigned)grid, kSlabThreads, smem_bytes, stream>>>(ta, tb, p);
+    B2_LAUNCH(conv3d_slab_kernel<64>, (unsigned)grid, kSlabThreads, smem_bytes, stream, ta, tb, p);
   } else {
     B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    conv3d_slab_kernel<32><<<(unsigned)grid, kSlabThreads, smem_bytes, stream>>>(ta, tb, p);
+    B2_LAUNCH(conv3d_slab_kernel<32>, (unsigned)grid, kSlabThreads, smem_bytes, stream, ta, tb, p);
   }
   B2_CHECK_CUDA(cudaGetLastError());
   if (n_partials) *n_partials = (int)grid;

@@ -42,6 +42,7 @@ static constexpr int kWgThreads = 32 * (1 + kWgProducers + 1 + 4);
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                     const WgradParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem;                                   // 2 x dY tile
@@ -214,6 +215,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 // co (128-byte runs), writes run along (ci, tap) (864-byte runs) through a padded shared-memory transpose.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int Cin, int Cout) {
+  pdl_prologue();
   __shared__ float t[32 * 217];
   const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 8;
   const long long total = 27LL * Cin * Cout;
@@ -234,6 +236,7 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int sp
 // small layers (few (co, ci) tiles): one thread per element, all splits summed in registers
 __global__ void __launch_bounds__(256)
 wgrad_reduce_simple_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int Cin, int Cout) {
+  pdl_prologue();
   const long long total = 27LL * Cin * Cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -254,6 +257,7 @@ wgrad_reduce_simple_kernel(const float* __restrict__ ws, float* __restrict__ dw,
 // roles swapped (see b2_conv3d_wgrad): ws[s][tap'][co][ci] with tap' = 26 - tap  ->  dW[co][ci][tap]
 __global__ void __launch_bounds__(256)
 wgrad_reduce_swapped_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int Cin, int Cout) {
+  pdl_prologue();
   const long long total = 27LL * Cin * Cout;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -367,16 +371,16 @@ extern "C" int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* d
   const size_t smem_bytes = 2 * (size_t)p.b_bytes + (size_t)p.stages_a * p.a_bytes + 1024 + 512;
   B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   dim3 grid((unsigned)(p.n_gchunks * p.n_cout_tiles), (unsigned)p.splits);
-  conv3d_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tx, ty, p);
+  B2_LAUNCH(conv3d_wgrad_kernel, grid, kWgThreads, smem_bytes, stream, tx, ty, p);
   B2_CHECK_CUDA(cudaGetLastError());
   if (swap) {
     const long long total = 27LL * Cin * Cout;
-    wgrad_reduce_swapped_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p.ws, dw, p.splits, Cin, Cout);
+    B2_LAUNCH(wgrad_reduce_swapped_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, p.ws, dw, p.splits, Cin, Cout);
   } else if ((Cout / 32) * (Cin / 8) >= 2 * num_sms()) {
-    wgrad_reduce_kernel<<<dim3(Cout / 32, Cin / 8), 256, 0, stream>>>(p.ws, dw, p.splits, Cin, Cout);
+    B2_LAUNCH(wgrad_reduce_kernel, dim3(Cout / 32, Cin / 8), 256, 0, stream, p.ws, dw, p.splits, Cin, Cout);
   } else {
     const long long total = 27LL * Cin * Cout;
-    wgrad_reduce_simple_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p.ws, dw, p.splits, Cin, Cout);
+    B2_LAUNCH(wgrad_reduce_simple_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, p.ws, dw, p.splits, Cin, Cout);
   }
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;

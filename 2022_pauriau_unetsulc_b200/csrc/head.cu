@@ -26,6 +26,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __global__ void count_labelled_kernel(const long long* __restrict__ labels, long long n, int* __restrict__ count) {
+  pdl_prologue();
   int c = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     c += (labels[i] >= 0) ? 1 : 0;
@@ -115,6 +116,7 @@ head_ce_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict_
                float grad_scale, const float* __restrict__ grad_scale_dev, int compute_grad, int eval_softmax,
                int* __restrict__ preds, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial,
                long long per_block) {
+  pdl_prologue();
   constexpr int WS = CIN + 4;        // padded row strides (floats)
   constexpr int DS = kMaxCo + 1;
   constexpr int CPT = CIN / 4;       // channels per thread in the dX and dW phases
@@ -328,6 +330,7 @@ __global__ void __launch_bounds__(256)
 head_ce_finalize_kernel(const float* __restrict__ partial, int nblocks, int Cin, int Cout,
                         const int* __restrict__ count, float* __restrict__ dW, float* __restrict__ db,
                         float* __restrict__ loss_out /*[2]: mean loss, sum*/) {
+  pdl_prologue();
   __shared__ double red[8][32];
   const int stride = kMaxCo * Cin + kMaxCo + 1;
   const int o = threadIdx.x & 31, rg = threadIdx.x >> 5;
@@ -366,6 +369,7 @@ __global__ void __launch_bounds__(256)
 head_gather_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ index, long long nidx,
                    const float* __restrict__ W, const float* __restrict__ b, int Cout, int softmax,
                    float* __restrict__ scores /*[nidx][Cout]*/, int* __restrict__ preds) {
+  pdl_prologue();
   extern __shared__ float shm[];
   float* Wt = shm;
   float* bs = Wt + CIN * kMaxCo;
@@ -394,6 +398,7 @@ template <int CIN>
 __global__ void __launch_bounds__(128)
 head_dense_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long V, int N, const float* __restrict__ W,
                       const float* __restrict__ b, int Cout, int softmax, float* __restrict__ out /*[N][Cout][V]*/) {
+  pdl_prologue();
   __shared__ float Ws[kMaxCo * CIN];
   __shared__ float bs[kMaxCo];
   for (int i = threadIdx.x; i < kMaxCo * CIN; i += blockDim.x) Ws[i] = (i < Cout * CIN) ? W[i] : 0.f;
@@ -454,6 +459,7 @@ __global__ void __launch_bounds__(128)
 head_dense_bwd_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ x, long long V, int N,
                       const float* __restrict__ W, int Cout, __nv_bfloat16* __restrict__ dx,
                       float* __restrict__ partial /*[grid][kMaxCo*CIN + kMaxCo]*/) {
+  pdl_prologue();
   extern __shared__ float shm[];
   float* Ws = shm;                          // [kMaxCo][CIN]
   float* gs = Ws + kMaxCo * CIN;            // [128][kMaxCo]
@@ -536,6 +542,7 @@ head_dense_bwd_kernel(const float* __restrict__ g, const __nv_bfloat16* __restri
 
 __global__ void head_dense_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, int Cin, int Cout,
                                                float* __restrict__ dW, float* __restrict__ db) {
+  pdl_prologue();
   const int stride = kMaxCo * Cin + kMaxCo;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= stride) return;
@@ -575,7 +582,7 @@ extern "C" int b2_head_ce(const void* x, const long long* labels, long long NV, 
   if (compute_grad && dx) B2_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)NV * Cin * 2, stream));
   int cblocks = (int)((NV + 255) / 256);
   if (cblocks > num_sms() * 8) cblocks = num_sms() * 8;
-  count_labelled_kernel<<<cblocks, 256, 0, stream>>>(labels, NV, count_out);
+  B2_LAUNCH(count_labelled_kernel, cblocks, 256, 0, stream, labels, NV, count_out);
   B2_CHECK_CUDA(cudaGetLastError());
   B2_REQUIRE(NV < (1LL << 31), "b2_head_ce: %lld voxels unsupported", NV);
   const size_t sh = (size_t)(kMaxCo * (Cin + 4) + kMaxCo + kCeGroup * (kMaxCo + 1) + kCeGroup * (Cin + 4) + kCeGroup) *
@@ -587,18 +594,18 @@ extern "C" int b2_head_ce(const void* x, const long long* labels, long long NV, 
   auto* dxb = reinterpret_cast<__nv_bfloat16*>(dx);
   if (Cin == 64) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(head_ce_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    head_ce_kernel<64><<<kCeBlocks, kCeThreads, sh, stream>>>(xb, labels, NV, W, b, Cout, count_out, grad_scale,
+    B2_LAUNCH(head_ce_kernel<64>, kCeBlocks, kCeThreads, sh, stream, xb, labels, NV, W, b, Cout, count_out, grad_scale,
                                                               grad_scale_dev, compute_grad, eval_softmax, preds, dxb,
                                                               partial, per_block);
   } else {
     B2_CHECK_CUDA(cudaFuncSetAttribute(head_ce_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    head_ce_kernel<32><<<kCeBlocks, kCeThreads, sh, stream>>>(xb, labels, NV, W, b, Cout, count_out, grad_scale,
+    B2_LAUNCH(head_ce_kernel<32>, kCeBlocks, kCeThreads, sh, stream, xb, labels, NV, W, b, Cout, count_out, grad_scale,
                                                               grad_scale_dev, compute_grad, eval_softmax, preds, dxb,
                                                               partial, per_block);
   }
   B2_CHECK_CUDA(cudaGetLastError());
   const int stride = kMaxCo * Cin + kMaxCo + 1;
-  head_ce_finalize_kernel<<<(stride + 31) / 32, 256, 0, stream>>>(partial, kCeBlocks, Cin, Cout, count_out,
+  B2_LAUNCH(head_ce_finalize_kernel, (stride + 31) / 32, 256, 0, stream, partial, kCeBlocks, Cin, Cout, count_out,
                                                                    compute_grad ? dW : nullptr,
                                                                    compute_grad ? db : nullptr, loss_out);
   B2_CHECK_CUDA(cudaGetLastError());
@@ -616,9 +623,9 @@ extern "C" int b2_head_gather(const void* x, const long long* index, long long n
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   auto* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   if (Cin == 64)
-    head_gather_kernel<64><<<blocks, 256, sh, stream>>>(xb, index, nidx, W, b, Cout, softmax, scores, preds);
+    B2_LAUNCH(head_gather_kernel<64>, blocks, 256, sh, stream, xb, index, nidx, W, b, Cout, softmax, scores, preds);
   else
-    head_gather_kernel<32><<<blocks, 256, sh, stream>>>(xb, index, nidx, W, b, Cout, softmax, scores, preds);
+    B2_LAUNCH(head_gather_kernel<32>, blocks, 256, sh, stream, xb, index, nidx, W, b, Cout, softmax, scores, preds);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }
@@ -631,9 +638,9 @@ extern "C" int b2_head_dense_fwd(const void* x, int N, long long V, const float*
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   auto* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   if (Cin == 64)
-    head_dense_fwd_kernel<64><<<(unsigned)blocks, 128, 0, stream>>>(xb, V, N, W, b, Cout, softmax, out);
+    B2_LAUNCH(head_dense_fwd_kernel<64>, (unsigned)blocks, 128, 0, stream, xb, V, N, W, b, Cout, softmax, out);
   else
-    head_dense_fwd_kernel<32><<<(unsigned)blocks, 128, 0, stream>>>(xb, V, N, W, b, Cout, softmax, out);
+    B2_LAUNCH(head_dense_fwd_kernel<32>, (unsigned)blocks, 128, 0, stream, xb, V, N, W, b, Cout, softmax, out);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }
@@ -650,14 +657,14 @@ extern "C" int b2_head_dense_bwd(const float* g, const void* x, int N, long long
   auto* dxb = reinterpret_cast<__nv_bfloat16*>(dx);
   if (Cin == 64) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(head_dense_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    head_dense_bwd_kernel<64><<<kCeBlocks, 128, sh, stream>>>(g, xb, V, N, W, Cout, dxb, partial);
+    B2_LAUNCH(head_dense_bwd_kernel<64>, kCeBlocks, 128, sh, stream, g, xb, V, N, W, Cout, dxb, partial);
   } else {
     B2_CHECK_CUDA(cudaFuncSetAttribute(head_dense_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    head_dense_bwd_kernel<32><<<kCeBlocks, 128, sh, stream>>>(g, xb, V, N, W, Cout, dxb, partial);
+    B2_LAUNCH(head_dense_bwd_kernel<32>, kCeBlocks, 128, sh, stream, g, xb, V, N, W, Cout, dxb, partial);
   }
   B2_CHECK_CUDA(cudaGetLastError());
   const int stride = kMaxCo * Cin + kMaxCo;
-  head_dense_bwd_finalize_kernel<<<(stride + 127) / 128, 128, 0, stream>>>(partial, kCeBlocks, Cin, Cout, dW, db);
+  B2_LAUNCH(head_dense_bwd_finalize_kernel, (stride + 127) / 128, 128, 0, stream, partial, kCeBlocks, Cin, Cout, dW, db);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(kStatThreads)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ r, long long V, int C, float* __restrict__ partial, int* counters,
                 int G, float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float* __restrict__ mean_rstd, float* __restrict__ scale_shift) {
+  pdl_prologue();
   extern __shared__ float sh[];  // [vpi][C][2]
   const int C8 = C >> 3;
   const int vpi = kStatThreads / C8;
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(1024)
 gn_finalize_partials_kernel(const float* __restrict__ partial, int nblk, int C, int G, long long V, float eps,
                             const float* __restrict__ gamma, const float* __restrict__ beta,
                             float* __restrict__ mean_rstd, float* __restrict__ scale_shift) {
+  pdl_prologue();
   extern __shared__ float sh[];
   double* csum = reinterpret_cast<double*>(sh);
   reduce_partials(partial, 0, nblk, C, csum);
@@ -176,6 +178,7 @@ gn_finalize_partials_kernel(const float* __restrict__ partial, int nblk, int C, 
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ r, long long V, int C, const float* __restrict__ scale_shift,
                 __nv_bfloat16* __restrict__ y, int ldy, int y_coff) {
+  pdl_prologue();
   const int C8 = C >> 3;
   const int n = blockIdx.y;
   const int oct = threadIdx.x % C8;
@@ -214,6 +217,7 @@ __global__ void __launch_bounds__(256)
 gn_apply_pool_kernel(const __nv_bfloat16* __restrict__ r, int N, int D, int H, int W, int C,
                      const float* __restrict__ scale_shift, __nv_bfloat16* __restrict__ y, int ldy, int y_coff,
                      __nv_bfloat16* __restrict__ pooled /*[N][D/2][H/2][W/2][C]*/) {
+  pdl_prologue();
   const int C8 = C >> 3;
   const int Dc = (D + 1) >> 1, Hc = (H + 1) >> 1, Wc = (W + 1) >> 1;
   const int Dp = D >> 1, Hp = H >> 1, Wp = W >> 1;
@@ -267,6 +271,7 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
                     long long V, int C, const float* __restrict__ mean_rstd, float* __restrict__ partial,
                     int* counters, int N, int G, const float* __restrict__ gamma, float* __restrict__ coef,
                     float* __restrict__ dgb_n /*[N][C][2]*/, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_prologue();
   extern __shared__ float sh[];
   const int C8 = C >> 3;
   const int vpi = kStatThreads / C8;
@@ -369,6 +374,7 @@ __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff, const __nv_bfloat16* __restrict__ r,
                     long long V, int C, const float* __restrict__ mean_rstd, const float* __restrict__ coef,
                     __nv_bfloat16* __restrict__ dr) {
+  pdl_prologue();
   const int C8 = C >> 3;
   const int n = blockIdx.y;
   const int oct = threadIdx.x % C8;
@@ -423,6 +429,7 @@ __global__ void __launch_bounds__(1024)
 gn_bwd_finalize_partials_kernel(const float* __restrict__ partial, int nblk, int C, int G, long long V,
                                 const float* __restrict__ gamma, const float* __restrict__ mean_rstd,
                                 float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_prologue();
   extern __shared__ float sh[];
   double* csum = reinterpret_cast<double*>(sh);
   reduce_partials(partial, 0, nblk, C, csum);
@@ -507,7 +514,7 @@ extern "C" int b2_relu_gn_stats(const void* r, int N, long long V, int C, int G,
   const int nblk = stat_blocks(V, C);
   const int vpi = kStatThreads / (C / 8);
   const size_t sh = (size_t)vpi * C * 2 * sizeof(float);
-  gn_stats_kernel<<<dim3(nblk, N), kStatThreads, sh, stream>>>(reinterpret_cast<const __nv_bfloat16*>(r), V, C,
+  B2_LAUNCH(gn_stats_kernel, dim3(nblk, N), kStatThreads, sh, stream, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
                                                                reinterpret_cast<float*>(workspace), counters, G, eps,
                                                                gamma, beta, mean_rstd, scale_shift);
   B2_CHECK_CUDA(cudaGetLastError());
@@ -522,7 +529,7 @@ extern "C" int b2_relu_gn_finalize(const float* stat_partial, int n_partials, lo
              "b2_relu_gn_finalize: null pointer");
   int rc = check_gn_shape("b2_relu_gn_finalize", 1, V, C, G);
   if (rc) return rc;
-  gn_finalize_partials_kernel<<<1, 1024, (size_t)C * 2 * sizeof(double), stream>>>(
+  B2_LAUNCH(gn_finalize_partials_kernel, 1, 1024, (size_t)C * 2 * sizeof(double), stream, 
       stat_partial, n_partials, C, G, V, eps, gamma, beta, mean_rstd, scale_shift);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
@@ -536,12 +543,12 @@ extern "C" int b2_relu_gn_apply(const void* r, int N, int D, int H, int W, int C
   const long long V = (long long)D * H * W;
   if (pooled) {
     const long long total = (long long)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-    gn_apply_pool_kernel<<<ew_blocks(total), 256, 0, stream>>>(
+    B2_LAUNCH(gn_apply_pool_kernel, ew_blocks(total), 256, 0, stream, 
         reinterpret_cast<const __nv_bfloat16*>(r), N, D, H, W, C, scale_shift, reinterpret_cast<__nv_bfloat16*>(y), ldy,
         y_coff, reinterpret_cast<__nv_bfloat16*>(pooled));
   } else {
     B2_REQUIRE(256 % (C / 8) == 0, "b2_relu_gn_apply: C=%d unsupported", C);
-    gn_apply_kernel<<<dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream>>>(
+    B2_LAUNCH(gn_apply_kernel, dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream, 
         reinterpret_cast<const __nv_bfloat16*>(r), V, C, scale_shift, reinterpret_cast<__nv_bfloat16*>(y), ldy, y_coff);
   }
   B2_CHECK_CUDA(cudaGetLastError());
@@ -564,11 +571,11 @@ extern "C" int b2_relu_gn_bwd(const void* dy, int lddy, int dy_coff, const void*
   const int nblk = stat_blocks(V, C);
   const int vpi = kStatThreads / (C / 8);
   const size_t sh = (size_t)vpi * C * 2 * sizeof(float);
-  gn_bwd_stats_kernel<<<dim3(nblk, N), kStatThreads, sh, stream>>>(
+  B2_LAUNCH(gn_bwd_stats_kernel, dim3(nblk, N), kStatThreads, sh, stream, 
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
       mean_rstd, partial, counters, N, G, gamma, coef, dgb_n, dgamma, dbeta);
   B2_CHECK_CUDA(cudaGetLastError());
-  gn_bwd_apply_kernel<<<dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream>>>(
+  B2_LAUNCH(gn_bwd_apply_kernel, dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
       mean_rstd, coef, reinterpret_cast<__nv_bfloat16*>(dr));
   B2_CHECK_CUDA(cudaGetLastError());
@@ -592,10 +599,10 @@ extern "C" int b2_relu_gn_bwd_from_partials(const float* stat_partial, int n_par
   B2_REQUIRE(workspace_bytes >= (long long)C * 4 * (long long)sizeof(float),
              "b2_relu_gn_bwd_from_partials: workspace too small");
   float* coef = reinterpret_cast<float*>(workspace);
-  gn_bwd_finalize_partials_kernel<<<1, 1024, (size_t)C * 2 * sizeof(double), stream>>>(
+  B2_LAUNCH(gn_bwd_finalize_partials_kernel, 1, 1024, (size_t)C * 2 * sizeof(double), stream, 
       stat_partial, n_partials, C, G, V, gamma, mean_rstd, coef, dgamma, dbeta);
   B2_CHECK_CUDA(cudaGetLastError());
-  gn_bwd_apply_kernel<<<dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream>>>(
+  B2_LAUNCH(gn_bwd_apply_kernel, dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
       mean_rstd, coef, reinterpret_cast<__nv_bfloat16*>(dr));
   B2_CHECK_CUDA(cudaGetLastError());

@@ -21,6 +21,7 @@ struct SgdArgs {
 };
 
 __global__ void __launch_bounds__(256) sgd_multi_kernel(const SgdArgs a) {
+  pdl_prologue();
   int t = 0;
   while (t + 1 < a.count && (int)blockIdx.x >= a.first_block[t + 1]) ++t;
   const long long base = (long long)(blockIdx.x - a.first_block[t]) * kChunk;
@@ -54,38 +55,56 @@ struct PackArgs {
   int count;
 };
 
+// one (16 co x TW ci) tile; TW is a compile-time constant so that every index split is a multiply-shift
+template <int TW>
+__device__ __forceinline__ void pack_tile(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                          __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int co0, int ci0,
+                                          __nv_bfloat16 (*tile)[kPkCi * 27 + 2]) {
+  constexpr int RUN4 = TW * 27 / 4;   // float4 per co row
+  for (int e = threadIdx.x; e < kPkCo * RUN4; e += 256) {
+    const int j = e / RUN4, r4 = e - j * RUN4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(w + ((size_t)(co0 + j) * Cin + ci0) * 27) + r4);
+    __nv_bfloat162* d = reinterpret_cast<__nv_bfloat162*>(&tile[j][4 * r4]);   // r = ci*27 + tap
+    d[0] = __floats2bfloat162_rn(v.x, v.y);
+    d[1] = __floats2bfloat162_rn(v.z, v.w);
+  }
+  __syncthreads();
+  if (wf != nullptr) {
+    for (int e = threadIdx.x; e < 27 * kPkCo * (TW / 2); e += 256) {
+      const int ci = (e % (TW / 2)) * 2, row = e / (TW / 2);
+      const int j = row % kPkCo, tap = row / kPkCo;
+      __nv_bfloat162 o;
+      o.x = tile[j][ci * 27 + tap];
+      o.y = tile[j][(ci + 1) * 27 + tap];
+      *reinterpret_cast<__nv_bfloat162*>(wf + ((size_t)tap * Cout + co0 + j) * Cin + ci0 + ci) = o;
+    }
+  }
+  if (wd != nullptr) {
+    for (int e = threadIdx.x; e < 27 * TW * (kPkCo / 2); e += 256) {
+      const int j = (e % (kPkCo / 2)) * 2, row = e / (kPkCo / 2);
+      const int ci = row % TW, tap = row / TW;
+      __nv_bfloat162 o;
+      o.x = tile[j][ci * 27 + tap];
+      o.y = tile[j + 1][ci * 27 + tap];
+      *reinterpret_cast<__nv_bfloat162*>(wd + ((size_t)(26 - tap) * Cin + ci0 + ci) * Cout + co0 + j) = o;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(16) uint8_t pack_smem[];
   auto tile = reinterpret_cast<__nv_bfloat16(*)[kPkCi * 27 + 2]>(pack_smem);   // [kPkCo][..], odd word stride
   int l = 0;
   while (l + 1 < a.count && (int)blockIdx.x >= a.first_block[l + 1]) ++l;
   const int Cout = a.cout[l], Cin = a.cin[l];
-  const float* __restrict__ w = a.w[l];
   const int b = blockIdx.x - a.first_block[l];
-  const int ci_tiles = (Cin + kPkCi - 1) / kPkCi;
-  const int co0 = (b / ci_tiles) * kPkCo, ci0 = (b % ci_tiles) * kPkCi;
-  const int th = min(kPkCo, Cout - co0), tw = min(kPkCi, Cin - ci0);
-  const int run = tw * 27;
-  for (int e = threadIdx.x; e < th * run; e += 256) {
-    const int j = e / run, r = e - j * run;   // r = ci*27 + tap
-    tile[j][r] = __float2bfloat16_rn(w[((size_t)(co0 + j) * Cin + ci0) * 27 + r]);
-  }
-  __syncthreads();
-  if (a.wf[l] != nullptr) {
-    __nv_bfloat16* dst = a.wf[l];
-    for (int e = threadIdx.x; e < 27 * th * tw; e += 256) {
-      const int ci = e % tw, t2 = e / tw;
-      const int j = t2 % th, tap = t2 / th;
-      dst[((size_t)tap * Cout + co0 + j) * Cin + ci0 + ci] = tile[j][ci * 27 + tap];
-    }
-  }
-  if (a.wd[l] != nullptr) {
-    __nv_bfloat16* dst = a.wd[l];
-    for (int e = threadIdx.x; e < 27 * tw * th; e += 256) {
-      const int j = e % th, t2 = e / th;
-      const int ci = t2 % tw, tap = t2 / tw;
-      dst[((size_t)(26 - tap) * Cin + ci0 + ci) * Cout + co0 + j] = tile[j][ci * 27 + tap];
-    }
+  if (Cin % 64 == 0) {
+    const int ci_tiles = Cin / 64;
+    pack_tile<64>(a.w[l], a.wf[l], a.wd[l], Cout, Cin, (b / ci_tiles) * kPkCo, (b % ci_tiles) * 64, tile);
+  } else {
+    const int ci_tiles = Cin / 32;
+    pack_tile<32>(a.w[l], a.wf[l], a.wd[l], Cout, Cin, (b / ci_tiles) * kPkCo, (b % ci_tiles) * 32, tile);
   }
 }
 
@@ -119,7 +138,7 @@ extern "C" int b2_sgd_step(float* const* params, const float* const* grads, floa
     a.momentum = momentum;
     a.grad_scale = grad_scale;
     if (blocks > 0) {
-      sgd_multi_kernel<<<blocks, 256, 0, stream>>>(a);
+      B2_LAUNCH(sgd_multi_kernel, blocks, 256, 0, stream, a);
       B2_CHECK_CUDA(cudaGetLastError());
     }
     done += k;
@@ -144,7 +163,10 @@ extern "C" int b2_pack_conv_weights_multi(const float* const* w, void* const* wf
       a.cout[k] = cout[i];
       a.cin[k] = cin[i];
       a.first_block[k] = blocks;
-      blocks += ((cout[i] + kPkCo - 1) / kPkCo) * ((cin[i] + kPkCi - 1) / kPkCi);
+      B2_REQUIRE(cout[i] % kPkCo == 0 && cin[i] % 32 == 0,
+                 "b2_pack_conv_weights_multi: layer %d: Cout=%d must be a multiple of 16 and Cin=%d of 32", i, cout[i],
+                 cin[i]);
+      blocks += (cout[i] / kPkCo) * (cin[i] % 64 == 0 ? cin[i] / 64 : cin[i] / 32);
       ++k;
     }
     a.first_block[k] = blocks;
@@ -152,7 +174,7 @@ extern "C" int b2_pack_conv_weights_multi(const float* const* w, void* const* wf
     if (blocks > 0) {
       const int sh = kPkCo * (kPkCi * 27 + 2) * 2;
       B2_CHECK_CUDA(cudaFuncSetAttribute(pack_weights_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh));
-      pack_weights_multi_kernel<<<blocks, 256, sh, stream>>>(a);
+      B2_LAUNCH(pack_weights_multi_kernel, blocks, 256, sh, stream, a);
       B2_CHECK_CUDA(cudaGetLastError());
     }
     done += k;

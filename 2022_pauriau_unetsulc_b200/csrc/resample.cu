@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256)
 pool_bwd_add_kernel(const __nv_bfloat16* __restrict__ y, int ldy, int y_coff, const __nv_bfloat16* __restrict__ dskip,
                     int ldd, int d_coff, const __nv_bfloat16* __restrict__ dpool, __nv_bfloat16* __restrict__ out,
                     int N, int D, int H, int W, int C) {
+  pdl_prologue();
   const int C8 = C >> 3;
   const int Dc = (D + 1) >> 1, Hc = (H + 1) >> 1, Wc = (W + 1) >> 1;
   const int Dp = D >> 1, Hp = H >> 1, Wp = W >> 1;
@@ -94,6 +95,7 @@ static constexpr int kMaxTouch = 8;   // fine samples that can touch one coarse 
 __global__ void __launch_bounds__(256)
 upsample_cat_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int Di, int Hi, int Wi, int C,
                         __nv_bfloat16* __restrict__ cat, int ldc, int coff, int Do, int Ho, int Wo) {
+  pdl_prologue();
   __shared__ int s_i0[kMaxUpW], s_i1[kMaxUpW];
   __shared__ float s_l1[kMaxUpW];
   const int C8 = C >> 3;
@@ -160,6 +162,7 @@ __device__ __forceinline__ Cell2x cell2x(int j, int n_in) {
 __global__ void __launch_bounds__(256)
 upsample2x_cat_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int Di, int Hi, int Wi, int C,
                           __nv_bfloat16* __restrict__ cat, int ldc, int coff) {
+  pdl_prologue();
   const int C8 = C >> 3;
   const int Do = 2 * Di, Ho = 2 * Hi, Wo = 2 * Wi;
   const long long total = (long long)N * (Di + 1) * (Hi + 1) * (Wi + 1) * C8;
@@ -248,6 +251,7 @@ __device__ __forceinline__ int touch_list(int i, float scale, int in_size, int o
 __global__ void __launch_bounds__(256)
 upsample_cat_bwd_kernel(const __nv_bfloat16* __restrict__ dcat, int ldc, int coff, int N, int Do, int Ho, int Wo,
                         __nv_bfloat16* __restrict__ dx, int Di, int Hi, int Wi, int C) {
+  pdl_prologue();
   __shared__ int s_cnt[kMaxUpW];
   __shared__ int s_idx[kMaxUpW][kMaxTouch];
   __shared__ float s_wt[kMaxUpW][kMaxTouch];
@@ -299,6 +303,7 @@ upsample_cat_bwd_kernel(const __nv_bfloat16* __restrict__ dcat, int ldc, int cof
 __global__ void __launch_bounds__(256)
 upsample_bwd_w_kernel(const __nv_bfloat16* __restrict__ dcat, int ldc, int coff, int Wo, __nv_bfloat16* __restrict__ t,
                       int Wi, int C) {
+  pdl_prologue();
   __shared__ int s_cnt[kMaxUpW];
   __shared__ int s_idx[kMaxUpW][kMaxTouch];
   __shared__ float s_wt[kMaxUpW][kMaxTouch];
@@ -337,6 +342,7 @@ upsample_bwd_w_kernel(const __nv_bfloat16* __restrict__ dcat, int ldc, int coff,
 __global__ void __launch_bounds__(256)
 upsample_bwd_hd_kernel(const __nv_bfloat16* __restrict__ t, int Do, int Ho, __nv_bfloat16* __restrict__ dx, int Di,
                        int Hi, int Wi, int C) {
+  pdl_prologue();
   const int row = blockIdx.x;
   const int h = row % Hi, d = (row / Hi) % Di, n = row / (Hi * Di);
   const float sd = (float)Di / (float)Do, shh = (float)Hi / (float)Ho;
@@ -376,7 +382,7 @@ extern "C" int b2_maxpool3d_bwd_add(const void* y, int ldy, int y_coff, const vo
   B2_REQUIRE(C % 8 == 0 && ldy % 8 == 0 && y_coff % 8 == 0 && ldd % 8 == 0 && d_coff % 8 == 0,
              "b2_maxpool3d_bwd_add: channel counts must be multiples of 8");
   const long long total = (long long)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  pool_bwd_add_kernel<<<ew_blocks(total), 256, 0, stream>>>(
+  B2_LAUNCH(pool_bwd_add_kernel, ew_blocks(total), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(y), ldy, y_coff, reinterpret_cast<const __nv_bfloat16*>(dskip), ldd, d_coff,
       reinterpret_cast<const __nv_bfloat16*>(dpool), reinterpret_cast<__nv_bfloat16*>(out), N, D, H, W, C);
   B2_CHECK_CUDA(cudaGetLastError());
@@ -391,12 +397,12 @@ extern "C" int b2_upcat_fwd(const void* x, int N, int Di, int Hi, int Wi, int C,
   B2_REQUIRE((long long)Wi * C < (1LL << 31) && (long long)Wo * ldc < (1LL << 31), "b2_upcat_fwd: row too large");
   if (Do == 2 * Di && Ho == 2 * Hi && Wo == 2 * Wi) {
     const long long total = (long long)N * (Di + 1) * (Hi + 1) * (Wi + 1) * (C / 8);
-    upsample2x_cat_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+    B2_LAUNCH(upsample2x_cat_fwd_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, 
         reinterpret_cast<const __nv_bfloat16*>(x), N, Di, Hi, Wi, C, reinterpret_cast<__nv_bfloat16*>(cat), ldc, coff);
     B2_CHECK_CUDA(cudaGetLastError());
     return B2_OK;
   }
-  upsample_cat_fwd_kernel<<<(unsigned)(N * Do * Ho), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, Di, Hi,
+  B2_LAUNCH(upsample_cat_fwd_kernel, (unsigned)(N * Do * Ho), 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x), N, Di, Hi,
                                                                 Wi, C, reinterpret_cast<__nv_bfloat16*>(cat), ldc, coff,
                                                                 Do, Ho, Wo);
   B2_CHECK_CUDA(cudaGetLastError());
@@ -418,10 +424,10 @@ extern "C" int b2_upcat_bwd_separable(const void* dcat, int ldc, int coff, int N
   B2_REQUIRE((long long)Wo * ldc < (1LL << 31) && (long long)Wi * C < (1LL << 31), "b2_upcat_bwd_separable: row too large");
   B2_REQUIRE(workspace_bytes >= b2_upcat_bwd_workspace_bytes(N, Do, Ho, Wi, C), "b2_upcat_bwd_separable: workspace too small");
   __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(workspace);
-  upsample_bwd_w_kernel<<<(unsigned)(N * Do * Ho), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dcat), ldc,
+  B2_LAUNCH(upsample_bwd_w_kernel, (unsigned)(N * Do * Ho), 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(dcat), ldc,
                                                                       coff, Wo, t, Wi, C);
   B2_CHECK_CUDA(cudaGetLastError());
-  upsample_bwd_hd_kernel<<<(unsigned)(N * Di * Hi), 256, 0, stream>>>(t, Do, Ho, reinterpret_cast<__nv_bfloat16*>(dx),
+  B2_LAUNCH(upsample_bwd_hd_kernel, (unsigned)(N * Di * Hi), 256, 0, stream, t, Do, Ho, reinterpret_cast<__nv_bfloat16*>(dx),
                                                                       Di, Hi, Wi, C);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
@@ -434,7 +440,7 @@ extern "C" int b2_upcat_bwd(const void* dcat, int ldc, int coff, int N, int Do, 
   B2_REQUIRE(Wo <= kMaxUpW && Wi <= kMaxUpW, "b2_upcat_bwd: row width %d > %d", Wo, kMaxUpW);
   B2_REQUIRE(2 * Do <= 7 * Di && 2 * Ho <= 7 * Hi && 2 * Wo <= 7 * Wi, "b2_upcat_bwd: upsampling ratio > 3.5 unsupported");
   B2_REQUIRE((long long)Wo * ldc < (1LL << 31), "b2_upcat_bwd: row too large");
-  upsample_cat_bwd_kernel<<<(unsigned)(N * Di * Hi), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dcat), ldc, coff,
+  B2_LAUNCH(upsample_cat_bwd_kernel, (unsigned)(N * Di * Hi), 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(dcat), ldc, coff,
                                                                 N, Do, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(dx), Di,
                                                                 Hi, Wi, C);
   B2_CHECK_CUDA(cudaGetLastError());

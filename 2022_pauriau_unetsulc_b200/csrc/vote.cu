@@ -10,6 +10,7 @@ namespace b2 {
 __global__ void __launch_bounds__(256)
 vote_argmax_hist_kernel(const float* __restrict__ scores, const int* __restrict__ fold, long long n, int C,
                         int* __restrict__ lab, int* __restrict__ hist) {
+  pdl_prologue();
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
     const float* s = scores + v * C;
     float best = s[0];
@@ -27,6 +28,7 @@ vote_argmax_hist_kernel(const float* __restrict__ scores, const int* __restrict_
 __global__ void __launch_bounds__(128)
 vote_decide_kernel(const int* __restrict__ hist, int F, int C, const int* __restrict__ thresholds, int T,
                    int4* __restrict__ decision) {
+  pdl_prologue();
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   const int* h = hist + (long long)f * C;
@@ -45,6 +47,7 @@ vote_decide_kernel(const int* __restrict__ hist, int F, int C, const int* __rest
 __global__ void __launch_bounds__(256)
 vote_assign_kernel(const float* __restrict__ scores, const int* __restrict__ fold, long long n, int C, int F, int T,
                    const int4* __restrict__ decision, int* __restrict__ out /*[T][n]*/) {
+  pdl_prologue();
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < n; v += (long long)gridDim.x * blockDim.x) {
     const int f = fold[v];
     for (int t = 0; t < T; ++t) {
@@ -62,6 +65,7 @@ vote_assign_kernel(const float* __restrict__ scores, const int* __restrict__ fol
 __global__ void __launch_bounds__(256)
 esi_counts_kernel(const int* __restrict__ y_true, const int* __restrict__ y_pred, long long n, int C,
                   unsigned long long* __restrict__ counts /*[3][C]: TP, FP, FN*/) {
+  pdl_prologue();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int t = y_true[i], p = y_pred[i];
     if (t == p) {
@@ -95,11 +99,11 @@ extern "C" int b2_fold_vote(const float* scores, const int* fold, long long n, i
   B2_CHECK_CUDA(cudaMemsetAsync(hist, 0, (size_t)F * C * sizeof(int), stream));
   int blocks = (int)((n + 255) / 256);
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  vote_argmax_hist_kernel<<<blocks, 256, 0, stream>>>(scores, fold, n, C, lab, hist);
+  B2_LAUNCH(vote_argmax_hist_kernel, blocks, 256, 0, stream, scores, fold, n, C, lab, hist);
   B2_CHECK_CUDA(cudaGetLastError());
-  vote_decide_kernel<<<(F + 127) / 128, 128, 0, stream>>>(hist, F, C, thresholds, T, decision);
+  B2_LAUNCH(vote_decide_kernel, (F + 127) / 128, 128, 0, stream, hist, F, C, thresholds, T, decision);
   B2_CHECK_CUDA(cudaGetLastError());
-  vote_assign_kernel<<<blocks, 256, 0, stream>>>(scores, fold, n, C, F, T, decision, out);
+  B2_LAUNCH(vote_assign_kernel, blocks, 256, 0, stream, scores, fold, n, C, F, T, decision, out);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }
@@ -111,7 +115,7 @@ extern "C" int b2_esi_counts(const int* y_true, const int* y_pred, long long n, 
   B2_REQUIRE(y_true && y_pred && counts && C > 0, "b2_esi_counts: null pointer");
   int blocks = (int)((n + 255) / 256);
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-  esi_counts_kernel<<<blocks, 256, 0, stream>>>(y_true, y_pred, n, C, counts);
+  B2_LAUNCH(esi_counts_kernel, blocks, 256, 0, stream, y_true, y_pred, n, C, counts);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }
