@@ -16,17 +16,14 @@ SIGNATURES = {
     "b2_conv3d_igemm": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b2_conv3d_splitk_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
     "b2_conv3d_igemm_splitk": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
-    "b2_conv3d_stats_max_partials": (_i, []),
-    "b2_conv3d_igemm_stats": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "b2_conv3d_igemm_bstats": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "b2_relu_gn_bwd_from_partials": (_i, [_vp, _i, _vp, _i, _i, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll,
-                                          _vp]),
-    "b2_relu_gn_finalize": (_i, [_vp, _i, _ll, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "b2_conv3d_igemm_stats": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "b2_conv3d_igemm_bstats": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "b2_relu_gn_finalize_acc": (_i, [_vp, _ll, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "b2_relu_gn_bwd_acc": (_i, [_vp, _vp, _i, _i, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
     "b2_conv3d_wgrad_workspace_bytes": (_ll, [_i, _i, _i, _i, _i, _i]),
     "b2_conv3d_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
     "b2_conv3d_first_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "b2_conv3d_first_stats_max_partials": (_i, []),
-    "b2_conv3d_first_fwd_stats": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "b2_conv3d_first_fwd_stats": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "b2_conv3d_first_wgrad_workspace_bytes": (_ll, [_i]),
     "b2_conv3d_first_wgrad": (_i, [_vp, _vp, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     "b2_gn_workspace_bytes": (_ll, [_i, _i]),
@@ -35,12 +32,16 @@ SIGNATURES = {
     "b2_relu_gn_bwd_workspace_bytes": (_ll, [_i, _i]),
     "b2_relu_gn_bwd": (_i, [_vp, _i, _i, _vp, _i, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp]),
     "b2_maxpool3d_bwd_add": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b2_maxpool3d_bwd_add_bstats": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b2_upcat_fwd": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "b2_upcat_bwd": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "b2_upcat_bwd_workspace_bytes": (_ll, [_i, _i, _i, _i, _i]),
     "b2_upcat_bwd_separable": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _ll, _vp]),
+    "b2_upcat_bwd_separable_bstats": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp]),
     "b2_head_workspace_bytes": (_ll, [_i]),
     "b2_head_ce": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _f, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "b2_head_ce_bstats": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp,
+                               _vp, _vp]),
     "b2_head_gather": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "b2_head_dense_fwd": (_i, [_vp, _i, _ll, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "b2_head_dense_bwd": (_i, [_vp, _vp, _i, _ll, _vp, _i, _i, _vp, _vp, _vp, _vp, _ll, _vp]),

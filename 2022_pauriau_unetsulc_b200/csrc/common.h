@@ -48,6 +48,26 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 bool pdl_enabled();
 
 #ifdef __CUDACC__
+// ---- exact, order-independent statistics accumulators --------------------------------------------------------------
+// GroupNorm needs per-channel sums over the whole volume; the kernels that PRODUCE a tensor (conv epilogues, pooling /
+// upsampling backward, the head) add their per-block fp32 partial sums into a two-limb fixed-point accumulator
+// (int64 integer part + int64 fraction in units of 2^-32) with integer atomics.  Integer addition is associative, so
+// the total is bit-identical whatever the arrival order (no float atomics, run-to-run deterministic), and it is exact:
+// an fp32 value splits into rintf(p) and a fraction whose 2^32 multiple is an integer.  The kernels that CONSUME the
+// statistics (GroupNorm apply / backward apply) turn the accumulators into mean, rstd and coefficients in their
+// prologue — no partial buffers, no "last block" pass, no finalize launch.
+// Layout per channel: [4] = {sum_hi, sum_lo, sq_hi, sq_lo}.
+__device__ __forceinline__ void stat_atomic_add(long long* slot, float p) {
+  const float h = rintf(p);
+  const long long hi = (long long)h;
+  const long long lo = __float2ll_rn((p - h) * 4294967296.f);
+  if (hi != 0) atomicAdd(reinterpret_cast<unsigned long long*>(slot), (unsigned long long)hi);
+  if (lo != 0) atomicAdd(reinterpret_cast<unsigned long long*>(slot + 1), (unsigned long long)lo);
+}
+__device__ __forceinline__ double stat_read(const long long* slot) {
+  return (double)__ldcg(slot) + (double)__ldcg(slot + 1) * (1.0 / 4294967296.0);
+}
+
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

@@ -11,14 +11,14 @@ static constexpr int kMaxC1 = 64;
 
 // One warp per 32 consecutive voxels, lane = voxel.  All 27 neighbour loads are issued before any arithmetic (the
 // round-1 kernel walked the taps one dependent L1 load at a time and was latency-bound at 680 GB/s); a tap is skipped
-// when no lane of the warp has a non-zero input there.  When stat_partial != NULL the kernel also accumulates, per
+// when no lane of the warp has a non-zero input there.  When stat_acc != NULL the kernel also accumulates, per
 // channel, sum and sum of squares of the STORED (ReLU'd, bf16-rounded) outputs — the GroupNorm statistics — into
-// one fp32 [COUT][2] row per block (same partial layout as b2_conv3d_igemm_stats; finalised by b2_relu_gn_finalize).
+// the exact [COUT][4] accumulators of common.h (one atomic add per block and channel).
 template <int COUT>
 __global__ void __launch_bounds__(128)
 conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /*[COUT][27]*/,
                       __nv_bfloat16* __restrict__ y, int N, int D, int H, int W, int ldy, int y_coff, int relu,
-                      float* __restrict__ stat_partial) {
+                      long long* __restrict__ stat_acc) {
   pdl_prologue();
   __shared__ __align__(16) float ws[27][COUT];
   __shared__ float2 sred[4][COUT];
@@ -80,7 +80,7 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /
         dst[j] = o;
       }
     }
-    if (stat_partial != nullptr) {
+    if (stat_acc != nullptr) {
 #pragma unroll
       for (int k = 0; k < COUT / 32; ++k) {
         float xs[32], xq[32];
@@ -97,14 +97,14 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /
       }
     }
   }
-  if (stat_partial != nullptr) {
+  if (stat_acc != nullptr) {
 #pragma unroll
     for (int k = 0; k < COUT / 32; ++k) sred[warp][32 * k + lane] = make_float2(st_s[k], st_q[k]);
     __syncthreads();
     for (int c = threadIdx.x; c < COUT; c += blockDim.x) {
       const float2 a = sred[0][c], b = sred[1][c], cc = sred[2][c], d = sred[3][c];
-      reinterpret_cast<float2*>(stat_partial)[(size_t)blockIdx.x * COUT + c] =
-          make_float2((a.x + b.x) + (cc.x + d.x), (a.y + b.y) + (cc.y + d.y));
+      stat_atomic_add(stat_acc + 4 * c, (a.x + b.x) + (cc.x + d.x));
+      stat_atomic_add(stat_acc + 4 * c + 2, (a.y + b.y) + (cc.y + d.y));
     }
   }
 }
@@ -284,40 +284,37 @@ static constexpr int kFirstFwdStatBlocks = 148 * 4;
 using namespace b2;
 
 static int conv_first_fwd_impl(const float* x, const float* w, void* y, int ldy, int y_coff, int N, int D, int H,
-                               int W, int Cout, int relu, float* stat_partial, int* n_partials, cudaStream_t stream) {
+                               int W, int Cout, int relu, long long* stat_acc, cudaStream_t stream) {
   B2_REQUIRE(x && w && y, "b2_conv3d_first_fwd: null pointer");
   B2_REQUIRE(ldy % 8 == 0 && y_coff % 8 == 0, "b2_conv3d_first_fwd: ldy/y_coff must be multiples of 8");
   const long long V = (long long)N * D * H * W;
   long long blocks = (V + 127) / 128;
-  const long long cap = stat_partial ? (long long)kFirstFwdStatBlocks : (long long)num_sms() * 16;
+  const long long cap = stat_acc ? (long long)kFirstFwdStatBlocks : (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   __nv_bfloat16* yy = reinterpret_cast<__nv_bfloat16*>(y);
   switch (Cout) {
-    case 32: B2_LAUNCH(conv_first_fwd_kernel<32>, (unsigned)blocks, 128, 0, stream, x, w, yy, N, D, H, W, ldy, y_coff, relu, stat_partial); break;
-    case 64: B2_LAUNCH(conv_first_fwd_kernel<64>, (unsigned)blocks, 128, 0, stream, x, w, yy, N, D, H, W, ldy, y_coff, relu, stat_partial); break;
+    case 32: B2_LAUNCH(conv_first_fwd_kernel<32>, (unsigned)blocks, 128, 0, stream, x, w, yy, N, D, H, W, ldy, y_coff, relu, stat_acc); break;
+    case 64: B2_LAUNCH(conv_first_fwd_kernel<64>, (unsigned)blocks, 128, 0, stream, x, w, yy, N, D, H, W, ldy, y_coff, relu, stat_acc); break;
     default:
       set_error("b2_conv3d_first_fwd: Cout=%d unsupported (32 or 64)", Cout);
       return B2_ERR_UNSUPPORTED;
   }
   B2_CHECK_CUDA(cudaGetLastError());
-  if (n_partials) *n_partials = (int)blocks;
   return B2_OK;
 }
 
 extern "C" int b2_conv3d_first_fwd(const float* x, const float* w, void* y, int ldy, int y_coff, int N, int D, int H,
                                    int W, int Cout, int relu, cudaStream_t stream) {
-  return conv_first_fwd_impl(x, w, y, ldy, y_coff, N, D, H, W, Cout, relu, nullptr, nullptr, stream);
+  return conv_first_fwd_impl(x, w, y, ldy, y_coff, N, D, H, W, Cout, relu, nullptr, stream);
 }
 
-// Same, with the GroupNorm statistics of the stored output fused in (batch 1): stat_partial fp32
-// [b2_conv3d_first_stats_max_partials()][Cout][2]; *n_partials (HOST) receives the rows written.
-extern "C" int b2_conv3d_first_stats_max_partials(void) { return kFirstFwdStatBlocks; }
+// Same, with the GroupNorm statistics of the stored output fused in (batch 1): stat_acc int64 [Cout][4] exact
+// accumulators (zero before the launch), consumed by b2_relu_gn_apply_acc.
 extern "C" int b2_conv3d_first_fwd_stats(const float* x, const float* w, void* y, int ldy, int y_coff, int N, int D,
-                                         int H, int W, int Cout, int relu, float* stat_partial, int* n_partials,
-                                         cudaStream_t stream) {
-  B2_REQUIRE(stat_partial && n_partials, "b2_conv3d_first_fwd_stats: null pointer");
+                                         int H, int W, int Cout, int relu, long long* stat_acc, cudaStream_t stream) {
+  B2_REQUIRE(stat_acc, "b2_conv3d_first_fwd_stats: null pointer");
   B2_REQUIRE(N == 1, "b2_conv3d_first_fwd_stats: fused statistics need batch 1");
-  return conv_first_fwd_impl(x, w, y, ldy, y_coff, N, D, H, W, Cout, relu, stat_partial, n_partials, stream);
+  return conv_first_fwd_impl(x, w, y, ldy, y_coff, N, D, H, W, Cout, relu, stat_acc, stream);
 }
 
 extern "C" long long b2_conv3d_first_wgrad_workspace_bytes(int Cout) {

@@ -33,9 +33,8 @@ struct IgemmParams {
   int ldy, y_coff;
   __nv_bfloat16* y;
   float* y32;          // optional fp32 output (same indexing, ld = ldy) instead of bf16
-  float* stat_partial; // optional [gridDim.x][Cout][2]: per-CTA sum / sum-of-squares of the
-                       // bf16-rounded outputs per channel (GroupNorm statistics fused into the epilogue; N == 1,
-                       // one N tile only)
+  long long* stat_acc;  // optional [Cout][4] exact accumulators (common.h): per-channel sum / sum of squares of the
+                        // bf16-rounded outputs (GroupNorm statistics fused into the epilogue; N == 1, one N tile)
   const __nv_bfloat16* stat_r;  // when set, the statistics are (sum dy, sum dy*r) with r = this dense [V][Cout]
                                 // tensor: the two per-channel sums GroupNorm backward needs (dgrad launches)
   long long total_tiles;
@@ -208,7 +207,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t v[32];
         tmem_ld32(t_addr + c0, v);
         tmem_ld_wait();
-        if (p.stat_partial != nullptr) {   // warp-uniform branch
+        if (p.stat_acc != nullptr) {   // warp-uniform branch
           float xs[32], xq[32];
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
@@ -275,17 +274,17 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
-    if (p.stat_partial != nullptr) {
-      // combine the four epilogue warps through the (now idle) operand ring, one partial row per CTA
+    if (p.stat_acc != nullptr) {
+      // combine the four epilogue warps through the (now idle) operand ring, then one exact atomic add per CTA
       float2* sbuf = reinterpret_cast<float2*>(smem_a);   // [4][Cout]
 #pragma unroll
       for (int chunk = 0; chunk < 8; ++chunk)
         if (chunk * 32 < p.BN) sbuf[q * p.Cout + chunk * 32 + lane] = make_float2(st_s[chunk], st_q[chunk]);
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      float2* dst = reinterpret_cast<float2*>(p.stat_partial) + (size_t)blockIdx.x * p.Cout;
       for (int c = q * 32 + lane; c < p.Cout; c += 128) {
         const float2 a = sbuf[c], b = sbuf[p.Cout + c], cc = sbuf[2 * p.Cout + c], d = sbuf[3 * p.Cout + c];
-        dst[c] = make_float2((a.x + b.x) + (cc.x + d.x), (a.y + b.y) + (cc.y + d.y));
+        stat_atomic_add(p.stat_acc + 4 * c, (a.x + b.x) + (cc.x + d.x));
+        stat_atomic_add(p.stat_acc + 4 * c + 2, (a.y + b.y) + (cc.y + d.y));
       }
     }
   }
@@ -344,7 +343,7 @@ static void choose_box(int W, int H, int D, int& bw, int& bh, int& bd) {
 
 bool slab_applicable(int N, int D, int H, int W, int Cin, int Cout, int y_is_fp32);
 int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff, int N, int D,
-                int H, int W, int Cin, int Cout, int relu, float* stat_partial, const void* stat_r, int* n_partials,
+                int H, int W, int Cin, int Cout, int relu, long long* stat_acc, const void* stat_r,
                 cudaStream_t stream);
 
 int make_act_tmap(CUtensorMap* map, const void* base, int N, int D, int H, int W, int C, int ld, int coff,
@@ -365,7 +364,7 @@ using namespace b2;
 // See include/unetsulc_b200.h for the contract.
 static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff,
                              int y_is_fp32, int N, int D, int H, int W, int Cin, int Cout, int relu,
-                             float* stat_partial, const void* stat_r, int* n_partials, void* splitk_workspace,
+                             long long* stat_acc, const void* stat_r, void* splitk_workspace,
                              long long splitk_workspace_bytes, cudaStream_t stream) {
   B2_REQUIRE(x && wpack && y, "b2_conv3d_igemm: null pointer");
   B2_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "b2_conv3d_igemm: bad shape %dx%dx%dx%d", N, D, H, W);
@@ -378,8 +377,7 @@ static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpa
   // narrow-N layers at (almost) tile-aligned resolutions: shared-memory tap-reuse kernel (conv_slab.cu)
   static const bool no_slab = getenv("B2_NO_SLAB") != nullptr;
   if (!no_slab && slab_applicable(N, D, H, W, Cin, Cout, y_is_fp32))
-    return launch_slab(x, ldx, x_coff, wpack, y, ldy, y_coff, N, D, H, W, Cin, Cout, relu, stat_partial, stat_r,
-                       n_partials, stream);
+    return launch_slab(x, ldx, x_coff, wpack, y, ldy, y_coff, N, D, H, W, Cin, Cout, relu, stat_acc, stat_r, stream);
 
   IgemmParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
@@ -415,7 +413,7 @@ static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpa
   p.split_stride = 0;
   // split-K over taps when the layer has too few tiles to fill the machine (needs a caller-provided fp32 workspace)
   float* splitk_ws = nullptr;
-  if (!y_is_fp32 && !stat_partial && splitk_workspace && p.total_tiles * 2 <= num_sms()) {
+  if (!y_is_fp32 && !stat_acc && splitk_workspace && p.total_tiles * 2 <= num_sms()) {
     int sp = (int)(num_sms() / p.total_tiles);
     if (sp > 9) sp = 9;
     const long long need = (long long)sp * N * D * H * W * Cout * (long long)sizeof(float);
@@ -425,9 +423,9 @@ static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpa
       splitk_ws = reinterpret_cast<float*>(splitk_workspace);
     }
   }
-  p.stat_partial = stat_partial;
+  p.stat_acc = stat_acc;
   p.stat_r = reinterpret_cast<const __nv_bfloat16*>(stat_r);
-  if (stat_partial) {
+  if (stat_acc) {
     B2_REQUIRE(N == 1 && p.n_tiles_n == 1 && !y_is_fp32,
                "b2_conv3d_igemm_stats: fused statistics need batch 1, Cout <= 256 and a bf16 output");
   }
@@ -469,7 +467,6 @@ static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpa
                                                                 user_ldy, user_coff);
     B2_CHECK_CUDA(cudaGetLastError());
   }
-  if (n_partials) *n_partials = (int)grid;
   return B2_OK;
 }
 
@@ -478,7 +475,7 @@ extern "C" int b2_conv3d_igemm(const void* x, int ldx, int x_coff, const void* w
                                int y_is_fp32, int N, int D, int H, int W, int Cin, int Cout, int relu,
                                cudaStream_t stream) {
   return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, ldy, y_coff, y_is_fp32, N, D, H, W, Cin, Cout, relu, nullptr,
-                           nullptr, nullptr, nullptr, 0, stream);
+                           nullptr, nullptr, 0, stream);
 }
 
 // Same as b2_conv3d_igemm with an optional fp32 workspace: layers with fewer than num_SMs/2 output tiles are split
@@ -490,29 +487,27 @@ extern "C" int b2_conv3d_igemm_splitk(const void* x, int ldx, int x_coff, const 
                                       int y_coff, int N, int D, int H, int W, int Cin, int Cout, int relu,
                                       void* workspace, long long workspace_bytes, cudaStream_t stream) {
   return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, ldy, y_coff, 0, N, D, H, W, Cin, Cout, relu, nullptr, nullptr,
-                           nullptr, workspace, workspace_bytes, stream);
+                           workspace, workspace_bytes, stream);
 }
 
-extern "C" int b2_conv3d_stats_max_partials(void) { return num_sms(); }
-
 // fprop with the GroupNorm statistics of the stored (bf16-rounded, post-ReLU) output fused into the epilogue.
-// stat_partial: fp32 [b2_conv3d_stats_max_partials()][Cout][2]; *n_partials (HOST) receives the rows written.
+// stat_acc: int64 [Cout][4] exact accumulators (zero before the launch; see common.h), consumed by
+// b2_relu_gn_apply_acc.  Batch 1, Cout <= 256.
 extern "C" int b2_conv3d_igemm_stats(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy,
                                      int y_coff, int N, int D, int H, int W, int Cin, int Cout, int relu,
-                                     float* stat_partial, int* n_partials, cudaStream_t stream) {
-  B2_REQUIRE(stat_partial && n_partials, "b2_conv3d_igemm_stats: null pointer");
-  return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, ldy, y_coff, 0, N, D, H, W, Cin, Cout, relu, stat_partial,
-                           nullptr, n_partials, nullptr, 0, stream);
+                                     long long* stat_acc, cudaStream_t stream) {
+  B2_REQUIRE(stat_acc, "b2_conv3d_igemm_stats: null pointer");
+  return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, ldy, y_coff, 0, N, D, H, W, Cin, Cout, relu, stat_acc, nullptr,
+                           nullptr, 0, stream);
 }
 
 // dgrad (x = dY, wpack = dgrad pack, output dX written densely) with the GroupNorm-BACKWARD statistics of the layer
 // that produced dX's forward tensor fused into the epilogue: per channel sum(dX) and sum(dX * r), r = that layer's
-// stored relu(conv) (dense bf16 [V][Cout]).  Same partial layout / limits as b2_conv3d_igemm_stats.
+// stored relu(conv) (dense bf16 [V][Cout]).  Same accumulator layout; consumed by b2_relu_gn_bwd_apply_acc.
 extern "C" int b2_conv3d_igemm_bstats(const void* x, int ldx, int x_coff, const void* wpack, void* y, int N, int D,
-                                      int H, int W, int Cin, int Cout, const void* r, float* stat_partial,
-                                      int* n_partials, cudaStream_t stream) {
-  B2_REQUIRE(stat_partial && n_partials && r, "b2_conv3d_igemm_bstats: null pointer");
-  return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, Cout, 0, 0, N, D, H, W, Cin, Cout, 0, stat_partial, r,
-                           n_partials, nullptr, 0, stream);
+                                      int H, int W, int Cin, int Cout, const void* r, long long* stat_acc,
+                                      cudaStream_t stream) {
+  B2_REQUIRE(stat_acc && r, "b2_conv3d_igemm_bstats: null pointer");
+  return conv3d_igemm_impl(x, ldx, x_coff, wpack, y, Cout, 0, 0, N, D, H, W, Cin, Cout, 0, stat_acc, r, nullptr, 0,
+                           stream);
 }
-

@@ -34,7 +34,7 @@ struct SlabParams {
   int relu;
   int ldy, y_coff;
   __nv_bfloat16* y;
-  float* stat_partial;   // optional [gridDim.x][Cout][2] (see conv_igemm.cu)
+  long long* stat_acc;   // optional [Cout][4] exact statistics accumulators (see conv_igemm.cu, common.h)
   const __nv_bfloat16* stat_r;   // optional: backward statistics (sum dy, sum dy*r)
   long long total_tiles;
 };
@@ -227,7 +227,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           tmem_ld32(t_addr + c0, v);
           tmem_ld_wait();
           tmem_st32_zero(t_addr + c0);   // ready for the next tile's always-accumulating MMAs
-          if (p.stat_partial != nullptr) {
+          if (p.stat_acc != nullptr) {
             float xs[32], xq[32];
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
@@ -280,16 +280,16 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
-    if (p.stat_partial != nullptr) {
+    if (p.stat_acc != nullptr) {
       float2* sbuf = reinterpret_cast<float2*>(smem_p);   // [4][Cout] in the (now idle) plane ring
 #pragma unroll
       for (int chunk = 0; chunk < 2; ++chunk)
         if (chunk * 32 < BN) sbuf[q * BN + chunk * 32 + lane] = make_float2(st_s[chunk], st_q[chunk]);
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      float2* dst = reinterpret_cast<float2*>(p.stat_partial) + (size_t)blockIdx.x * BN;
       for (int c = q * 32 + lane; c < BN; c += 128) {
         const float2 a = sbuf[c], b = sbuf[BN + c], cc = sbuf[2 * BN + c], d = sbuf[3 * BN + c];
-        dst[c] = make_float2((a.x + b.x) + (cc.x + d.x), (a.y + b.y) + (cc.y + d.y));
+        stat_atomic_add(p.stat_acc + 4 * c, (a.x + b.x) + (cc.x + d.x));
+        stat_atomic_add(p.stat_acc + 4 * c + 2, (a.y + b.y) + (cc.y + d.y));
       }
     }
   }
@@ -313,7 +313,7 @@ bool slab_applicable(int N, int D, int H, int W, int Cin, int Cout, int y_is_fp3
 }
 
 int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff, int N, int D,
-                int H, int W, int Cin, int Cout, int relu, float* stat_partial, const void* stat_r, int* n_partials,
+                int H, int W, int Cin, int Cout, int relu, long long* stat_acc, const void* stat_r,
                 cudaStream_t stream) {
   SlabParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
@@ -326,9 +326,9 @@ int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, 
   p.ldy = ldy; p.y_coff = y_coff;
   p.y = reinterpret_cast<__nv_bfloat16*>(y);
   p.total_tiles = (long long)N * p.tiles_w * p.tiles_h * p.tiles_d;
-  p.stat_partial = stat_partial;
+  p.stat_acc = stat_acc;
   p.stat_r = reinterpret_cast<const __nv_bfloat16*>(stat_r);
-  if (stat_partial) B2_REQUIRE(N == 1, "b2_conv3d_igemm_stats: fused statistics need batch 1");
+  if (stat_acc) B2_REQUIRE(N == 1, "b2_conv3d_igemm_stats: fused statistics need batch 1");
   const int plane_bytes = kPlaneRows * KC * 2;
   const int b_bytes = 9 * Cout * KC * 2;
   const int budget = 227 * 1024 - 1024 - 512;
@@ -356,7 +356,6 @@ int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, 
     B2_LAUNCH(conv3d_slab_kernel<32>, (unsigned)grid, kSlabThreads, smem_bytes, stream, ta, tb, p);
   }
   B2_CHECK_CUDA(cudaGetLastError());
-  if (n_partials) *n_partials = (int)grid;
   return B2_OK;
 }
 

@@ -115,7 +115,7 @@ head_ce_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict_
                const float* __restrict__ W, const float* __restrict__ b, int Cout, const int* __restrict__ count,
                float grad_scale, const float* __restrict__ grad_scale_dev, int compute_grad, int eval_softmax,
                int* __restrict__ preds, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial,
-               long long per_block) {
+               long long per_block, const __nv_bfloat16* __restrict__ stat_r, long long* __restrict__ stat_acc) {
   pdl_prologue();
   constexpr int WS = CIN + 4;        // padded row strides (floats)
   constexpr int DS = kMaxCo + 1;
@@ -126,7 +126,11 @@ head_ce_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict_
   float* ds = bs + kMaxCo;                    // [kCeGroup][DS]  logits, then d(logits)
   float* xs = ds + kCeGroup * DS;             // [kCeGroup][WS]  x rows (fp32)
   float* lossv = xs + kCeGroup * WS;          // [kCeGroup]
-  int* s_u = reinterpret_cast<int*>(lossv + kCeGroup);   // [kCeChunk] voxel offsets relative to r_begin
+  // dX is the gradient at the last GroupNorm output: with stat_acc the kernel also accumulates that layer's
+  // GroupNorm-backward statistics (sum dX, sum dX*r) — dX is zero away from the labelled voxels, so these rows are all
+  float* dxs = lossv + kCeGroup;              // [kCeGroup][WS]  stored (bf16-rounded) dX rows
+  float* rs = dxs + kCeGroup * WS;            // [kCeGroup][WS]  r rows
+  int* s_u = reinterpret_cast<int*>(rs + kCeGroup * WS);   // [kCeChunk] voxel offsets relative to r_begin
   int* s_lab = s_u + kCeChunk;                           // [kCeChunk]
   int* s_cnt = s_lab + kCeChunk;                         // [kCeChunk / 32 + 1]
   for (int i = threadIdx.x; i < kMaxCo * WS; i += blockDim.x) {
@@ -149,6 +153,7 @@ head_ce_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict_
 #pragma unroll
   for (int i = 0; i < CPT; ++i) accW[i] = 0.f;
   float accb = 0.f, block_loss = 0.f;
+  float st_s = 0.f, st_q = 0.f;   // threads < CIN: running (sum dX, sum dX*r) of channel threadIdx.x
 
   const long long r_begin = (long long)blockIdx.x * per_block;
   const long long r_end = (r_begin + per_block < NV) ? r_begin + per_block : NV;
@@ -288,6 +293,15 @@ head_ce_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict_
             o.x = *reinterpret_cast<uint32_t*>(&lo);
             o.y = *reinterpret_cast<uint32_t*>(&hi);
             *reinterpret_cast<uint2*>(dx + vv * CIN + 16 * mm + 4 * q) = o;
+            if (stat_acc != nullptr) {
+              const uint2 rr = __ldg(reinterpret_cast<const uint2*>(stat_r + vv * CIN + 16 * mm + 4 * q));
+              float* dd = dxs + j * WS + 16 * mm + 4 * q;
+              float* rd = rs + j * WS + 16 * mm + 4 * q;
+              dd[0] = __uint_as_float(o.x << 16); dd[1] = __uint_as_float(o.x & 0xffff0000u);
+              dd[2] = __uint_as_float(o.y << 16); dd[3] = __uint_as_float(o.y & 0xffff0000u);
+              rd[0] = __uint_as_float(rr.x << 16); rd[1] = __uint_as_float(rr.x & 0xffff0000u);
+              rd[2] = __uint_as_float(rr.y << 16); rd[3] = __uint_as_float(rr.y & 0xffff0000u);
+            }
           }
         }
       }
@@ -307,6 +321,13 @@ head_ce_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict_
           }
           if ((threadIdx.x & 3) == 0) accb += dco;
         }
+        if (stat_acc != nullptr && dx != nullptr && threadIdx.x < CIN) {
+          for (int jv = 0; jv < nj; ++jv) {
+            const float g = dxs[jv * WS + threadIdx.x];
+            st_s += g;
+            st_q = fmaf(g, rs[jv * WS + threadIdx.x], st_q);
+          }
+        }
       }
       if (warp == 0) {
         float v = lossv[lane] + lossv[lane + 32];
@@ -321,6 +342,10 @@ head_ce_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict_
   for (int i = 0; i < CPT; ++i) dst[(wcb + i) * kMaxCo + wco] = accW[i];
   if ((threadIdx.x & 3) == 0) dst[kMaxCo * CIN + wco] = accb;
   if (threadIdx.x == 0) dst[kMaxCo * CIN + kMaxCo] = block_loss;
+  if (stat_acc != nullptr && compute_grad && dx != nullptr && threadIdx.x < CIN) {
+    stat_atomic_add(stat_acc + 4 * threadIdx.x, st_s);
+    stat_atomic_add(stat_acc + 4 * threadIdx.x + 2, st_q);
+  }
 }
 
 // Sums the per-block partials in a fixed order: block = 32 consecutive outputs x 8 row groups (row r goes to group
@@ -570,10 +595,10 @@ extern "C" long long b2_head_workspace_bytes(int Cin) {
 
 // Fused final_conv + CrossEntropyLoss(ignore_index=-1) + argmax (+ backward when compute_grad).
 // loss_out[0] = mean loss over labelled voxels (NaN if none), loss_out[1] = sum; count_out = #labelled.
-extern "C" int b2_head_ce(const void* x, const long long* labels, long long NV, const float* W, const float* b, int Cin,
-                          int Cout, float grad_scale, const float* grad_scale_dev, int compute_grad, int eval_softmax,
-                          int* preds, void* dx, float* dW, float* db, float* loss_out, int* count_out,
-                          void* workspace, long long workspace_bytes, cudaStream_t stream) {
+static int head_ce_impl(const void* x, const long long* labels, long long NV, const float* W, const float* b, int Cin,
+                        int Cout, float grad_scale, const float* grad_scale_dev, int compute_grad, int eval_softmax,
+                        int* preds, void* dx, float* dW, float* db, float* loss_out, int* count_out, void* workspace,
+                        long long workspace_bytes, const void* stat_r, long long* stat_acc, cudaStream_t stream) {
   B2_REQUIRE(x && labels && W && loss_out && count_out && workspace, "b2_head_ce: null pointer");
   B2_HEAD_CHECK("b2_head_ce");
   B2_REQUIRE(workspace_bytes >= b2_head_workspace_bytes(Cin), "b2_head_ce: workspace too small");
@@ -585,8 +610,8 @@ extern "C" int b2_head_ce(const void* x, const long long* labels, long long NV, 
   B2_LAUNCH(count_labelled_kernel, cblocks, 256, 0, stream, labels, NV, count_out);
   B2_CHECK_CUDA(cudaGetLastError());
   B2_REQUIRE(NV < (1LL << 31), "b2_head_ce: %lld voxels unsupported", NV);
-  const size_t sh = (size_t)(kMaxCo * (Cin + 4) + kMaxCo + kCeGroup * (kMaxCo + 1) + kCeGroup * (Cin + 4) + kCeGroup) *
-                        sizeof(float) +
+  const size_t sh = (size_t)(kMaxCo * (Cin + 4) + kMaxCo + kCeGroup * (kMaxCo + 1) + 3 * kCeGroup * (Cin + 4) +
+                             kCeGroup) * sizeof(float) +
                     (size_t)(2 * kCeChunk + kCeChunk / 32 + 1) * sizeof(int);
   long long per_block = (NV + kCeBlocks - 1) / kCeBlocks;
   per_block = (per_block + kCeThreads - 1) / kCeThreads * kCeThreads;
@@ -596,12 +621,14 @@ extern "C" int b2_head_ce(const void* x, const long long* labels, long long NV, 
     B2_CHECK_CUDA(cudaFuncSetAttribute(head_ce_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     B2_LAUNCH(head_ce_kernel<64>, kCeBlocks, kCeThreads, sh, stream, xb, labels, NV, W, b, Cout, count_out, grad_scale,
                                                               grad_scale_dev, compute_grad, eval_softmax, preds, dxb,
-                                                              partial, per_block);
+                                                              partial, per_block,
+                                                              reinterpret_cast<const __nv_bfloat16*>(stat_r), stat_acc);
   } else {
     B2_CHECK_CUDA(cudaFuncSetAttribute(head_ce_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     B2_LAUNCH(head_ce_kernel<32>, kCeBlocks, kCeThreads, sh, stream, xb, labels, NV, W, b, Cout, count_out, grad_scale,
                                                               grad_scale_dev, compute_grad, eval_softmax, preds, dxb,
-                                                              partial, per_block);
+                                                              partial, per_block,
+                                                              reinterpret_cast<const __nv_bfloat16*>(stat_r), stat_acc);
   }
   B2_CHECK_CUDA(cudaGetLastError());
   const int stride = kMaxCo * Cin + kMaxCo + 1;
@@ -610,6 +637,26 @@ extern "C" int b2_head_ce(const void* x, const long long* labels, long long NV, 
                                                                    compute_grad ? db : nullptr, loss_out);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
+}
+
+extern "C" int b2_head_ce(const void* x, const long long* labels, long long NV, const float* W, const float* b, int Cin,
+                          int Cout, float grad_scale, const float* grad_scale_dev, int compute_grad, int eval_softmax,
+                          int* preds, void* dx, float* dW, float* db, float* loss_out, int* count_out,
+                          void* workspace, long long workspace_bytes, cudaStream_t stream) {
+  return head_ce_impl(x, labels, NV, W, b, Cin, Cout, grad_scale, grad_scale_dev, compute_grad, eval_softmax, preds, dx,
+                      dW, db, loss_out, count_out, workspace, workspace_bytes, nullptr, nullptr, stream);
+}
+
+// Same with compute_grad and dx: dX is the gradient at the last GroupNorm output, so the kernel also accumulates that
+// layer's GroupNorm-backward statistics (sum dX, sum dX*r; r = its saved relu(conv), dense bf16 [NV][Cin]) into
+// stat_acc int64 [Cin][4] (see the statistics accumulators above b2_conv3d_igemm_stats in the header).
+extern "C" int b2_head_ce_bstats(const void* x, const long long* labels, long long NV, const float* W, const float* b,
+                                 int Cin, int Cout, float grad_scale, const float* grad_scale_dev, int* preds,
+                                 void* dx, float* dW, float* db, float* loss_out, int* count_out, void* workspace,
+                                 long long workspace_bytes, const void* r, long long* stat_acc, cudaStream_t stream) {
+  B2_REQUIRE(dx && r && stat_acc, "b2_head_ce_bstats: null pointer");
+  return head_ce_impl(x, labels, NV, W, b, Cin, Cout, grad_scale, grad_scale_dev, 1, 0, preds, dx, dW, db, loss_out,
+                      count_out, workspace, workspace_bytes, r, stat_acc, stream);
 }
 
 extern "C" int b2_head_gather(const void* x, const long long* index, long long nidx, const float* W, const float* b,

@@ -142,33 +142,94 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ r, long long V, int C, float* 
   if (threadIdx.x == 0) counters[n] = 0;   // self-resetting ticket
 }
 
-// statistics already reduced per (CTA, warp) by the conv epilogue: one block turns them into mean/rstd, scale/shift
-__global__ void __launch_bounds__(1024)
-gn_finalize_partials_kernel(const float* __restrict__ partial, int nblk, int C, int G, long long V, float eps,
-                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                            float* __restrict__ mean_rstd, float* __restrict__ scale_shift) {
+// ---- statistics from the exact accumulators (common.h) --------------------------------------------------------------
+// The producers leave per-channel EXACT sums in int64 [C][4]; one small block turns them into what the apply kernels
+// read.  Reading C accumulators instead of ~148 x C fp32 partials makes this a ~3 us kernel (one L2 round trip, fp64
+// only for the C conversions and the G group sums; no fp64 division or square root: 1/m comes from the host and rstd
+// is rsqrtf + one Newton step on the well-conditioned variance).
+// (Tried and measured slower, round 1: finalising in the prologue of EVERY block of the apply kernels — the dependent
+// L2 round trips under a saturated memory system cost +13..35 us per launch.)
+static constexpr int kMaxAccC = 512;
+
+__device__ __forceinline__ float rstd_from_var(double var_eps) {
+  const float v = (float)var_eps;
+  float r = rsqrtf(v);
+  return r * (1.5f - 0.5f * v * r * r);
+}
+
+__global__ void __launch_bounds__(kMaxAccC)
+gn_finalize_acc_kernel(const long long* __restrict__ acc, int C, int G, double inv_m, float eps,
+                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                       float* __restrict__ mean_rstd, float* __restrict__ scale_shift) {
   pdl_prologue();
-  extern __shared__ float sh[];
-  double* csum = reinterpret_cast<double*>(sh);
-  reduce_partials(partial, 0, nblk, C, csum);
-  __syncthreads();
+  __shared__ double s_c[kMaxAccC][2];
+  __shared__ float s_g[kMaxAccC][2];
+  const int c = threadIdx.x;
   const int cpg = C / G;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    double a = 0.0, b = 0.0;
-    for (int k = 0; k < cpg; ++k) { a += csum[2 * (g * cpg + k)]; b += csum[2 * (g * cpg + k) + 1]; }
-    const double m = (double)V * cpg;
-    const double mean = a / m;
-    double var = b / m - mean * mean;
+  float gm = 0.f, bt = 0.f;
+  if (c < C) {
+    gm = gamma[c];
+    bt = beta[c];
+    s_c[c][0] = stat_read(acc + 4 * c);
+    s_c[c][1] = stat_read(acc + 4 * c + 2);
+  }
+  __syncthreads();
+  if (c < G) {
+    double S = 0.0, Q = 0.0;
+    for (int k = 0; k < cpg; ++k) { S += s_c[c * cpg + k][0]; Q += s_c[c * cpg + k][1]; }
+    const double mean = S * inv_m;
+    double var = Q * inv_m - mean * mean;
     if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    for (int k = 0; k < cpg; ++k) {
-      const int c = g * cpg + k;
-      const float sc = rstd * gamma[c];
-      mean_rstd[c * 2 + 0] = (float)mean;
-      mean_rstd[c * 2 + 1] = rstd;
-      scale_shift[c * 2 + 0] = sc;
-      scale_shift[c * 2 + 1] = beta[c] - (float)mean * sc;
-    }
+    s_g[c][0] = (float)mean;
+    s_g[c][1] = rstd_from_var(var + (double)eps);
+  }
+  __syncthreads();
+  if (c < C) {
+    const float mean = s_g[c / cpg][0], rstd = s_g[c / cpg][1];
+    const float sc = rstd * gm;
+    mean_rstd[2 * c] = mean;
+    mean_rstd[2 * c + 1] = rstd;
+    scale_shift[2 * c] = sc;
+    scale_shift[2 * c + 1] = bt - mean * sc;
+  }
+}
+
+// backward: (sum dy, sum dy*r) per channel -> coef[c] = {a, b, c0, 0} (dr = a*dy + b*xhat + c0), dgamma, dbeta
+__global__ void __launch_bounds__(kMaxAccC)
+gn_bwd_finalize_acc_kernel(const long long* __restrict__ acc, int C, int G, double inv_m,
+                           const float* __restrict__ gamma, const float* __restrict__ mean_rstd,
+                           float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_prologue();
+  __shared__ double s_c[kMaxAccC][2];
+  __shared__ float s_g[kMaxAccC][2];
+  const int c = threadIdx.x;
+  const int cpg = C / G;
+  float gm = 0.f, rstd = 0.f;
+  if (c < C) {
+    gm = gamma[c];
+    const float mu = mean_rstd[2 * c];
+    rstd = mean_rstd[2 * c + 1];
+    const double sdy = stat_read(acc + 4 * c), sdyr = stat_read(acc + 4 * c + 2);
+    const double sdyx = (double)rstd * (sdyr - (double)mu * sdy);   // sum dy*xhat
+    s_c[c][0] = (double)gm * sdy;
+    s_c[c][1] = (double)gm * sdyx;
+    if (dgamma) dgamma[c] = (float)sdyx;
+    if (dbeta) dbeta[c] = (float)sdy;
+  }
+  __syncthreads();
+  if (c < G) {
+    double S1 = 0.0, S2 = 0.0;
+    for (int k = 0; k < cpg; ++k) { S1 += s_c[c * cpg + k][0]; S2 += s_c[c * cpg + k][1]; }
+    s_g[c][0] = (float)(S2 * inv_m);
+    s_g[c][1] = (float)(S1 * inv_m);
+  }
+  __syncthreads();
+  if (c < C) {
+    float* o = coef + (size_t)c * 4;
+    o[0] = rstd * gm;
+    o[1] = -rstd * s_g[c / cpg][0];
+    o[2] = -rstd * s_g[c / cpg][1];
+    o[3] = 0.f;
   }
 }
 
@@ -423,47 +484,6 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
   }
 }
 
-// backward statistics already reduced per CTA by the dgrad epilogue as (sum dy, sum dy*r): one block turns them into
-// the per-channel coefficients, d gamma and d beta (batch 1)
-__global__ void __launch_bounds__(1024)
-gn_bwd_finalize_partials_kernel(const float* __restrict__ partial, int nblk, int C, int G, long long V,
-                                const float* __restrict__ gamma, const float* __restrict__ mean_rstd,
-                                float* __restrict__ coef, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  pdl_prologue();
-  extern __shared__ float sh[];
-  double* csum = reinterpret_cast<double*>(sh);
-  reduce_partials(partial, 0, nblk, C, csum);
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {   // (sum dy, sum dy*r) -> (sum dy, sum dy*xhat)
-    const double mu = (double)mean_rstd[c * 2], rs = (double)mean_rstd[c * 2 + 1];
-    const double sdy = csum[2 * c], sdyr = csum[2 * c + 1];
-    const double sdyx = rs * (sdyr - mu * sdy);
-    csum[2 * c + 1] = sdyx;
-    if (dgamma) dgamma[c] = (float)sdyx;
-    if (dbeta) dbeta[c] = (float)sdy;
-  }
-  __syncthreads();
-  const int cpg = C / G;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    double S1 = 0.0, S2 = 0.0;
-    for (int k = 0; k < cpg; ++k) {
-      const double gm = (double)gamma[g * cpg + k];
-      S1 += gm * csum[2 * (g * cpg + k)];
-      S2 += gm * csum[2 * (g * cpg + k) + 1];
-    }
-    const double m = (double)V * cpg;
-    for (int k = 0; k < cpg; ++k) {
-      const int c = g * cpg + k;
-      const double rstd = (double)mean_rstd[c * 2 + 1];
-      float* o = coef + (size_t)c * 4;
-      o[0] = (float)(rstd * (double)gamma[c]);
-      o[1] = (float)(-rstd * S2 / m);
-      o[2] = (float)(-rstd * S1 / m);
-      o[3] = 0.f;
-    }
-  }
-}
-
 static inline int stat_blocks(long long V, int C) {
   // >= 16 KB of the tensor per block (round 1: 256 KB per block left the 12x14x12 and 24x28x24 levels with 3..31
   // blocks and 35 us of pure latency per launch), and at most ~16 k partial pairs for the finalising block to sum
@@ -521,16 +541,17 @@ extern "C" int b2_relu_gn_stats(const void* r, int N, long long V, int C, int G,
   return B2_OK;
 }
 
-// GroupNorm statistics from the per-(CTA, warp) partial sums written by b2_conv3d_igemm_stats (batch 1).
-extern "C" int b2_relu_gn_finalize(const float* stat_partial, int n_partials, long long V, int C, int G, float eps,
-                                   const float* gamma, const float* beta, float* mean_rstd, float* scale_shift,
-                                   cudaStream_t stream) {
-  B2_REQUIRE(stat_partial && gamma && beta && mean_rstd && scale_shift && n_partials > 0,
-             "b2_relu_gn_finalize: null pointer");
-  int rc = check_gn_shape("b2_relu_gn_finalize", 1, V, C, G);
+// GroupNorm statistics (batch 1) from the exact accumulators a producer kernel filled (b2_conv3d_igemm_stats,
+// b2_conv3d_first_fwd_stats): stat_acc int64 [C][4] -> mean_rstd fp32 [C][2], scale_shift fp32 [C][2].
+extern "C" int b2_relu_gn_finalize_acc(const long long* stat_acc, long long V, int C, int G, float eps,
+                                       const float* gamma, const float* beta, float* mean_rstd, float* scale_shift,
+                                       cudaStream_t stream) {
+  B2_REQUIRE(stat_acc && gamma && beta && mean_rstd && scale_shift, "b2_relu_gn_finalize_acc: null pointer");
+  int rc = check_gn_shape("b2_relu_gn_finalize_acc", 1, V, C, G);
   if (rc) return rc;
-  B2_LAUNCH(gn_finalize_partials_kernel, 1, 1024, (size_t)C * 2 * sizeof(double), stream, 
-      stat_partial, n_partials, C, G, V, eps, gamma, beta, mean_rstd, scale_shift);
+  B2_REQUIRE(C <= kMaxAccC, "b2_relu_gn_finalize_acc: C=%d > %d", C, kMaxAccC);
+  B2_LAUNCH(gn_finalize_acc_kernel, 1, (C + 31) / 32 * 32, 0, stream, stat_acc, C, G, 1.0 / ((double)V * (C / G)), eps,
+            gamma, beta, mean_rstd, scale_shift);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }
@@ -543,13 +564,14 @@ extern "C" int b2_relu_gn_apply(const void* r, int N, int D, int H, int W, int C
   const long long V = (long long)D * H * W;
   if (pooled) {
     const long long total = (long long)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-    B2_LAUNCH(gn_apply_pool_kernel, ew_blocks(total), 256, 0, stream, 
-        reinterpret_cast<const __nv_bfloat16*>(r), N, D, H, W, C, scale_shift, reinterpret_cast<__nv_bfloat16*>(y), ldy,
-        y_coff, reinterpret_cast<__nv_bfloat16*>(pooled));
+    B2_LAUNCH(gn_apply_pool_kernel, ew_blocks(total), 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(r), N, D,
+              H, W, C, scale_shift, reinterpret_cast<__nv_bfloat16*>(y), ldy, y_coff,
+              reinterpret_cast<__nv_bfloat16*>(pooled));
   } else {
     B2_REQUIRE(256 % (C / 8) == 0, "b2_relu_gn_apply: C=%d unsupported", C);
-    B2_LAUNCH(gn_apply_kernel, dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream, 
-        reinterpret_cast<const __nv_bfloat16*>(r), V, C, scale_shift, reinterpret_cast<__nv_bfloat16*>(y), ldy, y_coff);
+    B2_LAUNCH(gn_apply_kernel, dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream,
+              reinterpret_cast<const __nv_bfloat16*>(r), V, C, scale_shift, reinterpret_cast<__nv_bfloat16*>(y), ldy,
+              y_coff);
   }
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
@@ -586,25 +608,26 @@ extern "C" long long b2_relu_gn_bwd_workspace_bytes(int N, int C) {
   return b2_gn_workspace_bytes(N, C) + (long long)N * C * 6 * (long long)sizeof(float);
 }
 
-// GroupNorm backward when the statistics come from b2_conv3d_igemm_bstats (batch 1): finalize + apply, no statistics
-// pass over dy and r.  workspace: >= C*4 floats.
-extern "C" int b2_relu_gn_bwd_from_partials(const float* stat_partial, int n_partials, const void* dy, int lddy,
-                                            int dy_coff, const void* r, long long V, int C, int G, const float* gamma,
-                                            const float* mean_rstd, void* dr, float* dgamma, float* dbeta,
-                                            void* workspace, long long workspace_bytes, cudaStream_t stream) {
-  B2_REQUIRE(stat_partial && dy && r && gamma && mean_rstd && dr && workspace && n_partials > 0,
-             "b2_relu_gn_bwd_from_partials: null pointer");
-  int rc = check_gn_shape("b2_relu_gn_bwd_from_partials", 1, V, C, G);
+// GroupNorm backward (batch 1) when (sum dy, sum dy*r) arrive in the exact accumulators a producer kernel filled
+// (b2_conv3d_igemm_bstats, b2_maxpool3d_bwd_add_bstats, b2_upcat_bwd_separable_bstats, b2_head_ce_bstats): a one-block
+// finalize (coefficients, dgamma, dbeta) + the apply pass; no statistics pass over (dy, r).  workspace >= C*16 bytes.
+extern "C" int b2_relu_gn_bwd_acc(const long long* stat_acc, const void* dy, int lddy, int dy_coff, const void* r,
+                                  long long V, int C, int G, const float* gamma, const float* mean_rstd, void* dr,
+                                  float* dgamma, float* dbeta, void* workspace, long long workspace_bytes,
+                                  cudaStream_t stream) {
+  B2_REQUIRE(stat_acc && dy && r && gamma && mean_rstd && dr && workspace, "b2_relu_gn_bwd_acc: null pointer");
+  int rc = check_gn_shape("b2_relu_gn_bwd_acc", 1, V, C, G);
   if (rc) return rc;
-  B2_REQUIRE(workspace_bytes >= (long long)C * 4 * (long long)sizeof(float),
-             "b2_relu_gn_bwd_from_partials: workspace too small");
+  B2_REQUIRE(C <= kMaxAccC, "b2_relu_gn_bwd_acc: C=%d > %d", C, kMaxAccC);
+  B2_REQUIRE(lddy % 8 == 0 && dy_coff % 8 == 0, "b2_relu_gn_bwd_acc: lddy/dy_coff must be multiples of 8");
+  B2_REQUIRE(workspace_bytes >= (long long)C * 4 * (long long)sizeof(float), "b2_relu_gn_bwd_acc: workspace too small");
   float* coef = reinterpret_cast<float*>(workspace);
-  B2_LAUNCH(gn_bwd_finalize_partials_kernel, 1, 1024, (size_t)C * 2 * sizeof(double), stream, 
-      stat_partial, n_partials, C, G, V, gamma, mean_rstd, coef, dgamma, dbeta);
+  B2_LAUNCH(gn_bwd_finalize_acc_kernel, 1, (C + 31) / 32 * 32, 0, stream, stat_acc, C, G,
+            1.0 / ((double)V * (C / G)), gamma, mean_rstd, coef, dgamma, dbeta);
   B2_CHECK_CUDA(cudaGetLastError());
-  B2_LAUNCH(gn_bwd_apply_kernel, dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream, 
-      reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
-      mean_rstd, coef, reinterpret_cast<__nv_bfloat16*>(dr));
+  B2_LAUNCH(gn_bwd_apply_kernel, dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream,
+            reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
+            mean_rstd, static_cast<const float*>(coef), reinterpret_cast<__nv_bfloat16*>(dr));
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }

@@ -14,14 +14,46 @@ static inline int ew_blocks(long long total) {
   return (int)nb;
 }
 
+// GroupNorm-backward statistics of a tensor this file PRODUCES (it is the gradient at a GroupNorm output): per channel
+// sum(g) and sum(g * r) over the stored (bf16-rounded) values, r = the layer's saved relu(conv).  A thread keeps the
+// sums of its fixed channel octet in registers; the block combines them in a fixed order and adds ONE exact,
+// order-independent contribution per channel to the [C][4] accumulators (common.h) — the separate statistics pass
+// over (dy, r) disappears.  Requires blockDim.x == 256 and 256 % (C/8) == 0.
+__device__ __forceinline__ void block_bstats_commit(const float (&s)[8], const float (&q)[8], int C, int oct, int vloc,
+                                                    long long* __restrict__ acc) {
+  __shared__ float red[256 * 16];   // [256 / C8][C][2]
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red[((size_t)vloc * C + oct * 8 + k) * 2 + 0] = s[k];
+    red[((size_t)vloc * C + oct * 8 + k) * 2 + 1] = q[k];
+  }
+  __syncthreads();
+  const int rows = 256 / (C >> 3);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float a = 0.f, b = 0.f;
+    for (int j = 0; j < rows; ++j) { a += red[((size_t)j * C + c) * 2]; b += red[((size_t)j * C + c) * 2 + 1]; }
+    stat_atomic_add(acc + 4 * c, a);
+    stat_atomic_add(acc + 4 * c + 2, b);
+  }
+}
+__device__ __forceinline__ void bstats_accumulate(float (&s)[8], float (&q)[8], const uint4& stored, const uint4& rr) {
+  const f8 g = unpack8(stored), x = unpack8(rr);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s[k] += g.v[k]; q[k] = fmaf(g.v[k], x.v[k], q[k]); }
+}
+
 // out[v, c] = dskip[v, c] + (v is the arg-max of its 2x2x2 cell ? dpool[cell, c] : 0)
 // arg-max is recomputed from the stored forward tensor y; first maximum in (d, h, w) scan order wins, as in
 // PyTorch's max_pool3d_with_indices.
 __global__ void __launch_bounds__(256)
 pool_bwd_add_kernel(const __nv_bfloat16* __restrict__ y, int ldy, int y_coff, const __nv_bfloat16* __restrict__ dskip,
                     int ldd, int d_coff, const __nv_bfloat16* __restrict__ dpool, __nv_bfloat16* __restrict__ out,
-                    int N, int D, int H, int W, int C) {
+                    int N, int D, int H, int W, int C, const __nv_bfloat16* __restrict__ stat_r,
+                    long long* __restrict__ stat_acc) {
   pdl_prologue();
+  float st_s[8], st_q[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { st_s[k] = 0.f; st_q[k] = 0.f; }
   const int C8 = C >> 3;
   const int Dc = (D + 1) >> 1, Hc = (H + 1) >> 1, Wc = (W + 1) >> 1;
   const int Dp = D >> 1, Hp = H >> 1, Wp = W >> 1;
@@ -70,10 +102,14 @@ pool_bwd_add_kernel(const __nv_bfloat16* __restrict__ y, int ldy, int y_coff, co
           for (int k = 0; k < 8; ++k)
             if (arg[k] == j) g.v[k] += gp.v[k];
         }
-        stg16(out + v * C + oct * 8, pack8(g));
+        const uint4 pk = pack8(g);
+        stg16(out + v * C + oct * 8, pk);
+        if (stat_acc != nullptr) bstats_accumulate(st_s, st_q, pk, ldg16(stat_r + v * C + oct * 8));
       }
     }
   }
+  if (stat_acc != nullptr)   // grid stride is a multiple of C8: the octet of a thread never changes
+    block_bstats_commit(st_s, st_q, C, (int)(threadIdx.x % C8), (int)(threadIdx.x / C8), stat_acc);
 }
 
 // PyTorch upsample_trilinear3d, align_corners=False: src = scale*(dst+0.5)-0.5 clamped at 0, scale = in/out (fp32)
@@ -341,8 +377,12 @@ upsample_bwd_w_kernel(const __nv_bfloat16* __restrict__ dcat, int ldc, int coff,
 // pass 2 (H, D): dx[n, d, h, w, c] = sum_{od, oh} wd * wh * t[n, od, oh, w, c]; one block per coarse row (n, d, h)
 __global__ void __launch_bounds__(256)
 upsample_bwd_hd_kernel(const __nv_bfloat16* __restrict__ t, int Do, int Ho, __nv_bfloat16* __restrict__ dx, int Di,
-                       int Hi, int Wi, int C) {
+                       int Hi, int Wi, int C, const __nv_bfloat16* __restrict__ stat_r,
+                       long long* __restrict__ stat_acc) {
   pdl_prologue();
+  float st_s[8], st_q[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { st_s[k] = 0.f; st_q[k] = 0.f; }
   const int row = blockIdx.x;
   const int h = row % Hi, d = (row / Hi) % Di, n = row / (Hi * Di);
   const float sd = (float)Di / (float)Do, shh = (float)Hi / (float)Ho;
@@ -367,7 +407,13 @@ upsample_bwd_hd_kernel(const __nv_bfloat16* __restrict__ t, int Do, int Ho, __nv
     f8 o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.v[k] = acc[k];
-    stg16(out + e, pack8(o));
+    const uint4 pk = pack8(o);
+    stg16(out + e, pk);
+    if (stat_acc != nullptr) bstats_accumulate(st_s, st_q, pk, ldg16(stat_r + (size_t)row * rowlen + e));
+  }
+  if (stat_acc != nullptr) {   // 2048 % C == 0: a thread's channel octet is the same for every element it visits
+    const int C8 = C >> 3;
+    block_bstats_commit(st_s, st_q, C, (int)(threadIdx.x % C8), (int)(threadIdx.x / C8), stat_acc);
   }
 }
 
@@ -375,18 +421,40 @@ upsample_bwd_hd_kernel(const __nv_bfloat16* __restrict__ t, int Do, int Ho, __nv
 
 using namespace b2;
 
-extern "C" int b2_maxpool3d_bwd_add(const void* y, int ldy, int y_coff, const void* dskip, int ldd, int d_coff,
-                                    const void* dpool, void* out, int N, int D, int H, int W, int C,
-                                    cudaStream_t stream) {
+static int maxpool3d_bwd_add_impl(const void* y, int ldy, int y_coff, const void* dskip, int ldd, int d_coff,
+                                  const void* dpool, void* out, int N, int D, int H, int W, int C, const void* stat_r,
+                                  long long* stat_acc, cudaStream_t stream) {
   B2_REQUIRE(y && dpool && out, "b2_maxpool3d_bwd_add: null pointer");
   B2_REQUIRE(C % 8 == 0 && ldy % 8 == 0 && y_coff % 8 == 0 && ldd % 8 == 0 && d_coff % 8 == 0,
              "b2_maxpool3d_bwd_add: channel counts must be multiples of 8");
   const long long total = (long long)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  B2_LAUNCH(pool_bwd_add_kernel, ew_blocks(total), 256, 0, stream, 
-      reinterpret_cast<const __nv_bfloat16*>(y), ldy, y_coff, reinterpret_cast<const __nv_bfloat16*>(dskip), ldd, d_coff,
-      reinterpret_cast<const __nv_bfloat16*>(dpool), reinterpret_cast<__nv_bfloat16*>(out), N, D, H, W, C);
+  int blocks = ew_blocks(total);
+  if (stat_acc) {
+    B2_REQUIRE(N == 1 && 256 % (C / 8) == 0, "b2_maxpool3d_bwd_add_bstats: needs batch 1 and C/8 dividing 256 (C=%d)", C);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;   // one resident wave: fewer atomic contributions
+  }
+  B2_LAUNCH(pool_bwd_add_kernel, blocks, 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(y), ldy, y_coff,
+            reinterpret_cast<const __nv_bfloat16*>(dskip), ldd, d_coff, reinterpret_cast<const __nv_bfloat16*>(dpool),
+            reinterpret_cast<__nv_bfloat16*>(out), N, D, H, W, C, reinterpret_cast<const __nv_bfloat16*>(stat_r),
+            stat_acc);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
+}
+
+extern "C" int b2_maxpool3d_bwd_add(const void* y, int ldy, int y_coff, const void* dskip, int ldd, int d_coff,
+                                    const void* dpool, void* out, int N, int D, int H, int W, int C,
+                                    cudaStream_t stream) {
+  return maxpool3d_bwd_add_impl(y, ldy, y_coff, dskip, ldd, d_coff, dpool, out, N, D, H, W, C, nullptr, nullptr,
+                                stream);
+}
+
+// Same (batch 1); `out` is the gradient at a GroupNorm output: also accumulates that layer's GroupNorm-backward
+// statistics (sum out, sum out*r; r = the layer's saved relu(conv), dense bf16 [V][C]) into stat_acc int64 [C][4].
+extern "C" int b2_maxpool3d_bwd_add_bstats(const void* y, int ldy, int y_coff, const void* dskip, int ldd, int d_coff,
+                                           const void* dpool, void* out, int N, int D, int H, int W, int C,
+                                           const void* r, long long* stat_acc, cudaStream_t stream) {
+  B2_REQUIRE(r && stat_acc, "b2_maxpool3d_bwd_add_bstats: null pointer");
+  return maxpool3d_bwd_add_impl(y, ldy, y_coff, dskip, ldd, d_coff, dpool, out, N, D, H, W, C, r, stat_acc, stream);
 }
 
 extern "C" int b2_upcat_fwd(const void* x, int N, int Di, int Hi, int Wi, int C, void* cat, int ldc, int coff, int Do,
@@ -414,23 +482,44 @@ extern "C" long long b2_upcat_bwd_workspace_bytes(int N, int Do, int Ho, int Wi,
 }
 
 // separable variant: W pass into `workspace` (bf16 [N][Do][Ho][Wi][C]), then the H/D pass
-extern "C" int b2_upcat_bwd_separable(const void* dcat, int ldc, int coff, int N, int Do, int Ho, int Wo, void* dx,
-                                      int Di, int Hi, int Wi, int C, void* workspace, long long workspace_bytes,
-                                      cudaStream_t stream) {
+static int upcat_bwd_separable_impl(const void* dcat, int ldc, int coff, int N, int Do, int Ho, int Wo, void* dx,
+                                    int Di, int Hi, int Wi, int C, void* workspace, long long workspace_bytes,
+                                    const void* stat_r, long long* stat_acc, cudaStream_t stream) {
   B2_REQUIRE(dcat && dx && workspace, "b2_upcat_bwd_separable: null pointer");
   B2_REQUIRE(C % 8 == 0 && ldc % 8 == 0 && coff % 8 == 0, "b2_upcat_bwd_separable: channel counts must be multiples of 8");
   B2_REQUIRE(Wo <= kMaxUpW && Wi <= kMaxUpW, "b2_upcat_bwd_separable: row width %d > %d", Wo, kMaxUpW);
   B2_REQUIRE(2 * Do <= 7 * Di && 2 * Ho <= 7 * Hi && 2 * Wo <= 7 * Wi, "b2_upcat_bwd_separable: ratio > 3.5 unsupported");
   B2_REQUIRE((long long)Wo * ldc < (1LL << 31) && (long long)Wi * C < (1LL << 31), "b2_upcat_bwd_separable: row too large");
   B2_REQUIRE(workspace_bytes >= b2_upcat_bwd_workspace_bytes(N, Do, Ho, Wi, C), "b2_upcat_bwd_separable: workspace too small");
+  if (stat_acc)
+    B2_REQUIRE(N == 1 && 2048 % C == 0 && C >= 8, "b2_upcat_bwd_separable_bstats: needs batch 1 and C dividing 2048 (C=%d)", C);
   __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(workspace);
-  B2_LAUNCH(upsample_bwd_w_kernel, (unsigned)(N * Do * Ho), 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(dcat), ldc,
-                                                                      coff, Wo, t, Wi, C);
+  B2_LAUNCH(upsample_bwd_w_kernel, (unsigned)(N * Do * Ho), 256, 0, stream,
+            reinterpret_cast<const __nv_bfloat16*>(dcat), ldc, coff, Wo, t, Wi, C);
   B2_CHECK_CUDA(cudaGetLastError());
-  B2_LAUNCH(upsample_bwd_hd_kernel, (unsigned)(N * Di * Hi), 256, 0, stream, t, Do, Ho, reinterpret_cast<__nv_bfloat16*>(dx),
-                                                                      Di, Hi, Wi, C);
+  B2_LAUNCH(upsample_bwd_hd_kernel, (unsigned)(N * Di * Hi), 256, 0, stream, t, Do, Ho,
+            reinterpret_cast<__nv_bfloat16*>(dx), Di, Hi, Wi, C, reinterpret_cast<const __nv_bfloat16*>(stat_r),
+            stat_acc);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
+}
+
+extern "C" int b2_upcat_bwd_separable(const void* dcat, int ldc, int coff, int N, int Do, int Ho, int Wo, void* dx,
+                                      int Di, int Hi, int Wi, int C, void* workspace, long long workspace_bytes,
+                                      cudaStream_t stream) {
+  return upcat_bwd_separable_impl(dcat, ldc, coff, N, Do, Ho, Wo, dx, Di, Hi, Wi, C, workspace, workspace_bytes,
+                                  nullptr, nullptr, stream);
+}
+
+// Same (batch 1); dx is the gradient at a GroupNorm output: also accumulates that layer's GroupNorm-backward
+// statistics (sum dx, sum dx*r; r dense bf16 [Di*Hi*Wi][C]) into stat_acc int64 [C][4].
+extern "C" int b2_upcat_bwd_separable_bstats(const void* dcat, int ldc, int coff, int N, int Do, int Ho, int Wo,
+                                             void* dx, int Di, int Hi, int Wi, int C, void* workspace,
+                                             long long workspace_bytes, const void* r, long long* stat_acc,
+                                             cudaStream_t stream) {
+  B2_REQUIRE(r && stat_acc, "b2_upcat_bwd_separable_bstats: null pointer");
+  return upcat_bwd_separable_impl(dcat, ldc, coff, N, Do, Ho, Wo, dx, Di, Hi, Wi, C, workspace, workspace_bytes, r,
+                                  stat_acc, stream);
 }
 
 extern "C" int b2_upcat_bwd(const void* dcat, int ldc, int coff, int N, int Do, int Ho, int Wo, void* dx, int Di,

@@ -119,7 +119,7 @@ class UNet3D(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k == "_layers_cache":
+            if k in ("_layers_cache", "_stat_pool"):
                 new.__dict__[k] = None
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)
@@ -187,6 +187,12 @@ class UNet3D(nn.Module):
         up_c = [2 * f, 4 * f, 8 * f]               # channels upsampled into cat at level 0..2
         cats = [ActView.alloc(B, *dims[l], skip_c[l] + up_c[l], dev) for l in range(3)]
         rec = []                                   # per conv layer: dict(x=ActView|tensor, r=ActView, mr=tensor)
+        pool = None
+        if B == 1:                                 # statistics accumulators of this step, zeroed with one fill
+            pool = self.__dict__.get("_stat_pool")
+            if pool is None or pool.buf.device != dev:
+                pool = self.__dict__["_stat_pool"] = ops.StatPool(dev)
+            pool.reset()
 
         def conv_gn(layer, xin, out_view, pooled=None, first=False):
             cin, cout = layer.cin, layer.cout
@@ -195,13 +201,13 @@ class UNet3D(nn.Module):
             gamma, beta = layer.norm.weight.detach(), layer.norm.bias.detach()
             if first and B == 1:
                 mr, ss = ops.conv3d_first_fwd_gn_stats(xin, layer.conv.weight.detach(), r, G, layer.norm.eps, gamma,
-                                                       beta)
+                                                       beta, pool)
             elif first:
                 ops.conv3d_first_fwd(xin, layer.conv.weight.detach(), r, relu=True)
                 mr, ss = ops.relu_gn_stats(r, G, layer.norm.eps, gamma, beta)
             elif B == 1 and cout <= 256 and B * d * h * w > ops.SPLITK_MAX_VOXELS:
-                wf, _ = layer.packs()   # GroupNorm statistics come out of the conv epilogue
-                mr, ss = ops.conv3d_igemm_gn_stats(xin, wf, r, cin, cout, G, layer.norm.eps, gamma, beta)
+                wf, _ = layer.packs()   # GroupNorm statistics come out of the conv epilogue (exact accumulators)
+                mr, ss = ops.conv3d_igemm_gn_stats(xin, wf, r, cin, cout, G, layer.norm.eps, gamma, beta, pool)
             else:
                 wf, _ = layer.packs()
                 ops.conv3d_igemm_auto(xin, wf, r, cin, cout, relu=True)   # split-K when the volume is tiny
@@ -240,11 +246,11 @@ class UNet3D(nn.Module):
             cur = y2
         if save is not None:
             save.rec, save.cats, save.dims, save.x = rec, cats, dims, x
-            save.skip_c, save.up_c = skip_c, up_c
+            save.skip_c, save.up_c, save.pool = skip_c, up_c, pool
         return cur
 
     # ------------------------------------------------------------------------------------------ trunk backward
-    def _trunk_backward(self, save, dfeat, needs, outs=None):
+    def _trunk_backward(self, save, dfeat, needs, outs=None, dfeat_stats=None):
         """dfeat: ActView gradient w.r.t. the trunk output.  needs: list of 42 bools (w, gamma, beta per layer).
         outs: optional list of 42 pre-allocated fp32 tensors the gradients are written into (views of the
         data-parallel buckets).  Returns list of 42 grads (None where not needed)."""
@@ -296,7 +302,7 @@ class UNet3D(nn.Module):
             _, wd = layer.packs()
             if i % 2 == 1 and B == 1 and layer.cin <= 256 and xin.N * xin.V > ops.SPLITK_MAX_VOXELS:
                 # conv2 of a block: dx IS the gradient at conv1's GroupNorm output -> fuse its backward statistics
-                stats = ops.conv3d_dgrad_gn_bstats(dr, wd, dx, layer.cout, layer.cin, rec[i - 1]["r"])
+                stats = ops.conv3d_dgrad_gn_bstats(dr, wd, dx, layer.cout, layer.cin, rec[i - 1]["r"], save.pool)
                 return dx, stats
             ops.conv3d_igemm_auto(dr, wd, dx, layer.cout, layer.cin, relu=False)
             return dx
@@ -308,8 +314,12 @@ class UNet3D(nn.Module):
         def split(res):
             return res if isinstance(res, tuple) else (res, None)
 
+        # The kernel that PRODUCES the gradient at a GroupNorm output also accumulates that layer's GroupNorm-backward
+        # statistics (batch 1): the upsample adjoint for layers 11, 9, 7, the pooling adjoint for layers 5, 3, 1.
+        fuse = (B == 1)
+        st_next = dfeat_stats    # layer 13: accumulated by the head kernel when it produced dfeat
         for lvl in (0, 1, 2):
-            dy, st = split(layer_bwd(li, dy))
+            dy, st = split(layer_bwd(li, dy, st_next))
             li -= 1
             if dy is None:
                 return grads
@@ -318,13 +328,21 @@ class UNet3D(nn.Module):
             if dc is None:
                 return grads
             dcat[lvl] = dc
-            dy = ops.upcat_bwd(dc.window(skip_c[lvl], up_c[lvl]), *dims[lvl + 1])
+            if fuse and 2048 % up_c[lvl] == 0:
+                dy, st_next = ops.upcat_bwd(dc.window(skip_c[lvl], up_c[lvl]), *dims[lvl + 1], stat_r=rec[li]["r"],
+                                            pool=save.pool)
+            else:
+                dy, st_next = ops.upcat_bwd(dc.window(skip_c[lvl], up_c[lvl]), *dims[lvl + 1]), None
         # encoders: layers 7,6 (lvl 3) ... 1,0 (lvl 0)
         for lvl in (3, 2, 1, 0):
             if lvl < 3:
                 ywin = cats[lvl].window(0, skip_c[lvl])
-                dy = ops.maxpool3d_bwd_add(ywin, dcat[lvl].window(0, skip_c[lvl]), dy)
-            dy, st = split(layer_bwd(li, dy))
+                if fuse and 256 % (skip_c[lvl] // 8) == 0:
+                    dy, st_next = ops.maxpool3d_bwd_add(ywin, dcat[lvl].window(0, skip_c[lvl]), dy,
+                                                        stat_r=rec[li]["r"], pool=save.pool)
+                else:
+                    dy, st_next = ops.maxpool3d_bwd_add(ywin, dcat[lvl].window(0, skip_c[lvl]), dy), None
+            dy, st = split(layer_bwd(li, dy, st_next))
             li -= 1
             if dy is None:
                 return grads
@@ -375,12 +393,15 @@ class UNet3D(nn.Module):
         save = _Saved()
         with torch.no_grad():
             feat = self._trunk_forward(x, save)
+            fuse13 = x.shape[0] == 1 and any(needs[:42])
             out = ops.head_ce(feat, labels, head.weight.detach(), head.bias.detach(), compute_grad=True,
                               eval_softmax=False, grad_scale=float(loss_scale), want_preds=True,
-                              want_dx=any(needs[:42]), dW_out=outs[42], db_out=outs[43])
+                              want_dx=any(needs[:42]), dW_out=outs[42], db_out=outs[43],
+                              stat_r=save.rec[13]["r"] if fuse13 else None, pool=save.pool)
             if self.grad_ready_hook is not None:
                 self.grad_ready_hook(14, [t for t, n in zip((out["dW"], out["db"]), needs[42:]) if n])
-            grads = self._trunk_backward(save, out["dx"], needs[:42], outs[:42]) if any(needs[:42]) else [None] * 42
+            grads = (self._trunk_backward(save, out["dx"], needs[:42], outs[:42], out["dx_stats"])
+                     if any(needs[:42]) else [None] * 42)
         grads = list(grads) + [out["dW"] if needs[42] else None, out["db"] if needs[43] else None]
         return out["loss"], out["count"], out["preds"], grads
 

@@ -136,60 +136,87 @@ def conv3d_igemm_auto(x, wpack, y, cin, cout, relu):
     _count(2)
 
 
-def conv3d_igemm_gn_stats(x, wpack, y, cin, cout, groups, eps, gamma, beta):
-    """fprop + ReLU with the GroupNorm statistics fused into the conv epilogue (batch 1, cout <= 256).
-    Returns (mean_rstd [1,C,2], scale_shift [1,C,2]) like relu_gn_stats, without re-reading the output tensor."""
+class StatPool(object):
+    """Exact GroupNorm statistics accumulators (int64 [C][4] per layer, see include/unetsulc_b200.h) carved out of
+    one buffer that is zeroed with a single fill at the start of a step.  `take(C)` hands out the next slot."""
+    SLOT = 512 * 4
+
+    def __init__(self, device, slots=32):
+        self.buf = torch.zeros(slots * self.SLOT, dtype=torch.int64, device=device)
+        self.next = 0
+
+    def reset(self):
+        self.buf.zero_()
+        self.next = 0
+        _count(1)
+
+    def take(self, C):
+        if C > 512:
+            raise RuntimeError("unetsulc_b200: statistics accumulators support <= 512 channels, got %d" % C)
+        if (self.next + 1) * self.SLOT > self.buf.numel():
+            raise RuntimeError("unetsulc_b200: StatPool exhausted (reset() it once per step)")
+        t = self.buf[self.next * self.SLOT:self.next * self.SLOT + 4 * C]
+        self.next += 1
+        return t
+
+
+def _acc(pool, C, device):
+    return pool.take(C) if pool is not None else torch.zeros(4 * C, dtype=torch.int64, device=device)
+
+
+def conv3d_igemm_gn_stats(x, wpack, y, cin, cout, groups, eps, gamma, beta, pool=None):
+    """fprop + ReLU with the GroupNorm statistics fused into the conv epilogue (batch 1, cout <= 256): exact
+    accumulators + a one-block finalize.  Returns (mean_rstd [1,C,2], scale_shift [1,C,2]) like relu_gn_stats,
+    without re-reading the output tensor."""
     lib = _lib.load()
     _need_cuda(x.buf, wpack, y.buf, gamma, beta)
-    dev = x.buf.device
-    maxp = lib.b2_conv3d_stats_max_partials()
-    partial = Workspace.get(maxp * cout * 2 * 4, dev, "convstats")
-    n_partials = C.c_int(0)
+    acc = _acc(pool, cout, x.buf.device)
     with _Prof("conv3d_igemm", 2.0 * x.N * x.V * 27 * cin * cout):
         _lib.check(lib.b2_conv3d_igemm_stats(_p(x.buf), x.ld, x.coff, _p(wpack), _p(y.buf), y.ld, y.coff, x.N, x.D,
-                                             x.H, x.W, cin, cout, 1, _p(partial), C.byref(n_partials), _s()),
-                   "b2_conv3d_igemm_stats")
-    mean_rstd = torch.empty((1, cout, 2), dtype=torch.float32, device=dev)
-    scale_shift = torch.empty((1, cout, 2), dtype=torch.float32, device=dev)
-    _lib.check(lib.b2_relu_gn_finalize(_p(partial), n_partials.value, x.V, cout, groups, float(eps), _p(gamma),
-                                       _p(beta), _p(mean_rstd), _p(scale_shift), _s()), "b2_relu_gn_finalize")
-    _count(2)
+                                             x.H, x.W, cin, cout, 1, _p(acc), _s()), "b2_conv3d_igemm_stats")
+    _count(1)
+    return gn_finalize_acc(acc, x.V, cout, groups, eps, gamma, beta)
+
+
+def gn_finalize_acc(acc, V, C, groups, eps, gamma, beta):
+    """exact accumulators int64 [C][4] -> (mean_rstd [1,C,2], scale_shift [1,C,2])"""
+    lib = _lib.load()
+    mean_rstd = torch.empty((1, C, 2), dtype=torch.float32, device=acc.device)
+    scale_shift = torch.empty((1, C, 2), dtype=torch.float32, device=acc.device)
+    _lib.check(lib.b2_relu_gn_finalize_acc(_p(acc), V, C, groups, float(eps), _p(gamma), _p(beta), _p(mean_rstd),
+                                           _p(scale_shift), _s()), "b2_relu_gn_finalize_acc")
+    _count(1)
     return mean_rstd, scale_shift
 
 
-def conv3d_dgrad_gn_bstats(dy, wd, dx, cin, cout, r):
+def conv3d_dgrad_gn_bstats(dy, wd, dx, cin, cout, r, pool=None):
     """dgrad (dy: gradient w.r.t. the conv output with `cin` channels -> dx with `cout` channels, dense) with the
     GroupNorm-backward statistics of the layer that produced dx's forward tensor fused into the epilogue.
-    r: that layer's stored relu(conv) (dense ActView, `cout` channels).  Returns an opaque stats handle."""
+    r: that layer's stored relu(conv) (dense ActView, `cout` channels).  Returns the accumulator tensor."""
     lib = _lib.load()
-    dev = dy.buf.device
-    maxp = lib.b2_conv3d_stats_max_partials()
-    partial = Workspace.get(maxp * cout * 2 * 4, dev, "convbstats")
-    n_partials = C.c_int(0)
+    acc = _acc(pool, cout, dy.buf.device)
     with _Prof("conv3d_igemm", 2.0 * dy.N * dy.V * 27 * cin * cout):
         _lib.check(lib.b2_conv3d_igemm_bstats(_p(dy.buf), dy.ld, dy.coff, _p(wd), _p(dx.buf), dy.N, dy.D, dy.H, dy.W,
-                                              cin, cout, _p(r.buf), _p(partial), C.byref(n_partials), _s()),
-                   "b2_conv3d_igemm_bstats")
+                                              cin, cout, _p(r.buf), _p(acc), _s()), "b2_conv3d_igemm_bstats")
     _count(1)
-    return (partial, n_partials.value)
+    return acc
 
 
-def relu_gn_bwd_from_stats(stats, dy, r, groups, gamma, mean_rstd, want_param_grads=True, dgamma_out=None,
+def relu_gn_bwd_from_stats(acc, dy, r, groups, gamma, mean_rstd, want_param_grads=True, dgamma_out=None,
                            dbeta_out=None):
-    """GroupNorm backward using the statistics fused into the dgrad that produced `dy` (batch 1)."""
+    """GroupNorm backward using (sum dy, sum dy*r) accumulated by the kernel that produced `dy` (batch 1): a
+    one-block finalize + the apply pass, no statistics pass over (dy, r)."""
     lib = _lib.load()
     dev = r.buf.device
-    partial, n_partials = stats
     dr = ActView.alloc(r.N, r.D, r.H, r.W, r.C, dev)
     dgamma = dgamma_out if dgamma_out is not None else (
         torch.empty(r.C, dtype=torch.float32, device=dev) if want_param_grads else None)
     dbeta = dbeta_out if dbeta_out is not None else (
         torch.empty(r.C, dtype=torch.float32, device=dev) if want_param_grads else None)
     ws = Workspace.get(r.C * 16, dev, "gncoef")
-    _lib.check(lib.b2_relu_gn_bwd_from_partials(_p(partial), n_partials, _p(dy.buf), dy.ld, dy.coff, _p(r.buf), r.V,
-                                                r.C, groups, _p(gamma), _p(mean_rstd), _p(dr.buf), _p(dgamma),
-                                                _p(dbeta), _p(ws), ws.numel(), _s()),
-               "b2_relu_gn_bwd_from_partials")
+    _lib.check(lib.b2_relu_gn_bwd_acc(_p(acc), _p(dy.buf), dy.ld, dy.coff, _p(r.buf), r.V, r.C, groups, _p(gamma),
+                                      _p(mean_rstd), _p(dr.buf), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _s()),
+               "b2_relu_gn_bwd_acc")
     _count(2)
     return dr, dgamma, dbeta
 
@@ -219,22 +246,16 @@ def conv3d_first_fwd(x, w, y, relu=True):
     _count(1)
 
 
-def conv3d_first_fwd_gn_stats(x, w, y, groups, eps, gamma, beta):
+def conv3d_first_fwd_gn_stats(x, w, y, groups, eps, gamma, beta, pool=None):
     """first conv + ReLU with the GroupNorm statistics fused in (batch 1).  Returns (mean_rstd, scale_shift)."""
     lib = _lib.load()
     _need_cuda(x, w, y.buf, gamma, beta)
-    dev = x.device
     cout = w.shape[0]
-    partial = Workspace.get(lib.b2_conv3d_first_stats_max_partials() * cout * 2 * 4, dev, "convstats")
-    n_partials = C.c_int(0)
+    acc = _acc(pool, cout, x.device)
     _lib.check(lib.b2_conv3d_first_fwd_stats(_p(x), _p(w), _p(y.buf), y.ld, y.coff, y.N, y.D, y.H, y.W, cout, 1,
-                                             _p(partial), C.byref(n_partials), _s()), "b2_conv3d_first_fwd_stats")
-    mean_rstd = torch.empty((1, cout, 2), dtype=torch.float32, device=dev)
-    scale_shift = torch.empty((1, cout, 2), dtype=torch.float32, device=dev)
-    _lib.check(lib.b2_relu_gn_finalize(_p(partial), n_partials.value, y.V, cout, groups, float(eps), _p(gamma),
-                                       _p(beta), _p(mean_rstd), _p(scale_shift), _s()), "b2_relu_gn_finalize")
-    _count(2)
-    return mean_rstd, scale_shift
+                                             _p(acc), _s()), "b2_conv3d_first_fwd_stats")
+    _count(1)
+    return gn_finalize_acc(acc, y.V, cout, groups, eps, gamma, beta)
 
 
 def conv3d_first_wgrad(x, dy, cout, out=None):
@@ -290,14 +311,22 @@ def relu_gn_bwd(dy, r, groups, gamma, mean_rstd, want_param_grads=True, dgamma_o
     return dr, dgamma, dbeta
 
 
-def maxpool3d_bwd_add(y, dskip, dpool):
-    """y: forward tensor window (pre-pool); dskip: ActView or None; dpool: dense ActView at half res."""
+def maxpool3d_bwd_add(y, dskip, dpool, stat_r=None, pool=None):
+    """y: forward tensor window (pre-pool); dskip: ActView or None; dpool: dense ActView at half res.
+    stat_r (batch 1): the saved relu(conv) of the layer whose output gradient this is — the kernel then also
+    accumulates that layer's GroupNorm-backward statistics; returns (out, acc) instead of out."""
     lib = _lib.load()
     out = ActView.alloc(y.N, y.D, y.H, y.W, y.C, y.buf.device)
-    _lib.check(lib.b2_maxpool3d_bwd_add(_p(y.buf), y.ld, y.coff, _p(dskip.buf) if dskip is not None else C.c_void_p(0),
-                                        dskip.ld if dskip is not None else 8, dskip.coff if dskip is not None else 0,
-                                        _p(dpool.buf), _p(out.buf), y.N, y.D, y.H, y.W, y.C, _s()),
-               "b2_maxpool3d_bwd_add")
+    args = (_p(y.buf), y.ld, y.coff, _p(dskip.buf) if dskip is not None else C.c_void_p(0),
+            dskip.ld if dskip is not None else 8, dskip.coff if dskip is not None else 0,
+            _p(dpool.buf), _p(out.buf), y.N, y.D, y.H, y.W, y.C)
+    if stat_r is not None:
+        acc = _acc(pool, y.C, y.buf.device)
+        _lib.check(lib.b2_maxpool3d_bwd_add_bstats(*(args + (_p(stat_r.buf), _p(acc), _s()))),
+                   "b2_maxpool3d_bwd_add_bstats")
+        _count(1)
+        return out, acc
+    _lib.check(lib.b2_maxpool3d_bwd_add(*(args + (_s(),))), "b2_maxpool3d_bwd_add")
     _count(1)
     return out
 
@@ -310,12 +339,20 @@ def upcat_fwd(x, cat_window):
     _count(1)
 
 
-def upcat_bwd(dcat_window, Di, Hi, Wi, separable=True):
+def upcat_bwd(dcat_window, Di, Hi, Wi, separable=True, stat_r=None, pool=None):
+    """adjoint of the trilinear upsample.  stat_r (batch 1, separable): see maxpool3d_bwd_add; returns (dx, acc)."""
     lib = _lib.load()
     c = dcat_window
     dx = ActView.alloc(c.N, Di, Hi, Wi, c.C, c.buf.device)
     if separable:
         ws = Workspace.get(lib.b2_upcat_bwd_workspace_bytes(c.N, c.D, c.H, Wi, c.C), c.buf.device, "upbwd")
+        if stat_r is not None:
+            acc = _acc(pool, c.C, c.buf.device)
+            _lib.check(lib.b2_upcat_bwd_separable_bstats(_p(c.buf), c.ld, c.coff, c.N, c.D, c.H, c.W, _p(dx.buf), Di,
+                                                         Hi, Wi, c.C, _p(ws), ws.numel(), _p(stat_r.buf), _p(acc),
+                                                         _s()), "b2_upcat_bwd_separable_bstats")
+            _count(2)
+            return dx, acc
         _lib.check(lib.b2_upcat_bwd_separable(_p(c.buf), c.ld, c.coff, c.N, c.D, c.H, c.W, _p(dx.buf), Di, Hi, Wi,
                                               c.C, _p(ws), ws.numel(), _s()), "b2_upcat_bwd_separable")
         _count(2)
@@ -327,7 +364,7 @@ def upcat_bwd(dcat_window, Di, Hi, Wi, separable=True):
 
 
 def head_ce(x, labels, W, b, compute_grad, eval_softmax=False, grad_scale=1.0, grad_scale_dev=None,
-            want_preds=True, want_dx=True, dW_out=None, db_out=None):
+            want_preds=True, want_dx=True, dW_out=None, db_out=None, stat_r=None, pool=None):
     """x: dense ActView [N,D,H,W,Cin]; labels int64 [N,D,H,W] (-1 = ignore).
     Returns dict(loss [2] fp32 (mean, sum), count int32 [1], preds int32 [N,D,H,W] or None, dx ActView, dW, db)."""
     lib = _lib.load()
@@ -347,12 +384,21 @@ def head_ce(x, labels, W, b, compute_grad, eval_softmax=False, grad_scale=1.0, g
     Wc = W.reshape(cout, cin)
     if not Wc.is_contiguous():
         Wc = Wc.contiguous()
-    _lib.check(lib.b2_head_ce(_p(x.buf), _p(labels), NV, _p(Wc), _p(b), cin, cout, float(grad_scale),
-                              _p(grad_scale_dev), int(compute_grad), int(eval_softmax), _p(preds),
-                              _p(dx.buf) if dx is not None else C.c_void_p(0), _p(dW), _p(db), _p(loss), _p(count),
-                              _p(ws), ws.numel(), _s()), "b2_head_ce")
+    dx_stats = None
+    if stat_r is not None and dx is not None and not eval_softmax:
+        # dx is the gradient at the last GroupNorm output: its backward statistics come out of this kernel too
+        dx_stats = _acc(pool, cin, dev)
+        _lib.check(lib.b2_head_ce_bstats(_p(x.buf), _p(labels), NV, _p(Wc), _p(b), cin, cout, float(grad_scale),
+                                         _p(grad_scale_dev), _p(preds), _p(dx.buf), _p(dW), _p(db), _p(loss),
+                                         _p(count), _p(ws), ws.numel(), _p(stat_r.buf), _p(dx_stats), _s()),
+                   "b2_head_ce_bstats")
+    else:
+        _lib.check(lib.b2_head_ce(_p(x.buf), _p(labels), NV, _p(Wc), _p(b), cin, cout, float(grad_scale),
+                                  _p(grad_scale_dev), int(compute_grad), int(eval_softmax), _p(preds),
+                                  _p(dx.buf) if dx is not None else C.c_void_p(0), _p(dW), _p(db), _p(loss), _p(count),
+                                  _p(ws), ws.numel(), _s()), "b2_head_ce")
     _count(3)
-    return dict(loss=loss, count=count, preds=preds, dx=dx, dW=dW, db=db)
+    return dict(loss=loss, count=count, preds=preds, dx=dx, dW=dW, db=db, dx_stats=dx_stats)
 
 
 def head_gather(x, index, W, b, softmax=True):

@@ -9,6 +9,7 @@ on-device ESI counters.  Data-parallel training over subjects is enabled when ``
 import copy
 import json
 import os
+import sys
 import os.path as op
 import time
 
@@ -346,7 +347,11 @@ class UnetPatternSulciLabelling(object):
         pool = torch.cuda.graph_pool_handle()
         side = torch.cuda.Stream(device=sx.device)
 
+        dbg = os.environ.get("B2_DEBUG_DP") == "1"
+
         def begin():
+            if dbg:
+                print("[b2 dp-graph] capture segment %d" % len(segs), file=sys.stderr, flush=True)
             g = torch.cuda.CUDAGraph()
             # thread_local: the NCCL watchdog thread may query events while this thread captures
             g.capture_begin(pool=pool, capture_error_mode="thread_local")
@@ -402,10 +407,15 @@ class UnetPatternSulciLabelling(object):
             segs, sx, sy, loss = ent
             sx.copy_(x, non_blocking=True)
             sy.copy_(y, non_blocking=True)
-        for g, action in ent[0]:
+        dbg = os.environ.get("B2_DEBUG_DP") == "1"
+        for k, (g, action) in enumerate(ent[0]):
+            if dbg:
+                print("[b2 dp-graph] replay segment %d/%d then %r" % (k, len(ent[0]), action), file=sys.stderr, flush=True)
             g.replay()
             if action is None:
                 continue
+            if os.environ.get("B2_DP_GRAPH_SYNC") == "1":   # debugging aid: no compute / collective concurrency
+                torch.cuda.synchronize()
             if action[0] == "reduce":
                 reducer._launch(action[1])
             else:

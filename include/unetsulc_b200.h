@@ -39,26 +39,27 @@ int b2_conv3d_igemm_splitk(const void* x, int ldx, int x_coff, const void* wpack
                            int D, int H, int W, int Cin, int Cout, int relu, void* workspace,
                            long long workspace_bytes, cudaStream_t stream);
 
-/* fprop with the GroupNorm statistics of the stored (bf16, post-ReLU) output fused into the epilogue (batch 1, Cout
- * <= 256).  stat_partial: fp32 [b2_conv3d_stats_max_partials()][Cout][2]; *n_partials (HOST int) = rows written;
- * b2_relu_gn_finalize turns them into mean/rstd and scale/shift (replaces b2_relu_gn_stats, saves one tensor read). */
-int b2_conv3d_stats_max_partials(void);
+/* ---- statistics accumulators ------------------------------------------------------------------------------------
+ * GroupNorm statistics travel between kernels as EXACT, order-independent accumulators: int64 [C][4] per layer =
+ * {sum_hi, sum_lo, sq_hi, sq_lo} (integer part + fraction in units of 2^-32), filled with integer atomics by the
+ * kernel that PRODUCES the tensor and turned into mean / rstd / coefficients by a one-block finalize: no per-block
+ * partial buffers, no statistics pass over the tensor, bit-identical run to run.  The caller zeroes the accumulators before the producer runs.
+ *
+ * fprop with the statistics of the stored (bf16, post-ReLU) output fused into the epilogue (batch 1, Cout <= 256). */
 int b2_conv3d_igemm_stats(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff, int N,
-                          int D, int H, int W, int Cin, int Cout, int relu, float* stat_partial, int* n_partials,
-                          cudaStream_t stream);
+                          int D, int H, int W, int Cin, int Cout, int relu, long long* stat_acc, cudaStream_t stream);
 /* dgrad with the GroupNorm-BACKWARD statistics (sum dX, sum dX*r per channel) of the producing layer fused into the
- * epilogue; r = that layer's stored relu(conv), dense bf16 [V][Cout]; dX is written densely (ld = Cout).
- * b2_relu_gn_bwd_from_partials then runs finalize + apply without a statistics pass (workspace >= Cout*16 bytes).  */
+ * epilogue; r = that layer's stored relu(conv), dense bf16 [V][Cout]; dX is written densely (ld = Cout).            */
 int b2_conv3d_igemm_bstats(const void* x, int ldx, int x_coff, const void* wpack, void* y, int N, int D, int H, int W,
-                           int Cin, int Cout, const void* r, float* stat_partial, int* n_partials,
-                           cudaStream_t stream);
-int b2_relu_gn_bwd_from_partials(const float* stat_partial, int n_partials, const void* dy, int lddy, int dy_coff,
-                                 const void* r, long long V, int C, int G, const float* gamma,
-                                 const float* mean_rstd, void* dr, float* dgamma, float* dbeta, void* workspace,
-                                 long long workspace_bytes, cudaStream_t stream);
-int b2_relu_gn_finalize(const float* stat_partial, int n_partials, long long V, int C, int G, float eps,
-                        const float* gamma, const float* beta, float* mean_rstd, float* scale_shift,
-                        cudaStream_t stream);
+                           int Cin, int Cout, const void* r, long long* stat_acc, cudaStream_t stream);
+/* accumulators -> mean_rstd fp32 [C][2] + scale_shift fp32 [C][2] (one small block; then b2_relu_gn_apply), and the
+ * backward counterpart: accumulators of (sum dy, sum dy*r) -> coefficients, dgamma, dbeta (may be NULL) + the apply
+ * pass, without a statistics pass over (dy, r).  Batch 1.  workspace >= C*16 bytes.                                 */
+int b2_relu_gn_finalize_acc(const long long* stat_acc, long long V, int C, int G, float eps, const float* gamma,
+                            const float* beta, float* mean_rstd, float* scale_shift, cudaStream_t stream);
+int b2_relu_gn_bwd_acc(const long long* stat_acc, const void* dy, int lddy, int dy_coff, const void* r, long long V,
+                       int C, int G, const float* gamma, const float* mean_rstd, void* dr, float* dgamma,
+                       float* dbeta, void* workspace, long long workspace_bytes, cudaStream_t stream);
 
 /* dW[co][ci][3][3][3] (fp32, PyTorch layout) = sum_v dY[v,co] * X[v+off,ci]                                      */
 long long b2_conv3d_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout);
@@ -69,11 +70,9 @@ int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* dy, int ldy,
 /* encoders.0.conv1 (Cin = 1): direct convolution on the fp32 [N,D,H,W] skeleton volume (dataset.py:78-80)        */
 int b2_conv3d_first_fwd(const float* x, const float* w, void* y, int ldy, int y_coff, int N, int D, int H, int W,
                         int Cout, int relu, cudaStream_t stream);
-/* same, with the GroupNorm statistics of the stored output fused in (batch 1): stat_partial fp32
- * [b2_conv3d_first_stats_max_partials()][Cout][2], finalised by b2_relu_gn_finalize; *n_partials is a HOST int.     */
-int b2_conv3d_first_stats_max_partials(void);
+/* same, with the GroupNorm statistics of the stored output fused in (batch 1): stat_acc int64 [Cout][4], see above  */
 int b2_conv3d_first_fwd_stats(const float* x, const float* w, void* y, int ldy, int y_coff, int N, int D, int H, int W,
-                              int Cout, int relu, float* stat_partial, int* n_partials, cudaStream_t stream);
+                              int Cout, int relu, long long* stat_acc, cudaStream_t stream);
 long long b2_conv3d_first_wgrad_workspace_bytes(int Cout);
 int b2_conv3d_first_wgrad(const float* x, const void* dy, int lddy, int dy_coff, float* dw, void* workspace,
                           long long workspace_bytes, int N, int D, int H, int W, int Cout, cudaStream_t stream);
@@ -95,6 +94,11 @@ int b2_relu_gn_bwd(const void* dy, int lddy, int dy_coff, const void* r, int N, 
 /* ---- MaxPool3d(2) backward (+ skip gradient add), trilinear upsample + concat and its backward ------------------ */
 int b2_maxpool3d_bwd_add(const void* y, int ldy, int y_coff, const void* dskip, int ldd, int d_coff,
                          const void* dpool, void* out, int N, int D, int H, int W, int C, cudaStream_t stream);
+/* same (batch 1) + the GroupNorm-backward statistics (sum out, sum out*r) of the layer whose output gradient `out` is,
+ * accumulated into stat_acc int64 [C][4]; r = that layer's saved relu(conv), dense bf16 [V][C]                      */
+int b2_maxpool3d_bwd_add_bstats(const void* y, int ldy, int y_coff, const void* dskip, int ldd, int d_coff,
+                                const void* dpool, void* out, int N, int D, int H, int W, int C, const void* r,
+                                long long* stat_acc, cudaStream_t stream);
 int b2_upcat_fwd(const void* x, int N, int Di, int Hi, int Wi, int C, void* cat, int ldc, int coff, int Do, int Ho,
                  int Wo, cudaStream_t stream);
 int b2_upcat_bwd(const void* dcat, int ldc, int coff, int N, int Do, int Ho, int Wo, void* dx, int Di, int Hi,
@@ -105,6 +109,9 @@ int b2_upcat_bwd(const void* dcat, int ldc, int coff, int N, int Do, int Ho, int
 long long b2_upcat_bwd_workspace_bytes(int N, int Do, int Ho, int Wi, int C);
 int b2_upcat_bwd_separable(const void* dcat, int ldc, int coff, int N, int Do, int Ho, int Wo, void* dx, int Di,
                            int Hi, int Wi, int C, void* workspace, long long workspace_bytes, cudaStream_t stream);
+int b2_upcat_bwd_separable_bstats(const void* dcat, int ldc, int coff, int N, int Do, int Ho, int Wo, void* dx,
+                                  int Di, int Hi, int Wi, int C, void* workspace, long long workspace_bytes,
+                                  const void* r, long long* stat_acc, cudaStream_t stream);
 
 /* ---- final_conv 1x1x1 (pattern_class.py:364) fused with softmax / cross-entropy / argmax ------------------------ */
 long long b2_head_workspace_bytes(int Cin);
@@ -115,6 +122,12 @@ int b2_head_ce(const void* x, const long long* labels, long long NV, const float
                int Cout, float grad_scale, const float* grad_scale_dev, int compute_grad, int eval_softmax,
                int* preds, void* dx, float* dW, float* db, float* loss_out, int* count_out, void* workspace,
                long long workspace_bytes, cudaStream_t stream);
+/* training form (compute_grad, dx != NULL) that also accumulates the GroupNorm-backward statistics (sum dX, sum dX*r)
+ * of the last trunk layer into stat_acc int64 [Cin][4]; r = that layer's saved relu(conv), dense bf16 [NV][Cin]     */
+int b2_head_ce_bstats(const void* x, const long long* labels, long long NV, const float* W, const float* b, int Cin,
+                      int Cout, float grad_scale, const float* grad_scale_dev, int* preds, void* dx, float* dW,
+                      float* db, float* loss_out, int* count_out, void* workspace, long long workspace_bytes,
+                      const void* r, long long* stat_acc, cudaStream_t stream);
 int b2_head_gather(const void* x, const long long* index, long long nidx, const float* W, const float* b, int Cin,
                    int Cout, int softmax, float* scores, int* preds, cudaStream_t stream);
 int b2_head_dense_fwd(const void* x, int N, long long V, const float* W, const float* b, int Cin, int Cout,

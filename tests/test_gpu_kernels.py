@@ -132,7 +132,7 @@ def test_conv_epilogue_groupnorm_statistics(shape):
     wf, _ = ops.pack_conv_weights(w)
     xv = ops.ActView(to_ndhwc(x), N, D, H, W, Cin)
     r1 = ops.ActView.alloc(N, D, H, W, Cout, "cuda", zero=True)
-    mr1, ss1 = ops.conv3d_igemm_gn_stats(xv, wf, r1, Cin, Cout, 32, 1e-5, gamma, beta)
+    mr1, ss1 = ops.conv3d_igemm_gn_stats(xv, wf, r1, Cin, Cout, 32, 1e-5, gamma, beta)   # exact accumulators
     r2 = ops.ActView.alloc(N, D, H, W, Cout, "cuda", zero=True)
     ops.conv3d_igemm(xv, wf, r2, Cin, Cout, relu=True)
     mr2, ss2 = ops.relu_gn_stats(r2, 32, 1e-5, gamma, beta)
@@ -144,6 +144,17 @@ def test_conv_epilogue_groupnorm_statistics(shape):
     y = ops.ActView.alloc(N, D, H, W, Cout, "cuda")
     ops.relu_gn_apply(r1, ss1, y)
     assert rel_l2(from_view(y), ref) < 4e-3
+    # the accumulators hold the exact sums of the stored tensor: compare with an fp64 reduction
+    lib = ops._lib.load()
+    acc = torch.zeros(4 * Cout, dtype=torch.int64, device="cuda")
+    r3 = ops.ActView.alloc(N, D, H, W, Cout, "cuda", zero=True)
+    ops._lib.check(lib.b2_conv3d_igemm_stats(ops._p(xv.buf), xv.ld, xv.coff, ops._p(wf), ops._p(r3.buf), r3.ld, r3.coff,
+                                             N, D, H, W, Cin, Cout, 1, ops._p(acc), ops._s()), "b2_conv3d_igemm_stats")
+    torch.cuda.synchronize()
+    a4 = acc.view(Cout, 4).double()
+    rr = r2.buf.double().reshape(-1, Cout)
+    assert torch.allclose(a4[:, 0] + a4[:, 1] / 2.0 ** 32, rr.sum(0), rtol=1e-6, atol=1e-3)
+    assert torch.allclose(a4[:, 2] + a4[:, 3] / 2.0 ** 32, (rr * rr).sum(0), rtol=1e-6, atol=1e-3)
 
 
 @pytest.mark.parametrize("shape", [(1, 256, 512, 12, 14, 12), (1, 256, 256, 6, 7, 6), (1, 64, 128, 5, 7, 9),
@@ -323,6 +334,34 @@ def test_conv_first_layer():
     got = ops.conv3d_first_wgrad(x, ops.ActView(to_ndhwc(dy), N, D, H, W, Cout), Cout)
     torch.cuda.synchronize()
     assert rel_l2(got, wp.grad) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 8, 12, 64), (128, 64, 6, 8, 32), (256, 128, 6, 7, 6)])
+def test_dgrad_fused_groupnorm_backward_statistics(shape):
+    """dgrad with (sum dX, sum dX*r) accumulated in its epilogue + the one-launch GroupNorm backward that finalises
+    them in its prologue == plain dgrad followed by the two-pass GroupNorm backward."""
+    ops = _ops()
+    Cdy, Cdx, D, H, W = shape
+    G = 32
+    g = torch.Generator(device="cuda").manual_seed(61)
+    dy = ops.ActView(torch.randn(1, D, H, W, Cdy, device="cuda", generator=g).to(torch.bfloat16), 1, D, H, W, Cdy)
+    w = torch.randn(Cdy, Cdx, 3, 3, 3, device="cuda", generator=g) * (1.0 / (27 * Cdy) ** 0.5)
+    _, wd = ops.pack_conv_weights(w)
+    r = ops.ActView(torch.randn(1, D, H, W, Cdx, device="cuda", generator=g).relu().to(torch.bfloat16), 1, D, H, W, Cdx)
+    gamma = torch.randn(Cdx, device="cuda", generator=g) * 0.5 + 1.0
+    beta = torch.zeros(Cdx, device="cuda")
+    mr, _ = ops.relu_gn_stats(r, G, 1e-5, gamma, beta)
+    dx1 = ops.ActView.alloc(1, D, H, W, Cdx, "cuda")
+    acc = ops.conv3d_dgrad_gn_bstats(dy, wd, dx1, Cdy, Cdx, r)
+    dr1, dg1, db1 = ops.relu_gn_bwd_from_stats(acc, dx1, r, G, gamma, mr)
+    dx2 = ops.ActView.alloc(1, D, H, W, Cdx, "cuda")
+    ops.conv3d_igemm(dy, wd, dx2, Cdy, Cdx, relu=False)
+    dr2, dg2, db2 = ops.relu_gn_bwd(dx2, r, G, gamma, mr)
+    torch.cuda.synchronize()
+    assert torch.equal(dx1.buf, dx2.buf)
+    assert rel_l2(dr1.buf.float(), dr2.buf.float()) < 2e-3
+    assert torch.allclose(dg1, dg2, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(db1, db2, rtol=1e-4, atol=1e-3)
 
 
 def test_conv_first_layer_fused_gn_stats():
