@@ -45,7 +45,7 @@ __device__ __forceinline__ void bstats_accumulate(float (&s)[8], float (&q)[8], 
 // out[v, c] = dskip[v, c] + (v is the arg-max of its 2x2x2 cell ? dpool[cell, c] : 0)
 // arg-max is recomputed from the stored forward tensor y; first maximum in (d, h, w) scan order wins, as in
 // PyTorch's max_pool3d_with_indices.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 pool_bwd_add_kernel(const __nv_bfloat16* __restrict__ y, int ldy, int y_coff, const __nv_bfloat16* __restrict__ dskip,
                     int ldd, int d_coff, const __nv_bfloat16* __restrict__ dpool, __nv_bfloat16* __restrict__ out,
                     int N, int D, int H, int W, int C, const __nv_bfloat16* __restrict__ stat_r,

@@ -340,8 +340,8 @@ class UnetPatternSulciLabelling(object):
         return loss
 
     def _capture_segments(self, sx, sy, optimizer, reducer):
-        """Records one eager step into a list of (CUDAGraph, action) segments; action is None, ("reduce", bucket)
-        or ("finish", None) = what has to be enqueued eagerly after that segment's replay."""
+        """Records one eager step into a list of (CUDAGraph, actions) segments; actions = list of ("reduce", bucket)
+        / ("finish", None): what has to be enqueued eagerly after that segment's replay."""
         import gc
         segs, cur = [], []
         pool = torch.cuda.graph_pool_handle()
@@ -357,10 +357,16 @@ class UnetPatternSulciLabelling(object):
             g.capture_begin(pool=pool, capture_error_mode="thread_local")
             cur.append(g)
 
+        mark = [ops.LAUNCHES[0]]
+
         def cut(action):
+            if ops.LAUNCHES[0] == mark[0] and segs:     # nothing enqueued since the last cut: no empty graph
+                segs[-1][1].append(action)
+                return
             g = cur.pop()
             g.capture_end()
-            segs.append((g, action))
+            segs.append((g, [action]))
+            mark[0] = ops.LAUNCHES[0]
             begin()
 
         gc.collect()
@@ -377,7 +383,7 @@ class UnetPatternSulciLabelling(object):
                     reducer.segment_cb = None
                 g = cur.pop()
                 g.capture_end()
-            segs.append((g, None))
+            segs.append((g, []))
         torch.cuda.current_stream().wait_stream(side)
         return segs, loss
 
@@ -408,18 +414,18 @@ class UnetPatternSulciLabelling(object):
             sx.copy_(x, non_blocking=True)
             sy.copy_(y, non_blocking=True)
         dbg = os.environ.get("B2_DEBUG_DP") == "1"
-        for k, (g, action) in enumerate(ent[0]):
+        for k, (g, actions) in enumerate(ent[0]):
             if dbg:
-                print("[b2 dp-graph] replay segment %d/%d then %r" % (k, len(ent[0]), action), file=sys.stderr, flush=True)
+                print("[b2 dp-graph] replay segment %d/%d then %r" % (k, len(ent[0]), actions), file=sys.stderr,
+                      flush=True)
             g.replay()
-            if action is None:
-                continue
-            if os.environ.get("B2_DP_GRAPH_SYNC") == "1":   # debugging aid: no compute / collective concurrency
-                torch.cuda.synchronize()
-            if action[0] == "reduce":
-                reducer._launch(action[1])
-            else:
-                reducer.finish()
+            for action in actions:
+                if os.environ.get("B2_DP_GRAPH_SYNC") == "1":   # debugging aid: no compute / collective concurrency
+                    torch.cuda.synchronize()
+                if action[0] == "reduce":
+                    reducer._launch(action[1])
+                else:
+                    reducer.finish()
         # the replayed SGD changed the fp32 masters behind PyTorch's back: bump their version counters so that eager
         # paths (validation, labeling, state_dict consumers) re-pack the bf16 weights
         for p in self.model.ordered_parameters():

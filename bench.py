@@ -207,10 +207,9 @@ def run_ours(args):
     ls_d = [l.to(dev) for l in ls_h]
     h2d = xs_h[0].numel() * 4 + ls_h[0].numel() * 8
 
-    # one rank: the step is replayed from a CUDA graph.  Data parallel: eager launches — the segmented replay (one graph
-    # segment per gradient bucket, NCCL all-reduces enqueued eagerly in between) passes its single-rank test but hung
-    # on 2 x B200 in round 1, so it stays opt-in (B2_DP_GRAPH=1) until that is understood.
-    trainer.use_cuda_graph = (not args.no_cuda_graph) and (world == 1 or os.environ.get("B2_DP_GRAPH") == "1")
+    # the step is replayed from CUDA graphs: one graph on one rank; under data parallelism one graph segment per
+    # gradient bucket with the NCCL all-reduces enqueued eagerly in between (NCCL itself is never captured)
+    trainer.use_cuda_graph = not args.no_cuda_graph
 
     def step_resident(i):
         return trainer.train_step_device(xs_d[i % n_data], ls_d[i % n_data], opt, reducer)
@@ -221,8 +220,10 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        sync_all()
+    def timed(fn, steps, collective=True):
+        """collective=False: rank-local timing (no barrier / all-reduce) for work only one rank does"""
+        sync = sync_all if collective else torch.cuda.synchronize
+        sync()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         a.record()
@@ -232,11 +233,11 @@ def run_ours(args):
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ms = a.elapsed_time(b)
-        if world > 1:
+        if world > 1 and collective:
             t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1e3
-        sync_all()
+        sync()
         return ms / 1e3, wall
 
     # per-kernel CUDA-event profile of the dominant kernel: taken on eager steps (events cannot be recorded inside a
@@ -318,7 +319,7 @@ def run_ours(args):
 
         for i in range(3):
             infer(i)
-        isecs, _ = timed(infer, 10)
+        isecs, _ = timed(infer, 10, collective=False)   # rank 0 only: no barrier
         inference = {"ms_per_hemi": isecs / 10 * 1e3, "voxels": int(idx.numel()), "folds": nf,
                      "what": "eval forward + softmax gather at skeleton voxels + fold vote for 3 thresholds, "
                              "inputs resident in HBM"}
@@ -353,6 +354,9 @@ def run_ours(args):
 
 
 def main():
+    if os.environ.get("B2_DEBUG_DP") == "1":   # debugging aid: dump every thread's Python stack if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("B2_DEBUG_DP_AFTER", "75")), exit=False)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
