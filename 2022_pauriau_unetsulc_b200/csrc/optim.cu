@@ -29,6 +29,30 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(const SgdArgs a) {
   const float* __restrict__ g = a.g[t];
   float* __restrict__ v = a.v[t];
   const long long n = a.n[t];
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+                   base + kChunk <= n;
+  if (vec) {   // full, 16-byte aligned chunk: four float4 per thread, all loads issued before the first store
+    float4 pv[4], gv[4], vv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long j = base + (long long)(k * 256 + threadIdx.x) * 4;
+      pv[k] = *reinterpret_cast<const float4*>(p + j);
+      gv[k] = *reinterpret_cast<const float4*>(g + j);
+      vv[k] = *reinterpret_cast<const float4*>(v + j);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long j = base + (long long)(k * 256 + threadIdx.x) * 4;
+      float4 nv, np;
+      nv.x = a.momentum * vv[k].x + gv[k].x * a.grad_scale; np.x = pv[k].x - a.lr * nv.x;
+      nv.y = a.momentum * vv[k].y + gv[k].y * a.grad_scale; np.y = pv[k].y - a.lr * nv.y;
+      nv.z = a.momentum * vv[k].z + gv[k].z * a.grad_scale; np.z = pv[k].z - a.lr * nv.z;
+      nv.w = a.momentum * vv[k].w + gv[k].w * a.grad_scale; np.w = pv[k].w - a.lr * nv.w;
+      *reinterpret_cast<float4*>(v + j) = nv;
+      *reinterpret_cast<float4*>(p + j) = np;
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < kChunk; i += 256) {
     const long long j = base + i;
     if (j < n) {
