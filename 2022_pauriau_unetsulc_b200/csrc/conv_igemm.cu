@@ -297,6 +297,234 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for the wide layers (BN >= 128, Cin % 64 == 0).
+// The one-CTA kernel above needs a 16 KB A tile AND the full BN x 64 weight tile per 128 x BN x 64 MMA group, i.e.
+// 94..128 B/clk/SM of L2 -> SM traffic against ~64 B/clk/SM delivered: those layers run at 1150..1300 TFLOP/s.  Here
+// two CTAs of a cluster (one TPC) compute TWO adjacent 128-voxel tiles with one 256 x BN x 16 instruction stream issued
+// by the leader; each CTA stages only its own A tile and HALF of the weight tile (the tensor cores read both halves
+// through the pair's shared memory), so the L2 -> SM weight traffic per SM halves: 62..94 B/clk/SM.
+// MEASURED (round 1, profiles/r01_bench_kernels_2cta.txt): correct (all conv parity tests pass) but 20-30 % SLOWER
+// than the one-CTA kernel on every wide layer (dec1.conv1 fprop 1203 -> 894, dec0.conv1 fprop 1393 -> 1020, dec2.conv1
+// dgrad 1317 -> 1062 TFLOP/s): the partner's half of the weight tile is read over the SM-to-SM path on every MMA, so
+// the bytes an SM has to ingest per MMA do not go down, and the pair adds cross-CTA barrier latency.  Kept opt-in
+// (B2_2CTA=1) as the starting point for a version that also splits A.
+// Barriers: full[s] lives in the leader (4 arrivals: A- and B-loader of each CTA, transaction bytes of all four TMA
+// loads); empty[s] / tmem_full[a] exist in both CTAs and are signalled by multicast tcgen05.commit; tmem_empty[a] lives
+// in the leader and collects the 2 x 128 epilogue threads of the pair.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv3d_igemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const IgemmParams p) {
+  pdl_prologue();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int KC = 64;
+  constexpr int kABytes = 128 * KC * 2;
+  const int b_half = p.b_bytes;   // (BN / 2) x KC bf16: this CTA's half of the weight tile
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)p.stages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_half);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.stages;
+  uint64_t* tmem_full = bars + 2 * p.stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  const long long m_tiles = p.total_tiles / p.n_tiles_n;
+  const long long n_work = ((m_tiles + 1) >> 1) * p.n_tiles_n;   // (pair of M tiles, N tile)
+
+  if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 4);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc_2cta(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 1 && warp <= 2 * kProducerPairs) {
+    // ------------------------------------------------------------------ TMA producers (both CTAs)
+    const int me = (warp - 1) >> 1;
+    const bool loads_a = ((warp - 1) & 1) == 0;
+    uint32_t gs = 0;
+    for (long long work = cluster_id; work < n_work; work += n_clusters) {
+      long long mt = (work / p.n_tiles_n) * 2 + rank;
+      if (mt >= m_tiles) mt = m_tiles - 1;   // odd tile count: the partner re-loads the last tile, stores nothing
+      int n, d0, h0, w0, n0;
+      decode_tile(mt * p.n_tiles_n + work % p.n_tiles_n, p, n, d0, h0, w0, n0);
+      for (int tap = 0; tap < 27; ++tap) {
+        const int dd = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
+        for (int ch = 0; ch < p.n_chunks; ++ch, ++gs) {
+          if ((int)(gs % kProducerPairs) != me) continue;
+          const int stage = (int)(gs % (uint32_t)p.stages);
+          const uint32_t phase = (gs / (uint32_t)p.stages) & 1u;
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
+            const uint32_t lead_full = mapa_shared(smem_u32(&full[stage]), 0);
+            if (loads_a) {
+              mbar_arrive_expect_tx_cluster(lead_full, (uint32_t)kABytes);
+              tma_load_5d_2sm(smem_a + (size_t)stage * kABytes, &tmap_a, lead_full, ch * KC, w0 + dw, h0 + dh, d0 + dd,
+                              n);
+            } else {
+              mbar_arrive_expect_tx_cluster(lead_full, (uint32_t)b_half);
+              tma_load_2d_2sm(smem_b + (size_t)stage * b_half, &tmap_b, lead_full, ch * KC,
+                              tap * p.Cout + n0 + (int)rank * (p.BN >> 1));
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 0) {
+    if (rank == 0) {
+      // ---------------------------------------------------------------- MMA issuer (leader CTA only)
+      const uint32_t idesc = make_idesc_bf16(256, (uint32_t)p.BN, 0, 0);
+      const uint64_t desc_hi = make_smem_desc(0, 16, 8u * KC * 2u, SWZ_128B);
+      const uint32_t a0 = smem_u32(smem_a) >> 4, b0 = smem_u32(smem_b) >> 4;
+      const uint32_t a_step = kABytes >> 4, b_step = (uint32_t)b_half >> 4;
+      const int n_stage_per_tile = 27 * p.n_chunks;
+      int stage = 0;
+      uint32_t phase = 0, it = 0;
+      for (long long work = cluster_id; work < n_work; work += n_clusters, ++it) {
+        const uint32_t acc = it & 1u;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1u) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int ks = 0; ks < n_stage_per_tile; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t adesc = desc_hi | (uint64_t)(a0 + (uint32_t)stage * a_step);
+            const uint64_t bdesc = desc_hi | (uint64_t)(b0 + (uint32_t)stage * b_step);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k)
+              umma_bf16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(&empty[stage], 3);
+            if (ks == n_stage_per_tile - 1) umma_commit_2cta(&tmem_full[acc], 3);
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 9..12, both CTAs)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int lw = row % p.bw;
+    const int lh = (row / p.bw) % p.bh;
+    const int ld = row / (p.bw * p.bh);
+    float st_s[8], st_q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
+    uint32_t it = 0;
+    for (long long work = cluster_id; work < n_work; work += n_clusters, ++it) {
+      const long long mt = (work / p.n_tiles_n) * 2 + rank;
+      const bool tile_ok = mt < m_tiles;
+      int n, d0, h0, w0, n0;
+      decode_tile((tile_ok ? mt : m_tiles - 1) * p.n_tiles_n + work % p.n_tiles_n, p, n, d0, h0, w0, n0);
+      const uint32_t acc = it & 1u;
+      const int w = w0 + lw, h = h0 + lh, d = d0 + ld;
+      const bool valid = tile_ok && (w < p.W) && (h < p.H) && (d < p.D);
+      const size_t vox = (((size_t)n * p.D + d) * p.H + h) * p.W + w;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccStride;
+#pragma unroll
+      for (int chunk = 0; chunk < 8; ++chunk) {
+        const int c0 = chunk * 32;
+        if (c0 >= p.BN) break;
+        uint32_t v[32];
+        tmem_ld32(t_addr + c0, v);
+        tmem_ld_wait();
+        if (p.stat_acc != nullptr) {
+          float xs[32], xq[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float f = __uint_as_float(v[e]);
+            if (p.relu) f = fmaxf(f, 0.f);
+            f = valid ? __bfloat162float(__float2bfloat16_rn(f)) : 0.f;
+            xs[e] = f;
+            xq[e] = f * f;
+          }
+          if (p.stat_r != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.stat_r + vox * p.Cout + n0 + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u = make_uint4(0, 0, 0, 0);
+              if (valid) u = __ldg(rp + j);
+              const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                xq[8 * j + 2 * e] = xs[8 * j + 2 * e] * __uint_as_float(wds[e] << 16);
+                xq[8 * j + 2 * e + 1] = xs[8 * j + 2 * e + 1] * __uint_as_float(wds[e] & 0xffff0000u);
+              }
+            }
+          }
+          warp_column_sums(xs, lane);
+          warp_column_sums(xq, lane);
+          st_s[chunk] += xs[0];
+          st_q[chunk] += xq[0];
+        }
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(p.y + vox * p.ldy + p.y_coff + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              f[e] = __uint_as_float(v[8 * j + e]);
+              if (p.relu) f[e] = fmaxf(f[e], 0.f);
+            }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]);
+            o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]);
+            o.w = pack_bf16x2(f[6], f[7]);
+            dst[j] = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));   // the leader's MMA issuer owns the pair's TMEM
+    }
+    if (p.stat_acc != nullptr) {
+      // all MMAs that read this CTA's operand ring are complete (tmem_full of the last tile): reuse it as scratch
+      float2* sbuf = reinterpret_cast<float2*>(smem_a);   // [4][Cout]
+#pragma unroll
+      for (int chunk = 0; chunk < 8; ++chunk)
+        if (chunk * 32 < p.BN) sbuf[q * p.Cout + chunk * 32 + lane] = make_float2(st_s[chunk], st_q[chunk]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = q * 32 + lane; c < p.Cout; c += 128) {
+        const float2 a = sbuf[c], b = sbuf[p.Cout + c], cc = sbuf[2 * p.Cout + c], d = sbuf[3 * p.Cout + c];
+        stat_atomic_add(p.stat_acc + 4 * c, (a.x + b.x) + (cc.x + d.x));
+        stat_atomic_add(p.stat_acc + 4 * c + 2, (a.y + b.y) + (cc.y + d.y));
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // the partner's shared memory and TMEM stay alive until both CTAs are done
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
 // out[v, c] = (relu)(sum_s partial[s][v][c]) -> bf16 channel window
 __global__ void __launch_bounds__(256)
 conv_splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long split_stride, long long NV, int C,
@@ -439,6 +667,29 @@ static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpa
     const uint32_t box[2] = {(uint32_t)p.KC, (uint32_t)BN};
     rc = encode_tmap_bf16(&tb, wpack, 2, dims, strides, box, p.KC * 2);
     if (rc) return rc;
+  }
+  // wide layers: CTA pairs (each CTA stages half of the weight tile), see conv3d_igemm2_kernel.  Opt-in (B2_2CTA=1):
+  // bit-identical results, but measured SLOWER than the one-CTA kernel on B200 in round 1
+  // (profiles/r01_bench_kernels_2cta.txt)
+  static const bool no_pairs = getenv("B2_2CTA") == nullptr;
+  const long long m_tiles = p.total_tiles / p.n_tiles_n;
+  if (!no_pairs && p.KC == 64 && BN >= 128 && p.splits == 1 && !y_is_fp32 && m_tiles >= 8) {
+    p.b_bytes = (BN / 2) * p.KC * 2;
+    p.stages = smem_budget / (p.a_bytes + p.b_bytes);
+    if (p.stages > 12) p.stages = 12;
+    p.stages = (p.stages / kProducerPairs) * kProducerPairs;
+    const uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)27 * Cout};
+    const uint64_t strides[1] = {(uint64_t)Cin * 2};
+    const uint32_t box[2] = {(uint32_t)p.KC, (uint32_t)(BN / 2)};
+    rc = encode_tmap_bf16(&tb, wpack, 2, dims, strides, box, p.KC * 2);
+    if (rc) return rc;
+    const size_t smem2 = (size_t)p.stages * (p.a_bytes + p.b_bytes) + 1024 + 512;
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const long long n_work = ((m_tiles + 1) / 2) * p.n_tiles_n;
+    const long long clusters = n_work < num_sms() / 2 ? n_work : num_sms() / 2;
+    B2_LAUNCH(conv3d_igemm2_kernel, (unsigned)(2 * clusters), kThreads, smem2, stream, ta, tb, p);
+    B2_CHECK_CUDA(cudaGetLastError());
+    return B2_OK;
   }
   const size_t smem_bytes = (size_t)p.stages * (p.a_bytes + p.b_bytes) + 1024 + 512;
   if (p.splits > 1) {   // partial tiles: dense fp32 [split][voxel][Cout], no ReLU before the reduction
