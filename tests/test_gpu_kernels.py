@@ -6,6 +6,8 @@ Checker = plain PyTorch fp32 ops on the same (bf16-rounded) inputs.  Tolerances 
   * GroupNorm / resample (bf16 out) ..... rel-L2 <= 4e-3
   * integer pass (fold vote, counters) .. bit-exact
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -334,6 +336,42 @@ def test_conv_first_layer():
     got = ops.conv3d_first_wgrad(x, ops.ActView(to_ndhwc(dy), N, D, H, W, Cout), Cout)
     torch.cuda.synchronize()
     assert rel_l2(got, wp.grad) < 1e-5
+
+
+_PAIR_SNIPPET = r"""
+import sys, torch, torch.nn.functional as F
+sys.path.insert(0, %r)
+import unetsulc_b200
+from unetsulc_b200 import ops
+g = torch.Generator(device="cuda").manual_seed(3)
+worst = 0.0
+for (cin, cout, D, H, W) in [(64, 128, 16, 24, 40), (128, 256, 9, 20, 24), (192, 192, 8, 16, 24)]:
+    x = torch.randn(1, cin, D, H, W, device="cuda", generator=g).to(torch.bfloat16).float()
+    w = (torch.randn(cout, cin, 3, 3, 3, device="cuda", generator=g) / (27 * cin) ** 0.5).to(torch.bfloat16).float()
+    wf, _ = ops.pack_conv_weights(w)
+    xv = ops.ActView(x.permute(0, 2, 3, 4, 1).contiguous().to(torch.bfloat16), 1, D, H, W, cin)
+    y = ops.ActView.alloc(1, D, H, W, cout, "cuda")
+    ops.conv3d_igemm(xv, wf, y, cin, cout, relu=True)
+    ref = F.relu(F.conv3d(x, w, padding=1))
+    got = y.buf.float().permute(0, 4, 1, 2, 3)
+    worst = max(worst, float((got - ref).norm() / ref.norm()))
+torch.cuda.synchronize()
+print("PAIR_REL_L2 %%.3e" %% worst)
+"""
+
+
+def test_conv_cta_pair_kernel_opt_in():
+    """the cta_group::2 variant (B2_2CTA=1, read once per process) against fp32 torch on bf16-rounded inputs, with an
+    odd number of 128-voxel tiles in one case"""
+    import subprocess
+    import sys
+    env = dict(os.environ, B2_2CTA="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _PAIR_SNIPPET % root], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rel = float(r.stdout.split("PAIR_REL_L2")[1].split()[0])
+    assert rel < 3e-3, rel
 
 
 @pytest.mark.parametrize("shape", [(64, 64, 8, 12, 64), (128, 64, 6, 8, 32), (256, 128, 6, 7, 6)])
