@@ -111,6 +111,7 @@ class UNet3D(nn.Module):
         self._layers_cache = None
         # data-parallel hook: called as hook(name_prefix, [grad tensors]) when a level's gradients are ready
         self.grad_ready_hook = None
+        self.pre_head_hook = None
 
     # ------------------------------------------------------------------------------------------ plumbing
     def __deepcopy__(self, memo):
@@ -393,6 +394,8 @@ class UNet3D(nn.Module):
         save = _Saved()
         with torch.no_grad():
             feat = self._trunk_forward(x, save)
+            if self.pre_head_hook is not None:     # CUDA-graph capture: segment boundary before the labels are read
+                self.pre_head_hook()
             fuse13 = x.shape[0] == 1 and any(needs[:42])
             out = ops.head_ce(feat, labels, head.weight.detach(), head.bias.detach(), compute_grad=True,
                               eval_softmax=False, grad_scale=float(loss_scale), want_preds=True,

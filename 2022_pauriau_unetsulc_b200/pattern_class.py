@@ -375,10 +375,14 @@ class UnetPatternSulciLabelling(object):
         with torch.cuda.stream(side):
             if reducer is not None:
                 reducer.segment_cb = cut
+            # the labels are first needed by the head: a cut here lets train_step() overlap their H2D copy with the
+            # trunk forward (replay waits for the copy only after the first segment)
+            self.model.pre_head_hook = lambda: cut(("labels", None))
             begin()
             try:
                 loss = self._eager_step(sx, sy, optimizer, reducer)
             finally:
+                self.model.pre_head_hook = None
                 if reducer is not None:
                     reducer.segment_cb = None
                 g = cur.pop()
@@ -388,11 +392,17 @@ class UnetPatternSulciLabelling(object):
         return segs, loss
 
     def _graphed_step(self, x, y, optimizer, reducer=None):
-        """x, y: device tensors.  Returns the [2] loss tensor (mean, sum) of the step that was just enqueued."""
+        """x, y: device tensors, or HOST tensors (pinned): then x is copied into the graph's static input on the
+        compute stream and the labels on a copy stream, overlapped with the trunk forward.
+        Returns the [2] loss tensor (mean, sum) of the step that was just enqueued."""
         cache = self.__dict__.setdefault("_graphs", {})
         seen = self.__dict__.setdefault("_graph_seen", set())
         key = self._graph_key(x.shape, optimizer) + (id(reducer),)
         ent = cache.get(key)
+        labels_ev = None
+        if ent is None and not x.is_cuda:
+            x = x.to(self.device, non_blocking=True)
+            y = y.to(self.device, non_blocking=True)
         if ent is None:
             if key not in seen:          # first time: a real eager step (creates workspaces / momentum buffers)
                 seen.add(key)
@@ -412,7 +422,17 @@ class UnetPatternSulciLabelling(object):
         else:
             segs, sx, sy, loss = ent
             sx.copy_(x, non_blocking=True)
-            sy.copy_(y, non_blocking=True)
+            if y.is_cuda:
+                sy.copy_(y, non_blocking=True)
+            else:
+                cs = self.__dict__.get("_copy_stream")
+                if cs is None:
+                    cs = self.__dict__["_copy_stream"] = torch.cuda.Stream(device=self.device)
+                cs.wait_stream(torch.cuda.current_stream())   # the previous replay has finished reading sy
+                with torch.cuda.stream(cs):
+                    sy.copy_(y, non_blocking=True)
+                    labels_ev = torch.cuda.Event()
+                    labels_ev.record()
         dbg = os.environ.get("B2_DEBUG_DP") == "1"
         for k, (g, actions) in enumerate(ent[0]):
             if dbg:
@@ -424,6 +444,9 @@ class UnetPatternSulciLabelling(object):
                     torch.cuda.synchronize()
                 if action[0] == "reduce":
                     reducer._launch(action[1])
+                elif action[0] == "labels":
+                    if labels_ev is not None:
+                        torch.cuda.current_stream().wait_event(labels_ev)
                 else:
                     reducer.finish()
         # the replayed SGD changed the fp32 masters behind PyTorch's back: bump their version counters so that eager
@@ -444,6 +467,12 @@ class UnetPatternSulciLabelling(object):
         """One training step from HOST tensors (pinned memory recommended): H2D copy, fused forward + loss +
         backward, gradient all-reduce when data parallel, fused SGD.  Returns the loss as a Python float (one D2H
         read), i.e. what the reference's batch loop does per batch (training.py:198-215)."""
+        if self.use_cuda_graph and not inputs.is_cuda and not labels.is_cuda and labels.dtype == torch.int64:
+            # graph replay: the inputs go straight into the graph's static buffers; the labels (2/3 of the bytes) are
+            # copied on a second stream while the trunk forward runs
+            self.model.train()
+            loss = self._graphed_step(inputs, labels, optimizer, reducer)
+            return float(loss[0].item())
         x = inputs.to(self.device, non_blocking=True)
         y = labels.to(self.device, non_blocking=True)
         loss = self.train_step_device(x, y, optimizer, reducer)
