@@ -39,10 +39,11 @@ SIGNATURES = {
     "b2_upcat_bwd_separable": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _ll, _vp]),
     "b2_upcat_bwd_separable_bstats": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp]),
     "b2_head_workspace_bytes": (_ll, [_i]),
-    "b2_head_ce": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _f, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "b2_head_ce": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _f, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp,
+                        _vp]),
     "b2_head_ce_bstats": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp,
-                               _vp, _vp]),
-    "b2_head_gather": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+                               _vp, _vp, _vp]),
+    "b2_head_gather": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "b2_head_dense_fwd": (_i, [_vp, _i, _ll, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "b2_head_dense_bwd": (_i, [_vp, _vp, _i, _ll, _vp, _i, _i, _vp, _vp, _vp, _vp, _ll, _vp]),
     "b2_sgd_step": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _vp]),

@@ -115,7 +115,8 @@ head_ce_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict_
                const float* __restrict__ W, const float* __restrict__ b, int Cout, const int* __restrict__ count,
                float grad_scale, const float* __restrict__ grad_scale_dev, int compute_grad, int eval_softmax,
                int* __restrict__ preds, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial,
-               long long per_block, const __nv_bfloat16* __restrict__ stat_r, long long* __restrict__ stat_acc) {
+               long long per_block, const __nv_bfloat16* __restrict__ stat_r, long long* __restrict__ stat_acc,
+               const float* __restrict__ x_scale_shift) {
   pdl_prologue();
   constexpr int WS = CIN + 4;        // padded row strides (floats)
   constexpr int DS = kMaxCo + 1;
@@ -139,6 +140,12 @@ head_ce_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict_
   }
   for (int i = threadIdx.x; i < kMaxCo; i += blockDim.x) bs[i] = (i < Cout && b) ? b[i] : 0.f;
   for (int i = threadIdx.x; i < kCeGroup * DS; i += blockDim.x) ds[i] = 0.f;   // columns >= Cout stay zero
+  // x_scale_shift != NULL: x holds the last layer's relu(conv) and its GroupNorm apply y = bf16(r*scale + shift) is
+  // done here, on the gathered rows only — the dense apply pass over the whole volume is skipped
+  __shared__ float s_ss[2 * 64];
+  const bool gn_x = x_scale_shift != nullptr;
+  if (gn_x)
+    for (int i = threadIdx.x; i < 2 * CIN; i += blockDim.x) s_ss[i] = x_scale_shift[i];
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -206,14 +213,23 @@ head_ce_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict_
       for (int i8 = 0; i8 < CIN / 8; ++i8) {
         const f8 t = unpack8(ldg16(x + vv * CIN + i8 * 8));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) xr[i8 * 8 + k] = t.v[k];
+        for (int k = 0; k < 8; ++k) {
+          float v = t.v[k];
+          if (gn_x) v = __bfloat162float(__float2bfloat16_rn(fmaf(v, s_ss[2 * (i8 * 8 + k)], s_ss[2 * (i8 * 8 + k) + 1])));
+          xr[i8 * 8 + k] = v;
+        }
       }
       // this lane's quarter of the row, staged for the dW tile (re-loaded: indexing xr[] by q would spill it)
 #pragma unroll
       for (int i8 = 0; i8 < CPT / 8; ++i8) {
         const f8 t = unpack8(ldg16(x + vv * CIN + q * CPT + i8 * 8));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) xs[j * WS + q * CPT + i8 * 8 + k] = live ? t.v[k] : 0.f;
+        for (int k = 0; k < 8; ++k) {
+          const int c = q * CPT + i8 * 8 + k;
+          float v = t.v[k];
+          if (gn_x) v = __bfloat162float(__float2bfloat16_rn(fmaf(v, s_ss[2 * c], s_ss[2 * c + 1])));
+          xs[j * WS + c] = live ? v : 0.f;
+        }
       }
       float m = -INFINITY;
       int am = 0;
@@ -393,7 +409,8 @@ template <int CIN>
 __global__ void __launch_bounds__(256)
 head_gather_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ index, long long nidx,
                    const float* __restrict__ W, const float* __restrict__ b, int Cout, int softmax,
-                   float* __restrict__ scores /*[nidx][Cout]*/, int* __restrict__ preds) {
+                   float* __restrict__ scores /*[nidx][Cout]*/, int* __restrict__ preds,
+                   const float* __restrict__ x_scale_shift) {
   pdl_prologue();
   extern __shared__ float shm[];
   float* Wt = shm;
@@ -401,10 +418,19 @@ head_gather_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restr
   load_head_weights(W, b, CIN, Cout, Wt, nullptr, bs);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  // deferred GroupNorm apply of the last layer on the gathered rows (see head_ce_kernel): this lane's two channels
+  float4 ss = make_float4(1.f, 0.f, 1.f, 0.f);
+  const bool gn_x = x_scale_shift != nullptr;
+  if (gn_x && lane < CIN / 2) ss = __ldg(reinterpret_cast<const float4*>(x_scale_shift) + lane);
   for (long long k = (long long)blockIdx.x * nwarp + warp; k < nidx; k += (long long)gridDim.x * nwarp) {
     const long long vv = index[k];
     uint32_t xp = 0;
     if (lane < CIN / 2) xp = __ldg(reinterpret_cast<const uint32_t*>(x + vv * CIN) + lane);
+    if (gn_x) {
+      __nv_bfloat162 y2 = __floats2bfloat162_rn(fmaf(__uint_as_float(xp << 16), ss.x, ss.y),
+                                                fmaf(__uint_as_float(xp & 0xffff0000u), ss.z, ss.w));
+      xp = *reinterpret_cast<uint32_t*>(&y2);
+    }
     WarpHead h = warp_logits<CIN>(xp, Wt, bs, lane);
     const int am = warp_argmax(h.l0, h.l1, Cout, lane);
     float o0 = h.l0, o1 = h.l1;
@@ -598,7 +624,8 @@ extern "C" long long b2_head_workspace_bytes(int Cin) {
 static int head_ce_impl(const void* x, const long long* labels, long long NV, const float* W, const float* b, int Cin,
                         int Cout, float grad_scale, const float* grad_scale_dev, int compute_grad, int eval_softmax,
                         int* preds, void* dx, float* dW, float* db, float* loss_out, int* count_out, void* workspace,
-                        long long workspace_bytes, const void* stat_r, long long* stat_acc, cudaStream_t stream) {
+                        long long workspace_bytes, const void* stat_r, long long* stat_acc, const float* x_scale_shift,
+                        cudaStream_t stream) {
   B2_REQUIRE(x && labels && W && loss_out && count_out && workspace, "b2_head_ce: null pointer");
   B2_HEAD_CHECK("b2_head_ce");
   B2_REQUIRE(workspace_bytes >= b2_head_workspace_bytes(Cin), "b2_head_ce: workspace too small");
@@ -622,13 +649,15 @@ static int head_ce_impl(const void* x, const long long* labels, long long NV, co
     B2_LAUNCH(head_ce_kernel<64>, kCeBlocks, kCeThreads, sh, stream, xb, labels, NV, W, b, Cout, count_out, grad_scale,
                                                               grad_scale_dev, compute_grad, eval_softmax, preds, dxb,
                                                               partial, per_block,
-                                                              reinterpret_cast<const __nv_bfloat16*>(stat_r), stat_acc);
+                                                              reinterpret_cast<const __nv_bfloat16*>(stat_r), stat_acc,
+                                                              x_scale_shift);
   } else {
     B2_CHECK_CUDA(cudaFuncSetAttribute(head_ce_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     B2_LAUNCH(head_ce_kernel<32>, kCeBlocks, kCeThreads, sh, stream, xb, labels, NV, W, b, Cout, count_out, grad_scale,
                                                               grad_scale_dev, compute_grad, eval_softmax, preds, dxb,
                                                               partial, per_block,
-                                                              reinterpret_cast<const __nv_bfloat16*>(stat_r), stat_acc);
+                                                              reinterpret_cast<const __nv_bfloat16*>(stat_r), stat_acc,
+                                                              x_scale_shift);
   }
   B2_CHECK_CUDA(cudaGetLastError());
   const int stride = kMaxCo * Cin + kMaxCo + 1;
@@ -642,9 +671,9 @@ static int head_ce_impl(const void* x, const long long* labels, long long NV, co
 extern "C" int b2_head_ce(const void* x, const long long* labels, long long NV, const float* W, const float* b, int Cin,
                           int Cout, float grad_scale, const float* grad_scale_dev, int compute_grad, int eval_softmax,
                           int* preds, void* dx, float* dW, float* db, float* loss_out, int* count_out,
-                          void* workspace, long long workspace_bytes, cudaStream_t stream) {
+                          void* workspace, long long workspace_bytes, const float* x_scale_shift, cudaStream_t stream) {
   return head_ce_impl(x, labels, NV, W, b, Cin, Cout, grad_scale, grad_scale_dev, compute_grad, eval_softmax, preds, dx,
-                      dW, db, loss_out, count_out, workspace, workspace_bytes, nullptr, nullptr, stream);
+                      dW, db, loss_out, count_out, workspace, workspace_bytes, nullptr, nullptr, x_scale_shift, stream);
 }
 
 // Same with compute_grad and dx: dX is the gradient at the last GroupNorm output, so the kernel also accumulates that
@@ -653,14 +682,16 @@ extern "C" int b2_head_ce(const void* x, const long long* labels, long long NV, 
 extern "C" int b2_head_ce_bstats(const void* x, const long long* labels, long long NV, const float* W, const float* b,
                                  int Cin, int Cout, float grad_scale, const float* grad_scale_dev, int* preds,
                                  void* dx, float* dW, float* db, float* loss_out, int* count_out, void* workspace,
-                                 long long workspace_bytes, const void* r, long long* stat_acc, cudaStream_t stream) {
+                                 long long workspace_bytes, const void* r, long long* stat_acc,
+                                 const float* x_scale_shift, cudaStream_t stream) {
   B2_REQUIRE(dx && r && stat_acc, "b2_head_ce_bstats: null pointer");
   return head_ce_impl(x, labels, NV, W, b, Cin, Cout, grad_scale, grad_scale_dev, 1, 0, preds, dx, dW, db, loss_out,
-                      count_out, workspace, workspace_bytes, r, stat_acc, stream);
+                      count_out, workspace, workspace_bytes, r, stat_acc, x_scale_shift, stream);
 }
 
 extern "C" int b2_head_gather(const void* x, const long long* index, long long nidx, const float* W, const float* b,
-                              int Cin, int Cout, int softmax, float* scores, int* preds, cudaStream_t stream) {
+                              int Cin, int Cout, int softmax, float* scores, int* preds, const float* x_scale_shift,
+                              cudaStream_t stream) {
   B2_REQUIRE(x && W && scores, "b2_head_gather: null pointer");
   B2_HEAD_CHECK("b2_head_gather");
   if (nidx <= 0) return B2_OK;
@@ -670,9 +701,11 @@ extern "C" int b2_head_gather(const void* x, const long long* index, long long n
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   auto* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   if (Cin == 64)
-    B2_LAUNCH(head_gather_kernel<64>, blocks, 256, sh, stream, xb, index, nidx, W, b, Cout, softmax, scores, preds);
+    B2_LAUNCH(head_gather_kernel<64>, blocks, 256, sh, stream, xb, index, nidx, W, b, Cout, softmax, scores, preds,
+              x_scale_shift);
   else
-    B2_LAUNCH(head_gather_kernel<32>, blocks, 256, sh, stream, xb, index, nidx, W, b, Cout, softmax, scores, preds);
+    B2_LAUNCH(head_gather_kernel<32>, blocks, 256, sh, stream, xb, index, nidx, W, b, Cout, softmax, scores, preds,
+              x_scale_shift);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }

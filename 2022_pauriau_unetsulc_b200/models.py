@@ -167,8 +167,11 @@ class UNet3D(nn.Module):
         return x.contiguous()
 
     # ------------------------------------------------------------------------------------------ trunk forward
-    def _trunk_forward(self, x, save):
-        """x fp32 [B,1,D,H,W] -> feature ActView [B,D,H,W,f]; fills `save` (a _Saved) when not None."""
+    def _trunk_forward(self, x, save, defer_last_apply=False):
+        """x fp32 [B,1,D,H,W] -> feature ActView [B,D,H,W,f]; fills `save` (a _Saved) when not None.
+        defer_last_apply (batch 1): the GroupNorm apply of the LAST layer is not run over the volume; returns
+        (r, scale_shift) = its relu(conv) and fp32 [1,f,2] coefficients for the head kernels, which apply it to the
+        rows they gather (labelled / skeleton voxels, 2-4 % of the volume)."""
         L = self._layers()
         stale = [l for l in L if l.stale()]
         if stale:   # one launch re-packs every layer whose fp32 master changed (optimiser step, load_state_dict, .to())
@@ -195,7 +198,9 @@ class UNet3D(nn.Module):
                 pool = self.__dict__["_stat_pool"] = ops.StatPool(dev)
             pool.reset()
 
-        def conv_gn(layer, xin, out_view, pooled=None, first=False):
+        deferred = []
+
+        def conv_gn(layer, xin, out_view, pooled=None, first=False, defer=False):
             cin, cout = layer.cin, layer.cout
             d, h, w = (out_view.D, out_view.H, out_view.W)
             r = ActView.alloc(B, d, h, w, cout, dev)
@@ -213,7 +218,10 @@ class UNet3D(nn.Module):
                 wf, _ = layer.packs()
                 ops.conv3d_igemm_auto(xin, wf, r, cin, cout, relu=True)   # split-K when the volume is tiny
                 mr, ss = ops.relu_gn_stats(r, G, layer.norm.eps, gamma, beta)
-            ops.relu_gn_apply(r, ss, out_view, pooled)
+            if defer:
+                deferred.append((r, ss))
+            else:
+                ops.relu_gn_apply(r, ss, out_view, pooled)
             rec.append(dict(x=xin, r=r, mr=mr))
 
         cur = x
@@ -241,13 +249,16 @@ class UNet3D(nn.Module):
             y1 = ActView.alloc(B, d, h, w, L[li].cout, dev)
             conv_gn(L[li], cats[lvl], y1)
             li += 1
-            y2 = ActView.alloc(B, d, h, w, L[li].cout, dev)
-            conv_gn(L[li], y1, y2)
+            last = defer_last_apply and B == 1 and lvl == 0
+            y2 = None if last else ActView.alloc(B, d, h, w, L[li].cout, dev)
+            conv_gn(L[li], y1, y2 if y2 is not None else y1, defer=last)
             li += 1
             cur = y2
         if save is not None:
             save.rec, save.cats, save.dims, save.x = rec, cats, dims, x
             save.skip_c, save.up_c, save.pool = skip_c, up_c, pool
+        if deferred:
+            return deferred[0]
         return cur
 
     # ------------------------------------------------------------------------------------------ trunk backward
@@ -374,10 +385,15 @@ class UNet3D(nn.Module):
         params = self.trunk_parameters() + [head.weight, head.bias]
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in params):
             return _FusedLossFunction.apply(self, x, labels, *params)
-        feat = self._trunk_forward(x, None)
+        feat, xss = self._split_feat(self._trunk_forward(x, None, defer_last_apply=True))
         out = ops.head_ce(feat, labels, head.weight.detach(), head.bias.detach(), compute_grad=False,
-                          eval_softmax=not self.training)
+                          eval_softmax=not self.training, x_scale_shift=xss)
         return out["loss"][0], out["preds"]
+
+    @staticmethod
+    def _split_feat(res):
+        """_trunk_forward result -> (feature ActView, deferred GroupNorm scale_shift or None)"""
+        return res if isinstance(res, tuple) else (res, None)
 
     def forward_backward(self, x, labels, outs=None, loss_scale=1.0):
         """One fused training step without autograd: forward, CrossEntropyLoss(ignore_index=-1), backward.
@@ -393,14 +409,14 @@ class UNet3D(nn.Module):
             outs = [None] * 44
         save = _Saved()
         with torch.no_grad():
-            feat = self._trunk_forward(x, save)
+            feat, xss = self._split_feat(self._trunk_forward(x, save, defer_last_apply=True))
             if self.pre_head_hook is not None:     # CUDA-graph capture: segment boundary before the labels are read
                 self.pre_head_hook()
             fuse13 = x.shape[0] == 1 and any(needs[:42])
             out = ops.head_ce(feat, labels, head.weight.detach(), head.bias.detach(), compute_grad=True,
                               eval_softmax=False, grad_scale=float(loss_scale), want_preds=True,
                               want_dx=any(needs[:42]), dW_out=outs[42], db_out=outs[43],
-                              stat_r=save.rec[13]["r"] if fuse13 else None, pool=save.pool)
+                              stat_r=save.rec[13]["r"] if fuse13 else None, pool=save.pool, x_scale_shift=xss)
             if self.grad_ready_hook is not None:
                 self.grad_ready_hook(14, [t for t, n in zip((out["dW"], out["db"]), needs[42:]) if n])
             grads = (self._trunk_backward(save, out["dx"], needs[:42], outs[:42], out["dx_stats"])
@@ -419,8 +435,9 @@ class UNet3D(nn.Module):
         x = self._check_input(x)
         head = self._head()
         with torch.no_grad():
-            feat = self._trunk_forward(x, None)
-            return ops.head_gather(feat, index, head.weight.detach(), head.bias.detach(), softmax=True)
+            feat, xss = self._split_feat(self._trunk_forward(x, None, defer_last_apply=True))
+            return ops.head_gather(feat, index, head.weight.detach(), head.bias.detach(), softmax=True,
+                                   x_scale_shift=xss)
 
 
 def _needs(ctx_needs, offset):

@@ -364,8 +364,10 @@ def upcat_bwd(dcat_window, Di, Hi, Wi, separable=True, stat_r=None, pool=None):
 
 
 def head_ce(x, labels, W, b, compute_grad, eval_softmax=False, grad_scale=1.0, grad_scale_dev=None,
-            want_preds=True, want_dx=True, dW_out=None, db_out=None, stat_r=None, pool=None):
+            want_preds=True, want_dx=True, dW_out=None, db_out=None, stat_r=None, pool=None, x_scale_shift=None):
     """x: dense ActView [N,D,H,W,Cin]; labels int64 [N,D,H,W] (-1 = ignore).
+    x_scale_shift (batch 1): x is the last layer's relu(conv) and its GroupNorm apply is deferred to this kernel
+    (performed on the labelled rows only).
     Returns dict(loss [2] fp32 (mean, sum), count int32 [1], preds int32 [N,D,H,W] or None, dx ActView, dW, db)."""
     lib = _lib.load()
     _need_cuda(x.buf, labels, W, b)
@@ -390,19 +392,21 @@ def head_ce(x, labels, W, b, compute_grad, eval_softmax=False, grad_scale=1.0, g
         dx_stats = _acc(pool, cin, dev)
         _lib.check(lib.b2_head_ce_bstats(_p(x.buf), _p(labels), NV, _p(Wc), _p(b), cin, cout, float(grad_scale),
                                          _p(grad_scale_dev), _p(preds), _p(dx.buf), _p(dW), _p(db), _p(loss),
-                                         _p(count), _p(ws), ws.numel(), _p(stat_r.buf), _p(dx_stats), _s()),
+                                         _p(count), _p(ws), ws.numel(), _p(stat_r.buf), _p(dx_stats),
+                                         _p(x_scale_shift), _s()),
                    "b2_head_ce_bstats")
     else:
         _lib.check(lib.b2_head_ce(_p(x.buf), _p(labels), NV, _p(Wc), _p(b), cin, cout, float(grad_scale),
                                   _p(grad_scale_dev), int(compute_grad), int(eval_softmax), _p(preds),
                                   _p(dx.buf) if dx is not None else C.c_void_p(0), _p(dW), _p(db), _p(loss), _p(count),
-                                  _p(ws), ws.numel(), _s()), "b2_head_ce")
+                                  _p(ws), ws.numel(), _p(x_scale_shift), _s()), "b2_head_ce")
     _count(3)
     return dict(loss=loss, count=count, preds=preds, dx=dx, dW=dW, db=db, dx_stats=dx_stats)
 
 
-def head_gather(x, index, W, b, softmax=True):
-    """index: int64 linear voxel indices into [N*D*H*W].  Returns (scores fp32 [n, cout], preds int32 [n])."""
+def head_gather(x, index, W, b, softmax=True, x_scale_shift=None):
+    """index: int64 linear voxel indices into [N*D*H*W].  Returns (scores fp32 [n, cout], preds int32 [n]).
+    x_scale_shift: see head_ce."""
     lib = _lib.load()
     dev = x.buf.device
     cout, cin = W.shape[0], W.shape[1]
@@ -411,7 +415,7 @@ def head_gather(x, index, W, b, softmax=True):
     preds = torch.empty(n, dtype=torch.int32, device=dev)
     Wc = W.reshape(cout, cin).contiguous()
     _lib.check(lib.b2_head_gather(_p(x.buf), _p(index), n, _p(Wc), _p(b), cin, cout, int(softmax), _p(scores),
-                                  _p(preds), _s()), "b2_head_gather")
+                                  _p(preds), _p(x_scale_shift), _s()), "b2_head_gather")
     _count(1)
     return scores, preds
 

@@ -118,18 +118,20 @@ long long b2_head_workspace_bytes(int Cin);
 /* loss_out[0] = mean CE over voxels with label >= 0 (NaN if none), loss_out[1] = sum; count_out = #labelled.
  * compute_grad: also d(loss)/d(x, W, b), scaled by grad_scale * (*grad_scale_dev if non-NULL).
  * eval_softmax: loss of Softmax outputs fed to CrossEntropyLoss, the reference's val-phase loss (training.py:189). */
+/* x_scale_shift (fp32 [Cin][2], may be NULL; batch 1): x then holds the last layer's relu(conv) and its GroupNorm apply
+ * y = bf16(r*scale + shift) is done on the gathered rows only, i.e. the dense apply pass over the volume is skipped */
 int b2_head_ce(const void* x, const long long* labels, long long NV, const float* W, const float* b, int Cin,
                int Cout, float grad_scale, const float* grad_scale_dev, int compute_grad, int eval_softmax,
                int* preds, void* dx, float* dW, float* db, float* loss_out, int* count_out, void* workspace,
-               long long workspace_bytes, cudaStream_t stream);
+               long long workspace_bytes, const float* x_scale_shift, cudaStream_t stream);
 /* training form (compute_grad, dx != NULL) that also accumulates the GroupNorm-backward statistics (sum dX, sum dX*r)
  * of the last trunk layer into stat_acc int64 [Cin][4]; r = that layer's saved relu(conv), dense bf16 [NV][Cin]     */
 int b2_head_ce_bstats(const void* x, const long long* labels, long long NV, const float* W, const float* b, int Cin,
                       int Cout, float grad_scale, const float* grad_scale_dev, int* preds, void* dx, float* dW,
                       float* db, float* loss_out, int* count_out, void* workspace, long long workspace_bytes,
-                      const void* r, long long* stat_acc, cudaStream_t stream);
+                      const void* r, long long* stat_acc, const float* x_scale_shift, cudaStream_t stream);
 int b2_head_gather(const void* x, const long long* index, long long nidx, const float* W, const float* b, int Cin,
-                   int Cout, int softmax, float* scores, int* preds, cudaStream_t stream);
+                   int Cout, int softmax, float* scores, int* preds, const float* x_scale_shift, cudaStream_t stream);
 int b2_head_dense_fwd(const void* x, int N, long long V, const float* W, const float* b, int Cin, int Cout,
                       int softmax, float* out, cudaStream_t stream);
 int b2_head_dense_bwd(const float* g, const void* x, int N, long long V, const float* W, int Cin, int Cout, void* dx,

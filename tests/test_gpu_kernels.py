@@ -541,6 +541,31 @@ def test_head_ce_fused(Cout):
     assert abs(float(out2["loss"][0]) - float(ref2)) < 1e-4 * max(1.0, abs(float(ref2)))
 
 
+def test_head_deferred_groupnorm_apply_is_bit_identical():
+    """head kernels fed relu(conv) + GroupNorm scale/shift (apply deferred to the gathered rows) == head kernels fed
+    the tensor the dense apply pass would have written"""
+    ops = _ops()
+    x, Wt, b, labels = _head_inputs(12, N=1, D=9, H=11, W=13)
+    N, Cin, D, H, W = x.shape
+    g = torch.Generator(device="cuda").manual_seed(13)
+    r = ops.ActView(to_ndhwc(x.relu()), N, D, H, W, Cin)
+    gamma = torch.randn(Cin, device="cuda", generator=g) * 0.5 + 1.0
+    beta = torch.randn(Cin, device="cuda", generator=g) * 0.2
+    mr, ss = ops.relu_gn_stats(r, 32, 1e-5, gamma, beta)
+    y = ops.ActView.alloc(N, D, H, W, Cin, "cuda")
+    ops.relu_gn_apply(r, ss, y)
+    a = ops.head_ce(y, labels, Wt, b, compute_grad=True)
+    d = ops.head_ce(r, labels, Wt, b, compute_grad=True, x_scale_shift=ss)
+    idx = torch.nonzero(labels.reshape(-1) >= 0).reshape(-1)
+    sa, pa = ops.head_gather(y, idx, Wt, b, softmax=True)
+    sd, pd = ops.head_gather(r, idx, Wt, b, softmax=True, x_scale_shift=ss)
+    torch.cuda.synchronize()
+    for k in ("loss", "preds", "dW", "db"):
+        assert torch.equal(a[k], d[k]), k
+    assert torch.equal(a["dx"].buf, d["dx"].buf)
+    assert torch.equal(sa, sd) and torch.equal(pa, pd)
+
+
 def test_head_ce_no_labelled_voxel_is_nan():
     ops = _ops()
     x, Wt, b, labels = _head_inputs(10)
