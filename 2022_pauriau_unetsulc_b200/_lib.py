@@ -19,7 +19,7 @@ SIGNATURES = {
     "b2_conv3d_igemm_stats": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "b2_conv3d_igemm_bstats": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "b2_relu_gn_finalize_acc": (_i, [_vp, _ll, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
-    "b2_relu_gn_bwd_acc": (_i, [_vp, _vp, _i, _i, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "b2_relu_gn_bwd_acc": (_i, [_vp, _vp, _i, _i, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp]),
     "b2_conv3d_wgrad_workspace_bytes": (_ll, [_i, _i, _i, _i, _i, _i]),
     "b2_conv3d_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
     "b2_conv3d_first_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
@@ -42,7 +42,7 @@ SIGNATURES = {
     "b2_head_ce": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _f, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp,
                         _vp]),
     "b2_head_ce_bstats": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp,
-                               _vp, _vp, _vp]),
+                               _vp, _vp, _i, _vp]),
     "b2_head_gather": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "b2_head_dense_fwd": (_i, [_vp, _i, _ll, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "b2_head_dense_bwd": (_i, [_vp, _vp, _i, _ll, _vp, _i, _i, _vp, _vp, _vp, _vp, _ll, _vp]),

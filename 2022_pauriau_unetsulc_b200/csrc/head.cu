@@ -625,13 +625,13 @@ static int head_ce_impl(const void* x, const long long* labels, long long NV, co
                         int Cout, float grad_scale, const float* grad_scale_dev, int compute_grad, int eval_softmax,
                         int* preds, void* dx, float* dW, float* db, float* loss_out, int* count_out, void* workspace,
                         long long workspace_bytes, const void* stat_r, long long* stat_acc, const float* x_scale_shift,
-                        cudaStream_t stream) {
+                        int skip_dx_memset, cudaStream_t stream) {
   B2_REQUIRE(x && labels && W && loss_out && count_out && workspace, "b2_head_ce: null pointer");
   B2_HEAD_CHECK("b2_head_ce");
   B2_REQUIRE(workspace_bytes >= b2_head_workspace_bytes(Cin), "b2_head_ce: workspace too small");
   float* partial = reinterpret_cast<float*>(workspace);
   B2_CHECK_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int), stream));
-  if (compute_grad && dx) B2_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)NV * Cin * 2, stream));
+  if (compute_grad && dx && !skip_dx_memset) B2_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)NV * Cin * 2, stream));
   int cblocks = (int)((NV + 255) / 256);
   if (cblocks > num_sms() * 8) cblocks = num_sms() * 8;
   B2_LAUNCH(count_labelled_kernel, cblocks, 256, 0, stream, labels, NV, count_out);
@@ -673,20 +673,22 @@ extern "C" int b2_head_ce(const void* x, const long long* labels, long long NV, 
                           int* preds, void* dx, float* dW, float* db, float* loss_out, int* count_out,
                           void* workspace, long long workspace_bytes, const float* x_scale_shift, cudaStream_t stream) {
   return head_ce_impl(x, labels, NV, W, b, Cin, Cout, grad_scale, grad_scale_dev, compute_grad, eval_softmax, preds, dx,
-                      dW, db, loss_out, count_out, workspace, workspace_bytes, nullptr, nullptr, x_scale_shift, stream);
+                      dW, db, loss_out, count_out, workspace, workspace_bytes, nullptr, nullptr, x_scale_shift, 0, stream);
 }
 
 // Same with compute_grad and dx: dX is the gradient at the last GroupNorm output, so the kernel also accumulates that
 // layer's GroupNorm-backward statistics (sum dX, sum dX*r; r = its saved relu(conv), dense bf16 [NV][Cin]) into
 // stat_acc int64 [Cin][4] (see the statistics accumulators above b2_conv3d_igemm_stats in the header).
+// skip_dx_memset: dX is NOT cleared — only the rows of labelled voxels are written; the consumer
+// (b2_relu_gn_bwd_acc with dy_row_labels = labels) treats every other row as zero without reading it.
 extern "C" int b2_head_ce_bstats(const void* x, const long long* labels, long long NV, const float* W, const float* b,
                                  int Cin, int Cout, float grad_scale, const float* grad_scale_dev, int* preds,
                                  void* dx, float* dW, float* db, float* loss_out, int* count_out, void* workspace,
                                  long long workspace_bytes, const void* r, long long* stat_acc,
-                                 const float* x_scale_shift, cudaStream_t stream) {
+                                 const float* x_scale_shift, int skip_dx_memset, cudaStream_t stream) {
   B2_REQUIRE(dx && r && stat_acc, "b2_head_ce_bstats: null pointer");
   return head_ce_impl(x, labels, NV, W, b, Cin, Cout, grad_scale, grad_scale_dev, 1, 0, preds, dx, dW, db, loss_out,
-                      count_out, workspace, workspace_bytes, r, stat_acc, x_scale_shift, stream);
+                      count_out, workspace, workspace_bytes, r, stat_acc, x_scale_shift, skip_dx_memset, stream);
 }
 
 extern "C" int b2_head_gather(const void* x, const long long* index, long long nidx, const float* W, const float* b,

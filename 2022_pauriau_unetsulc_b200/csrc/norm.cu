@@ -434,8 +434,11 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff, const __nv_bfloat16* __restrict__ r,
                     long long V, int C, const float* __restrict__ mean_rstd, const float* __restrict__ coef,
-                    __nv_bfloat16* __restrict__ dr) {
+                    __nv_bfloat16* __restrict__ dr, const long long* __restrict__ row_labels) {
   pdl_prologue();
+  // row_labels != NULL (gradient produced by the head kernel): dy rows of voxels with label < 0 were never written
+  // and count as zero — they are not read (no memset of dy, 97 % of its rows skipped)
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   const int C8 = C >> 3;
   const int n = blockIdx.y;
   const int oct = threadIdx.x % C8;
@@ -457,8 +460,10 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
   const __nv_bfloat16* gp = dy + ((size_t)n * V) * lddy + dy_coff + oct * 8;
   __nv_bfloat16* op = dr + ((size_t)n * V) * C + oct * 8;
   for (; v + vstride < V; v += 2 * vstride) {
-    const uint4 ux0 = ldg16(rp + v * C), ug0 = ldg16(gp + v * lddy);
-    const uint4 ux1 = ldg16(rp + (v + vstride) * C), ug1 = ldg16(gp + (v + vstride) * lddy);
+    const bool l0 = row_labels == nullptr || __ldg(row_labels + (size_t)n * V + v) >= 0;
+    const bool l1 = row_labels == nullptr || __ldg(row_labels + (size_t)n * V + v + vstride) >= 0;
+    const uint4 ux0 = ldg16(rp + v * C), ug0 = l0 ? ldg16(gp + v * lddy) : zero4;
+    const uint4 ux1 = ldg16(rp + (v + vstride) * C), ug1 = l1 ? ldg16(gp + (v + vstride) * lddy) : zero4;
     const f8 x0 = unpack8(ux0), g0 = unpack8(ug0), x1 = unpack8(ux1), g1 = unpack8(ug1);
     f8 o0, o1;
 #pragma unroll
@@ -472,8 +477,9 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
     stg16(op + (v + vstride) * C, pack8(o1));
   }
   for (; v < V; v += vstride) {
+    const bool l0 = row_labels == nullptr || __ldg(row_labels + (size_t)n * V + v) >= 0;
     const f8 x = unpack8(ldg16(rp + v * C));
-    const f8 g = unpack8(ldg16(gp + v * lddy));
+    const f8 g = unpack8(l0 ? ldg16(gp + v * lddy) : zero4);
     f8 o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -599,7 +605,7 @@ extern "C" int b2_relu_gn_bwd(const void* dy, int lddy, int dy_coff, const void*
   B2_CHECK_CUDA(cudaGetLastError());
   B2_LAUNCH(gn_bwd_apply_kernel, dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
-      mean_rstd, coef, reinterpret_cast<__nv_bfloat16*>(dr));
+      mean_rstd, coef, reinterpret_cast<__nv_bfloat16*>(dr), static_cast<const long long*>(nullptr));
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }
@@ -611,10 +617,12 @@ extern "C" long long b2_relu_gn_bwd_workspace_bytes(int N, int C) {
 // GroupNorm backward (batch 1) when (sum dy, sum dy*r) arrive in the exact accumulators a producer kernel filled
 // (b2_conv3d_igemm_bstats, b2_maxpool3d_bwd_add_bstats, b2_upcat_bwd_separable_bstats, b2_head_ce_bstats): a one-block
 // finalize (coefficients, dgamma, dbeta) + the apply pass; no statistics pass over (dy, r).  workspace >= C*16 bytes.
+// dy_row_labels (int64 [V], may be NULL): dy comes from b2_head_ce_bstats with skip_dx_memset — only the rows of
+// voxels with label >= 0 hold data, all others count as zero and are not read.
 extern "C" int b2_relu_gn_bwd_acc(const long long* stat_acc, const void* dy, int lddy, int dy_coff, const void* r,
                                   long long V, int C, int G, const float* gamma, const float* mean_rstd, void* dr,
                                   float* dgamma, float* dbeta, void* workspace, long long workspace_bytes,
-                                  cudaStream_t stream) {
+                                  const long long* dy_row_labels, cudaStream_t stream) {
   B2_REQUIRE(stat_acc && dy && r && gamma && mean_rstd && dr && workspace, "b2_relu_gn_bwd_acc: null pointer");
   int rc = check_gn_shape("b2_relu_gn_bwd_acc", 1, V, C, G);
   if (rc) return rc;
@@ -627,7 +635,7 @@ extern "C" int b2_relu_gn_bwd_acc(const long long* stat_acc, const void* dy, int
   B2_CHECK_CUDA(cudaGetLastError());
   B2_LAUNCH(gn_bwd_apply_kernel, dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream,
             reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
-            mean_rstd, static_cast<const float*>(coef), reinterpret_cast<__nv_bfloat16*>(dr));
+            mean_rstd, static_cast<const float*>(coef), reinterpret_cast<__nv_bfloat16*>(dr), dy_row_labels);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }

@@ -262,7 +262,7 @@ class UNet3D(nn.Module):
         return cur
 
     # ------------------------------------------------------------------------------------------ trunk backward
-    def _trunk_backward(self, save, dfeat, needs, outs=None, dfeat_stats=None):
+    def _trunk_backward(self, save, dfeat, needs, outs=None, dfeat_stats=None, dfeat_row_labels=None):
         """dfeat: ActView gradient w.r.t. the trunk output.  needs: list of 42 bools (w, gamma, beta per layer).
         outs: optional list of 42 pre-allocated fp32 tensors the gradients are written into (views of the
         data-parallel buckets).  Returns list of 42 grads (None where not needed)."""
@@ -293,7 +293,8 @@ class UNet3D(nn.Module):
             go, bo = (outs[3 * i + 1] if want_gb else None), (outs[3 * i + 2] if want_gb else None)
             if dy_stats is not None:
                 dr, dg, db = ops.relu_gn_bwd_from_stats(dy_stats, dy, rc["r"], G, layer.norm.weight.detach(),
-                                                        rc["mr"], want_gb, go, bo)
+                                                        rc["mr"], want_gb, go, bo,
+                                                        dy_row_labels=dfeat_row_labels if i == 13 else None)
             else:
                 dr, dg, db = ops.relu_gn_bwd(dy, rc["r"], G, layer.norm.weight.detach(), rc["mr"], want_gb, go, bo)
             if needs[3 * i + 1]:
@@ -416,10 +417,12 @@ class UNet3D(nn.Module):
             out = ops.head_ce(feat, labels, head.weight.detach(), head.bias.detach(), compute_grad=True,
                               eval_softmax=False, grad_scale=float(loss_scale), want_preds=True,
                               want_dx=any(needs[:42]), dW_out=outs[42], db_out=outs[43],
-                              stat_r=save.rec[13]["r"] if fuse13 else None, pool=save.pool, x_scale_shift=xss)
+                              stat_r=save.rec[13]["r"] if fuse13 else None, pool=save.pool, x_scale_shift=xss,
+                              sparse_dx=fuse13)
             if self.grad_ready_hook is not None:
                 self.grad_ready_hook(14, [t for t, n in zip((out["dW"], out["db"]), needs[42:]) if n])
-            grads = (self._trunk_backward(save, out["dx"], needs[:42], outs[:42], out["dx_stats"])
+            grads = (self._trunk_backward(save, out["dx"], needs[:42], outs[:42], out["dx_stats"],
+                                          out["dx_row_labels"])
                      if any(needs[:42]) else [None] * 42)
         grads = list(grads) + [out["dW"] if needs[42] else None, out["db"] if needs[43] else None]
         return out["loss"], out["count"], out["preds"], grads

@@ -203,7 +203,7 @@ def conv3d_dgrad_gn_bstats(dy, wd, dx, cin, cout, r, pool=None):
 
 
 def relu_gn_bwd_from_stats(acc, dy, r, groups, gamma, mean_rstd, want_param_grads=True, dgamma_out=None,
-                           dbeta_out=None):
+                           dbeta_out=None, dy_row_labels=None):
     """GroupNorm backward using (sum dy, sum dy*r) accumulated by the kernel that produced `dy` (batch 1): a
     one-block finalize + the apply pass, no statistics pass over (dy, r)."""
     lib = _lib.load()
@@ -215,7 +215,8 @@ def relu_gn_bwd_from_stats(acc, dy, r, groups, gamma, mean_rstd, want_param_grad
         torch.empty(r.C, dtype=torch.float32, device=dev) if want_param_grads else None)
     ws = Workspace.get(r.C * 16, dev, "gncoef")
     _lib.check(lib.b2_relu_gn_bwd_acc(_p(acc), _p(dy.buf), dy.ld, dy.coff, _p(r.buf), r.V, r.C, groups, _p(gamma),
-                                      _p(mean_rstd), _p(dr.buf), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _s()),
+                                      _p(mean_rstd), _p(dr.buf), _p(dgamma), _p(dbeta), _p(ws), ws.numel(),
+                                      _p(dy_row_labels), _s()),
                "b2_relu_gn_bwd_acc")
     _count(2)
     return dr, dgamma, dbeta
@@ -364,10 +365,13 @@ def upcat_bwd(dcat_window, Di, Hi, Wi, separable=True, stat_r=None, pool=None):
 
 
 def head_ce(x, labels, W, b, compute_grad, eval_softmax=False, grad_scale=1.0, grad_scale_dev=None,
-            want_preds=True, want_dx=True, dW_out=None, db_out=None, stat_r=None, pool=None, x_scale_shift=None):
+            want_preds=True, want_dx=True, dW_out=None, db_out=None, stat_r=None, pool=None, x_scale_shift=None,
+            sparse_dx=False):
     """x: dense ActView [N,D,H,W,Cin]; labels int64 [N,D,H,W] (-1 = ignore).
     x_scale_shift (batch 1): x is the last layer's relu(conv) and its GroupNorm apply is deferred to this kernel
     (performed on the labelled rows only).
+    sparse_dx (with stat_r): dx is not cleared, only the rows of labelled voxels are written; hand `labels` to
+    relu_gn_bwd_from_stats(dy_row_labels=...) so that the other rows read as zero.
     Returns dict(loss [2] fp32 (mean, sum), count int32 [1], preds int32 [N,D,H,W] or None, dx ActView, dW, db)."""
     lib = _lib.load()
     _need_cuda(x.buf, labels, W, b)
@@ -393,7 +397,7 @@ def head_ce(x, labels, W, b, compute_grad, eval_softmax=False, grad_scale=1.0, g
         _lib.check(lib.b2_head_ce_bstats(_p(x.buf), _p(labels), NV, _p(Wc), _p(b), cin, cout, float(grad_scale),
                                          _p(grad_scale_dev), _p(preds), _p(dx.buf), _p(dW), _p(db), _p(loss),
                                          _p(count), _p(ws), ws.numel(), _p(stat_r.buf), _p(dx_stats),
-                                         _p(x_scale_shift), _s()),
+                                         _p(x_scale_shift), int(bool(sparse_dx)), _s()),
                    "b2_head_ce_bstats")
     else:
         _lib.check(lib.b2_head_ce(_p(x.buf), _p(labels), NV, _p(Wc), _p(b), cin, cout, float(grad_scale),
@@ -401,7 +405,8 @@ def head_ce(x, labels, W, b, compute_grad, eval_softmax=False, grad_scale=1.0, g
                                   _p(dx.buf) if dx is not None else C.c_void_p(0), _p(dW), _p(db), _p(loss), _p(count),
                                   _p(ws), ws.numel(), _p(x_scale_shift), _s()), "b2_head_ce")
     _count(3)
-    return dict(loss=loss, count=count, preds=preds, dx=dx, dW=dW, db=db, dx_stats=dx_stats)
+    return dict(loss=loss, count=count, preds=preds, dx=dx, dW=dW, db=db, dx_stats=dx_stats,
+                dx_row_labels=labels if (sparse_dx and dx_stats is not None) else None)
 
 
 def head_gather(x, index, W, b, softmax=True, x_scale_shift=None):

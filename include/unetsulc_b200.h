@@ -59,7 +59,8 @@ int b2_relu_gn_finalize_acc(const long long* stat_acc, long long V, int C, int G
                             const float* beta, float* mean_rstd, float* scale_shift, cudaStream_t stream);
 int b2_relu_gn_bwd_acc(const long long* stat_acc, const void* dy, int lddy, int dy_coff, const void* r, long long V,
                        int C, int G, const float* gamma, const float* mean_rstd, void* dr, float* dgamma,
-                       float* dbeta, void* workspace, long long workspace_bytes, cudaStream_t stream);
+                       float* dbeta, void* workspace, long long workspace_bytes, const long long* dy_row_labels,
+                       cudaStream_t stream);   /* dy_row_labels (may be NULL): see b2_head_ce_bstats */
 
 /* dW[co][ci][3][3][3] (fp32, PyTorch layout) = sum_v dY[v,co] * X[v+off,ci]                                      */
 long long b2_conv3d_wgrad_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout);
@@ -129,7 +130,9 @@ int b2_head_ce(const void* x, const long long* labels, long long NV, const float
 int b2_head_ce_bstats(const void* x, const long long* labels, long long NV, const float* W, const float* b, int Cin,
                       int Cout, float grad_scale, const float* grad_scale_dev, int* preds, void* dx, float* dW,
                       float* db, float* loss_out, int* count_out, void* workspace, long long workspace_bytes,
-                      const void* r, long long* stat_acc, const float* x_scale_shift, cudaStream_t stream);
+                      const void* r, long long* stat_acc, const float* x_scale_shift, int skip_dx_memset,
+                      cudaStream_t stream);   /* skip_dx_memset: only the labelled rows of dx are written; pass the
+                                                 labels to b2_relu_gn_bwd_acc (dy_row_labels) so the rest reads as 0 */
 int b2_head_gather(const void* x, const long long* index, long long nidx, const float* W, const float* b, int Cin,
                    int Cout, int softmax, float* scores, int* preds, const float* x_scale_shift, cudaStream_t stream);
 int b2_head_dense_fwd(const void* x, int N, long long V, const float* W, const float* b, int Cin, int Cout,
