@@ -49,6 +49,8 @@ SIGNATURES = {
     "b2_sgd_step": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _vp]),
     "b2_pack_conv_weights": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "b2_pack_conv_weights_multi": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "b2_scatter_volume_workspace_bytes": (_ll, [_i, _i, _i]),
+    "b2_scatter_volume": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _vp]),
     "b2_fold_vote_workspace_bytes": (_ll, [_ll, _i, _i, _i]),
     "b2_fold_vote": (_i, [_vp, _vp, _ll, _i, _i, _vp, _i, _vp, _vp, _ll, _vp]),
     "b2_esi_counts": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),

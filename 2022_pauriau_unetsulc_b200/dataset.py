@@ -62,7 +62,11 @@ def extract_data(graph, flip=False):
 
 class SulciDataset(Dataset):
     def __init__(self, gfile_list, dict_sulci, train=True, translation_file=None, dict_bck2={}, dict_names={},
-                 img_size=None):
+                 img_size=None, device=None):
+        """device (not in the reference): a CUDA device -> the dense volumes are built there by b2_scatter_volume
+        from the (augmented) point list; the random draws and the integer point list stay on the host, so a seeded
+        run visits exactly the same volumes."""
+        self.device = device
         self.gfile_list = gfile_list
         self.dict_sulci = dict_sulci
         if 'background' not in self.dict_sulci:
@@ -106,6 +110,10 @@ class SulciDataset(Dataset):
             pts = self.transform(pts)
         pts = np.array(pts, dtype=int)
         size = (np.max(pts, axis=0) + 1) if self.img_size is None else self.img_size
+        if self.device is not None and torch.device(self.device).type == "cuda":
+            from . import ops
+            return ops.scatter_volume(pts, [self.dict_sulci[n] for n in names], size, self.device,
+                                      background=self.dict_sulci['background'])
         ix = tuple(torch.as_tensor(pts[:, k], dtype=torch.long) for k in range(3))
         vol = torch.zeros(1, int(size[0]), int(size[1]), int(size[2]), dtype=torch.float)
         vol[0][ix] = 1

@@ -510,6 +510,29 @@ def pack_conv_weights_multi(ws):
     return outs
 
 
+def scatter_volume(points, point_labels, size, device, background=-1):
+    """points: int array-like [n, 3] (host), point_labels: int [n] (host), size: (D, H, W).
+    Returns (x fp32 [1, D, H, W], labels int64 [D, H, W]) on `device`, identical to the reference's CPU index_put
+    (last duplicate wins); 16 bytes per point are copied to the device instead of 12 bytes per voxel."""
+    import numpy as np
+    lib = _lib.load()
+    D, H, W = int(size[0]), int(size[1]), int(size[2])
+    pts = np.ascontiguousarray(np.asarray(points, dtype=np.int32).reshape(-1, 3))
+    lab = np.ascontiguousarray(np.asarray(point_labels, dtype=np.int32).reshape(-1))
+    n = pts.shape[0]
+    if n and (pts.min() < 0 or (pts.max(axis=0) >= np.array([D, H, W])).any()):
+        raise IndexError("scatter_volume: point outside the %dx%dx%d volume" % (D, H, W))
+    x = torch.empty((1, D, H, W), dtype=torch.float32, device=device)
+    labels = torch.empty((D, H, W), dtype=torch.int64, device=device)
+    ws = Workspace.get(lib.b2_scatter_volume_workspace_bytes(D, H, W), x.device, "scatter")
+    packed = torch.from_numpy(np.concatenate([pts.reshape(-1), lab])).to(device, non_blocking=True) if n else None
+    _lib.check(lib.b2_scatter_volume(_p(packed), C.c_void_p(packed.data_ptr() + 12 * n) if n else C.c_void_p(0), n,
+                                     D, H, W, _p(x), _p(labels), int(background), _p(ws), ws.numel(), _s()),
+               "b2_scatter_volume")
+    _count(3 if n else 1)
+    return x, labels
+
+
 def fold_vote(scores, fold_dense, n_folds, thresholds):
     """scores fp32 [n, C] cuda; fold_dense int32 [n] in [0, n_folds); thresholds: list of ints.
     Returns int32 [T, n]."""

@@ -273,8 +273,10 @@ class UnetPatternSulciLabelling(object):
         import random
 
         def make(files, train, img_size=None):
+            # volumes are built on the device from the point list (b2_scatter_volume)
             return SulciDataset(files, self.dict_sulci, train=train, translation_file=self.trfile,
-                                dict_bck2=self.dict_bck2, dict_names=self.dict_names, img_size=img_size)
+                                dict_bck2=self.dict_bck2, dict_names=self.dict_names, img_size=img_size,
+                                device=self.device if self.device.type == "cuda" else None)
 
         def loader(ds):
             return torch.utils.data.DataLoader(ds, batch_size=batch_size, shuffle=False, num_workers=0)

@@ -149,6 +149,15 @@ int b2_pack_conv_weights(const float* w, void* wf, void* wd, int Cout, int Cin, 
 int b2_pack_conv_weights_multi(const float* const* w, void* const* wf, void* const* wd, const int* cout,
                                const int* cin, int count, cudaStream_t stream);
 
+/* ---- SulciDataset.__getitem__ on the device (reference dataset.py:66-88) ------------------------
+ * point list (int32 [n][3] voxel coordinates + int32 [n] label ids) -> x fp32 [D][H][W] (1 at the points) and labels
+ * int64 [D][H][W] (background elsewhere); duplicate points: the LAST one of the list wins, like the reference's CPU
+ * index_put — bit-identical volumes.                                                                                 */
+long long b2_scatter_volume_workspace_bytes(int D, int H, int W);
+int b2_scatter_volume(const int* pts, const int* point_labels, int n, int D, int H, int W, float* x,
+                      long long* labels, long long background, void* workspace, long long workspace_bytes,
+                      cudaStream_t stream);
+
 /* ---- post-inference integer pass: cutting(yscores, vert_notcut, bck2, threshold) (pattern_class.py:230) ---------
  * fold: dense ids in [0,F); thresholds: device int32 [T]; out: int32 [T][n].                                      */
 long long b2_fold_vote_workspace_bytes(long long n, int C, int F, int T);

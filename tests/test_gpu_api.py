@@ -130,6 +130,43 @@ def test_transfer_learning_two_phases(tmp_path):
     assert tl.results['epoch_loss_train'][0][-1] < tl.results['epoch_loss_train'][0][0]
 
 
+def test_sulci_dataset_on_device_matches_reference_volumes():
+    """SulciDataset(device='cuda') (b2_scatter_volume) == the reference's SulciDataset volumes (golden fixtures made by
+    the reference's own dataset.py), incl. the seeded rotation augmentation; duplicate points: last one wins."""
+    from unetsulc_b200 import dataset as ds_mod, ops
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dataset_cases.npz"))
+    bck2, names, sslist = harness.synthetic_cohort(n_subjects=2, shape=(12, 14, 10), n_classes=5, seed=3)
+    dict_sulci = {s: i for i, s in enumerate(sslist)}
+    files = sorted(bck2)
+    for train in (False, True):
+        random.seed(11); np.random.seed(11)
+        d = ds_mod.SulciDataset(files, dict(dict_sulci), train=train, dict_bck2=bck2, dict_names=names, device="cuda")
+        for i in range(len(files)):
+            for rep in range(2 if train else 1):
+                x, y = d[i]
+                assert x.is_cuda and x.dtype == torch.float32 and y.dtype == torch.int64
+                assert np.array_equal(x.cpu().numpy().astype(np.uint8), g["x_train%d_s%d_r%d" % (train, i, rep)])
+                assert np.array_equal(y.cpu().numpy().astype(np.int16), g["y_train%d_s%d_r%d" % (train, i, rep)])
+    d = ds_mod.SulciDataset(files, dict(dict_sulci), train=False, dict_bck2=bck2, dict_names=names,
+                            img_size=[16, 16, 16], device="cuda")
+    x, y = d[0]
+    assert np.array_equal(x.cpu().numpy().astype(np.uint8), g["x_fixed"])
+    assert np.array_equal(y.cpu().numpy().astype(np.int16), g["y_fixed"])
+    # duplicates: the reference's CPU index_put keeps the LAST point of the list
+    rng = np.random.RandomState(5)
+    pts = rng.randint(0, 6, size=(400, 3))
+    lab = rng.randint(0, 9, size=400)
+    xg, yg = ops.scatter_volume(pts, lab, (6, 6, 6), "cuda", background=-1)
+    yr = torch.full((6, 6, 6), -1, dtype=torch.long)
+    ix = tuple(torch.as_tensor(pts[:, k], dtype=torch.long) for k in range(3))
+    yr[ix] = torch.as_tensor(lab, dtype=torch.long)
+    xr = torch.zeros(1, 6, 6, 6)
+    xr[0][ix] = 1
+    assert torch.equal(yg.cpu(), yr) and torch.equal(xg.cpu(), xr)
+    with pytest.raises(IndexError):
+        ops.scatter_volume([[0, 0, 7]], [1], (6, 6, 6), "cuda")
+
+
 @pytest.mark.parametrize("segmented", [False, True])
 def test_cuda_graph_step_matches_eager_step(tmp_path, segmented):
     """train_step with use_cuda_graph replays the same kernels: identical losses and weights, step after step.
