@@ -137,13 +137,41 @@ class UNet3D(nn.Module):
         return self._layers_cache
 
     def _head(self):
+        """final_conv as a list of 1x1x1 nn.Conv3d: one module, or the reference's chain for num_conv > 1
+        (nn.Sequential of 1x1x1 convs WITHOUT activations, pattern_class.py:357-363)."""
         fc = self.final_conv
-        if isinstance(fc, nn.Sequential):
-            raise RuntimeError("unetsulc_b200.UNet3D: final_conv = nn.Sequential (num_conv > 1) is not supported by "
-                               "the B200 head kernels; use num_conv = 1")
-        if not isinstance(fc, nn.Conv3d) or tuple(fc.kernel_size) != (1, 1, 1):
-            raise RuntimeError("unetsulc_b200.UNet3D: final_conv must be a 1x1x1 nn.Conv3d")
-        return fc
+        mods = list(fc) if isinstance(fc, nn.Sequential) else [fc]
+        if not mods:
+            raise RuntimeError("unetsulc_b200.UNet3D: empty final_conv")
+        for m in mods:
+            if not isinstance(m, nn.Conv3d) or tuple(m.kernel_size) != (1, 1, 1):
+                raise RuntimeError("unetsulc_b200.UNet3D: final_conv must be a 1x1x1 nn.Conv3d or an nn.Sequential "
+                                   "of them (got %r)" % (m,))
+        return mods
+
+    def head_parameters(self):
+        """[w0, b0, w1, b1, ...] of the head chain (bias-free convs are not supported by the head kernels)."""
+        ps = []
+        for m in self._head():
+            if m.bias is None:
+                raise RuntimeError("unetsulc_b200.UNet3D: final_conv without bias is unsupported")
+            ps += [m.weight, m.bias]
+        return ps
+
+    def _head_effective(self):
+        """The head as ONE affine map (W [Cout, Cin, 1, 1, 1], b [Cout]).  A chain of 1x1x1 convs without
+        activations composes exactly: W = Wn ... W1, b = Wn(...(W2 b1 + b2)...) + bn.  Built with differentiable torch
+        ops on the (<= 64 x 64) matrices: autograd carries dW / db of the fused head kernels back to every link."""
+        mods = self._head()
+        if len(mods) == 1:
+            return mods[0].weight, mods[0].bias
+        W = mods[0].weight.reshape(mods[0].out_channels, mods[0].in_channels)
+        b = mods[0].bias
+        for m in mods[1:]:
+            Wk = m.weight.reshape(m.out_channels, m.in_channels)
+            W = Wk @ W
+            b = Wk @ b + m.bias
+        return W.reshape(W.shape[0], W.shape[1], 1, 1, 1), b
 
     def trunk_parameters(self):
         """Parameters in the order the autograd functions take them (14 x (w, gamma, beta))."""
@@ -369,12 +397,12 @@ class UNet3D(nn.Module):
     def forward(self, x):
         """Dense nn.Module surface: logits [B,C,D,H,W] fp32 in train(), Softmax(dim=1) in eval()."""
         x = self._check_input(x)
-        head = self._head()
-        params = self.trunk_parameters() + [head.weight, head.bias]
+        hw, hb = self._head_effective()     # differentiable w.r.t. every link of a num_conv > 1 chain
+        params = self.trunk_parameters() + [hw, hb]
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _DenseFunction.apply(self, x, not self.training, *params)
         feat = self._trunk_forward(x, None)
-        return ops.head_dense_fwd(feat, head.weight.detach(), head.bias.detach(), softmax=not self.training)
+        return ops.head_dense_fwd(feat, hw.detach(), hb.detach(), softmax=not self.training)
 
     def loss_and_preds(self, x, labels):
         """Fused head: CrossEntropyLoss(ignore_index=-1)(model(x), labels) and torch.max(model(x), 1)[1] at the
@@ -382,12 +410,12 @@ class UNet3D(nn.Module):
         val-phase loss (CE applied to the Softmax outputs, training.py:189,205-208).
         Returns (loss: 0-dim fp32 tensor wired into autograd, preds: int32 [B,D,H,W], -1 where unlabelled)."""
         x = self._check_input(x)
-        head = self._head()
-        params = self.trunk_parameters() + [head.weight, head.bias]
+        hw, hb = self._head_effective()
+        params = self.trunk_parameters() + [hw, hb]
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in params):
             return _FusedLossFunction.apply(self, x, labels, *params)
         feat, xss = self._split_feat(self._trunk_forward(x, None, defer_last_apply=True))
-        out = ops.head_ce(feat, labels, head.weight.detach(), head.bias.detach(), compute_grad=False,
+        out = ops.head_ce(feat, labels, hw.detach(), hb.detach(), compute_grad=False,
                           eval_softmax=not self.training, x_scale_shift=xss)
         return out["loss"][0], out["preds"]
 
@@ -403,44 +431,63 @@ class UNet3D(nn.Module):
         Returns (loss_and_count: fp32 [2] = (mean, sum) device tensor, count int32 [1], preds int32 [B,D,H,W],
         grads: list of 44 tensors or None)."""
         x = self._check_input(x)
-        head = self._head()
-        params = list(self.trunk_parameters()) + [head.weight, head.bias]
+        hp = self.head_parameters()
+        chain = len(hp) > 2
+        params = list(self.trunk_parameters()) + hp
         needs = [bool(p.requires_grad) for p in params]
         if outs is None:
-            outs = [None] * 44
+            outs = [None] * len(params)
+        if chain:   # num_conv > 1: the kernels see the composed map; autograd on the small matrices splits dW / db
+            with torch.enable_grad():
+                hw, hb = self._head_effective()
+        else:
+            hw, hb = hp
         save = _Saved()
         with torch.no_grad():
             feat, xss = self._split_feat(self._trunk_forward(x, save, defer_last_apply=True))
             if self.pre_head_hook is not None:     # CUDA-graph capture: segment boundary before the labels are read
                 self.pre_head_hook()
             fuse13 = x.shape[0] == 1 and any(needs[:42])
-            out = ops.head_ce(feat, labels, head.weight.detach(), head.bias.detach(), compute_grad=True,
+            out = ops.head_ce(feat, labels, hw.detach(), hb.detach(), compute_grad=True,
                               eval_softmax=False, grad_scale=float(loss_scale), want_preds=True,
-                              want_dx=any(needs[:42]), dW_out=outs[42], db_out=outs[43],
+                              want_dx=any(needs[:42]), dW_out=None if chain else outs[42],
+                              db_out=None if chain else outs[43],
                               stat_r=save.rec[13]["r"] if fuse13 else None, pool=save.pool, x_scale_shift=xss,
                               sparse_dx=fuse13)
+        if chain:
+            head_grads = [None] * len(hp)
+            live = [i for i, p in enumerate(hp) if p.requires_grad]
+            if live:
+                gs = torch.autograd.grad([hw, hb], [hp[i] for i in live], [out["dW"].view_as(hw), out["db"]],
+                                         allow_unused=True)
+                for i, g in zip(live, gs):
+                    g = torch.zeros_like(hp[i]) if g is None else g
+                    if outs[42 + i] is not None:
+                        outs[42 + i].copy_(g)
+                        g = outs[42 + i]
+                    head_grads[i] = g
+        else:
+            head_grads = [out["dW"] if needs[42] else None, out["db"] if needs[43] else None]
+        with torch.no_grad():
             if self.grad_ready_hook is not None:
-                self.grad_ready_hook(14, [t for t, n in zip((out["dW"], out["db"]), needs[42:]) if n])
+                self.grad_ready_hook(14, [g for g in head_grads if g is not None])
             grads = (self._trunk_backward(save, out["dx"], needs[:42], outs[:42], out["dx_stats"],
                                           out["dx_row_labels"])
                      if any(needs[:42]) else [None] * 42)
-        grads = list(grads) + [out["dW"] if needs[42] else None, out["db"] if needs[43] else None]
-        return out["loss"], out["count"], out["preds"], grads
+        return out["loss"], out["count"], out["preds"], list(grads) + head_grads
 
     def ordered_parameters(self):
-        """The 44 parameters in the order forward_backward() reports gradients."""
-        head = self._head()
-        return list(self.trunk_parameters()) + [head.weight, head.bias]
+        """The parameters in the order forward_backward() reports gradients (42 trunk + 2 per head conv)."""
+        return list(self.trunk_parameters()) + self.head_parameters()
 
     def scores_at(self, x, index):
         """Eval forward + Softmax scores gathered at linear voxel indices (labeling(), pattern_class.py:266-277).
         Returns (scores fp32 [n, C], preds int32 [n])."""
         x = self._check_input(x)
-        head = self._head()
         with torch.no_grad():
+            hw, hb = self._head_effective()
             feat, xss = self._split_feat(self._trunk_forward(x, None, defer_last_apply=True))
-            return ops.head_gather(feat, index, head.weight.detach(), head.bias.detach(), softmax=True,
-                                   x_scale_shift=xss)
+            return ops.head_gather(feat, index, hw, hb, softmax=True, x_scale_shift=xss)
 
 
 def _needs(ctx_needs, offset):
@@ -452,9 +499,9 @@ class _DenseFunction(torch.autograd.Function):
     def forward(ctx, model, x, softmax, *params):
         save = _Saved()
         feat = model._trunk_forward(x, save)
-        head = model._head()
-        out = ops.head_dense_fwd(feat, head.weight.detach(), head.bias.detach(), softmax=softmax)
-        ctx.model, ctx.save_, ctx.feat, ctx.softmax = model, save, feat, softmax
+        hw, hb = params[42].detach(), params[43].detach()
+        out = ops.head_dense_fwd(feat, hw, hb, softmax=softmax)
+        ctx.model, ctx.save_, ctx.feat, ctx.softmax, ctx.hw = model, save, feat, softmax, hw
         if softmax:
             ctx.save_for_backward(out)
         return out
@@ -462,12 +509,11 @@ class _DenseFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         model, save, feat = ctx.model, ctx.save_, ctx.feat
-        head = model._head()
         g = g.contiguous().float()
         if ctx.softmax:  # d softmax: g_logit = p * (g - sum_c g*p)
             (p,) = ctx.saved_tensors
             g = p * (g - (g * p).sum(dim=1, keepdim=True))
-        dfeat, dW, db = ops.head_dense_bwd(g, feat, head.weight.detach())
+        dfeat, dW, db = ops.head_dense_bwd(g, feat, ctx.hw)
         needs = list(ctx.needs_input_grad[3:3 + 42])
         grads = model._trunk_backward(save, dfeat, needs)
         nh = ctx.needs_input_grad[45:47]
@@ -481,21 +527,19 @@ class _FusedLossFunction(torch.autograd.Function):
     def forward(ctx, model, x, labels, *params):
         save = _Saved()
         feat = model._trunk_forward(x, save)
-        head = model._head()
-        out = ops.head_ce(feat, labels, head.weight.detach(), head.bias.detach(), compute_grad=False,
-                          eval_softmax=False)
-        ctx.model, ctx.save_, ctx.feat, ctx.labels = model, save, feat, labels
+        hw, hb = params[42].detach(), params[43].detach()
+        out = ops.head_ce(feat, labels, hw, hb, compute_grad=False, eval_softmax=False)
+        ctx.model, ctx.save_, ctx.feat, ctx.labels, ctx.hw, ctx.hb = model, save, feat, labels, hw, hb
         ctx.mark_non_differentiable(out["preds"])
         return out["loss"][0].clone(), out["preds"]
 
     @staticmethod
     def backward(ctx, gloss, _gpreds):
         model, save, feat = ctx.model, ctx.save_, ctx.feat
-        head = model._head()
         gl = gloss.detach().float().reshape(1).contiguous()
         needs = list(ctx.needs_input_grad[3:3 + 42])
         nh = ctx.needs_input_grad[45:47]
-        out = ops.head_ce(feat, ctx.labels, head.weight.detach(), head.bias.detach(), compute_grad=True,
+        out = ops.head_ce(feat, ctx.labels, ctx.hw, ctx.hb, compute_grad=True,
                           eval_softmax=False, grad_scale=1.0, grad_scale_dev=gl, want_preds=False,
                           want_dx=any(needs))
         if model.grad_ready_hook is not None:

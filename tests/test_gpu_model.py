@@ -251,3 +251,45 @@ def test_odd_volume_and_batch2():
         a, b = ours(x), ref(x)
     print("odd volume batch2 rel-L2 %.3e" % rel_l2(a, b))
     assert rel_l2(a, b) < 3e-2
+
+
+def test_num_conv_chain_head_matches_sequential_reference():
+    """final_conv = nn.Sequential of 1x1x1 convs (reference pattern_class.py:357-363, num_conv > 1): the B200 head
+    kernels run the composed affine map, autograd on the small matrices splits dW / db over the links.  Checked against
+    the oracle carrying the SAME chain: logits, loss, and the gradient of every link (fused step and autograd
+    surface)."""
+    from unetsulc_b200.pattern_class import make_head
+    ref, ours = _pair(n_classes=56)
+    torch.manual_seed(7)
+    head = make_head(64, 56, 3).cuda()
+    ref.final_conv = head
+    ours.final_conv = copy.deepcopy(head)
+    assert [tuple(p.shape) for p in ours.head_parameters()] == [tuple(p.shape) for p in ref.final_conv.parameters()]
+    x, labels = _data()
+    ref.train(); ours.train()
+    lr_ = ref(x)
+    loss_r = F.cross_entropy(lr_, labels, ignore_index=-1)
+    loss_r.backward()
+    with torch.no_grad():
+        lo = ours(x)
+    assert rel_l2(lo, lr_.detach()) < 3e-2
+    loss, _, _, grads = ours.forward_backward(x, labels)
+    assert len(grads) == 42 + 6 and len(ours.ordered_parameters()) == 48
+    assert abs(float(loss[0]) - float(loss_r)) < 1e-2 * abs(float(loss_r))
+    ref_head = list(ref.final_conv.parameters())
+    for g, p in zip(grads[42:], ref_head):
+        assert g.shape == p.grad.shape
+        assert cosine(g, p.grad) > 0.97 and 0.8 < float(g.norm() / p.grad.norm()) < 1.25
+    # autograd surface: same gradients land in .grad of every link
+    lo2, _ = ours.loss_and_preds(x, labels)
+    lo2.backward()
+    for g, p in zip(grads[42:], ours.head_parameters()):
+        assert rel_l2(p.grad, g) < 1e-4
+    # one fused optimiser step over all 48 tensors
+    from unetsulc_b200.optim import SGD
+    opt = SGD(ours.ordered_parameters(), lr=1e-2, momentum=0.9)
+    before = [p.detach().clone() for p in ours.head_parameters()]
+    opt.step(grads=grads)
+    torch.cuda.synchronize()
+    for b, p, g in zip(before, ours.head_parameters(), grads[42:]):
+        assert torch.allclose(p.detach(), b - 1e-2 * g, rtol=1e-5, atol=1e-7)

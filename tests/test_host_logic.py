@@ -178,3 +178,28 @@ def test_reference_host_code_runs_unmodified_on_the_boundary(tmp_path):
                            rtol=2e-3, atol=1e-4), k
     assert method.results['divide_lr_epoch'] == golden['divide_lr_epoch']
     assert method.results['best_epoch'] == golden['best_epoch']
+
+
+def test_num_conv_chain_head_composes_exactly():
+    """A chain of 1x1x1 convs without activations (reference pattern_class.py:357-363) is one affine map: the composed
+    (W, b) the head kernels use reproduces the sequential application, and autograd reaches every link."""
+    import torch.nn.functional as F
+    from unetsulc_b200.pattern_class import make_head
+    torch.manual_seed(3)
+    m = unetsulc_b200.UNet3D(1, 56)
+    m.final_conv = make_head(64, 56, 3)
+    assert [c.out_channels for c in m.final_conv] == [61, 59, 56]
+    hw, hb = m._head_effective()
+    assert tuple(hw.shape) == (56, 64, 1, 1, 1) and tuple(hb.shape) == (56,)
+    x = torch.randn(2, 64, 3, 4, 5)
+    want = m.final_conv(x)
+    got = F.conv3d(x, hw, hb)
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5)
+    got.sum().backward()
+    assert all(p.grad is not None and p.grad.abs().sum() > 0 for p in m.head_parameters())
+    assert len(m.ordered_parameters()) == 42 + 6
+    # state_dict round trip with the chain (keys final_conv.0.weight ...)
+    m2 = unetsulc_b200.UNet3D(1, 56)
+    m2.final_conv = make_head(64, 56, 3)
+    m2.load_state_dict(m.state_dict())
+    assert "final_conv.2.bias" in m.state_dict()
