@@ -482,6 +482,36 @@ def test_maxpool_bwd_add(D, H, W):
     assert rel_l2(from_view(out), ref) < 4e-3
 
 
+@pytest.mark.parametrize("C,D,H,W", [(64, 8, 10, 12), (128, 7, 9, 11), (256, 6, 6, 8), (40, 6, 8, 10)])
+def test_maxpool_bwd_add_with_groupnorm_backward_statistics(C, D, H, W):
+    """pooling adjoint that also accumulates (sum out, sum out*r) of the tensor it produces: same output as the plain
+    entry point, accumulators == fp64 sums of the stored tensor (C = 40: plain entry point only)"""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(17)
+    y = bf16_round(torch.randn(1, C, D, H, W, device="cuda", generator=g)).requires_grad_(True)
+    dskip = bf16_round(torch.randn(1, C, D, H, W, device="cuda", generator=g))
+    dpool = bf16_round(torch.randn(1, C, D // 2, H // 2, W // 2, device="cuda", generator=g))
+    r = bf16_round(torch.randn(1, C, D, H, W, device="cuda", generator=g).relu())
+    F.max_pool3d(y, 2).backward(dpool)
+    ref = y.grad + dskip
+    yv = ops.ActView(to_ndhwc(y.detach()), 1, D, H, W, C)
+    dv = ops.ActView(to_ndhwc(dskip), 1, D, H, W, C)
+    pv = ops.ActView(to_ndhwc(dpool), 1, D // 2, H // 2, W // 2, C)
+    out0 = ops.maxpool3d_bwd_add(yv, dv, pv)
+    torch.cuda.synchronize()
+    assert rel_l2(from_view(out0), ref) < 4e-3
+    if 256 % (C // 8) != 0:
+        return          # the fused statistics need C/8 to divide the block size
+    out1, acc = ops.maxpool3d_bwd_add(yv, dv, pv, stat_r=ops.ActView(to_ndhwc(r), 1, D, H, W, C))
+    torch.cuda.synchronize()
+    assert torch.equal(out0.buf, out1.buf)
+    a4 = acc.view(C, 4).double()
+    o = out1.buf.double().reshape(-1, C)
+    rr = to_ndhwc(r).double().reshape(-1, C)
+    assert torch.allclose(a4[:, 0] + a4[:, 1] / 2.0 ** 32, o.sum(0), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(a4[:, 2] + a4[:, 3] / 2.0 ** 32, (o * rr).sum(0), rtol=1e-5, atol=1e-3)
+
+
 @pytest.mark.parametrize("din,dout", [((4, 5, 6), (8, 10, 12)), ((3, 4, 5), (7, 9, 11)), ((6, 7, 6), (12, 14, 12))])
 def test_upsample_concat_fwd_bwd(din, dout):
     ops = _ops()
