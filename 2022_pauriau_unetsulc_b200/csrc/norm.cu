@@ -431,6 +431,7 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
   if (threadIdx.x == 0) counters[N] = 0;
 }
 
+template <bool kRowLabels>   // separate instantiation: the label test must not touch the code of the dense launches
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff, const __nv_bfloat16* __restrict__ r,
                     long long V, int C, const float* __restrict__ mean_rstd, const float* __restrict__ coef,
@@ -460,8 +461,8 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
   const __nv_bfloat16* gp = dy + ((size_t)n * V) * lddy + dy_coff + oct * 8;
   __nv_bfloat16* op = dr + ((size_t)n * V) * C + oct * 8;
   for (; v + vstride < V; v += 2 * vstride) {
-    const bool l0 = row_labels == nullptr || __ldg(row_labels + (size_t)n * V + v) >= 0;
-    const bool l1 = row_labels == nullptr || __ldg(row_labels + (size_t)n * V + v + vstride) >= 0;
+    const bool l0 = !kRowLabels || __ldg(row_labels + (size_t)n * V + v) >= 0;
+    const bool l1 = !kRowLabels || __ldg(row_labels + (size_t)n * V + v + vstride) >= 0;
     const uint4 ux0 = ldg16(rp + v * C), ug0 = l0 ? ldg16(gp + v * lddy) : zero4;
     const uint4 ux1 = ldg16(rp + (v + vstride) * C), ug1 = l1 ? ldg16(gp + (v + vstride) * lddy) : zero4;
     const f8 x0 = unpack8(ux0), g0 = unpack8(ug0), x1 = unpack8(ux1), g1 = unpack8(ug1);
@@ -477,7 +478,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
     stg16(op + (v + vstride) * C, pack8(o1));
   }
   for (; v < V; v += vstride) {
-    const bool l0 = row_labels == nullptr || __ldg(row_labels + (size_t)n * V + v) >= 0;
+    const bool l0 = !kRowLabels || __ldg(row_labels + (size_t)n * V + v) >= 0;
     const f8 x = unpack8(ldg16(rp + v * C));
     const f8 g = unpack8(l0 ? ldg16(gp + v * lddy) : zero4);
     f8 o;
@@ -603,7 +604,7 @@ extern "C" int b2_relu_gn_bwd(const void* dy, int lddy, int dy_coff, const void*
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
       mean_rstd, partial, counters, N, G, gamma, coef, dgb_n, dgamma, dbeta);
   B2_CHECK_CUDA(cudaGetLastError());
-  B2_LAUNCH(gn_bwd_apply_kernel, dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream, 
+  B2_LAUNCH(gn_bwd_apply_kernel<false>, dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
       mean_rstd, coef, reinterpret_cast<__nv_bfloat16*>(dr), static_cast<const long long*>(nullptr));
   B2_CHECK_CUDA(cudaGetLastError());
@@ -633,9 +634,14 @@ extern "C" int b2_relu_gn_bwd_acc(const long long* stat_acc, const void* dy, int
   B2_LAUNCH(gn_bwd_finalize_acc_kernel, 1, (C + 31) / 32 * 32, 0, stream, stat_acc, C, G,
             1.0 / ((double)V * (C / G)), gamma, mean_rstd, coef, dgamma, dbeta);
   B2_CHECK_CUDA(cudaGetLastError());
-  B2_LAUNCH(gn_bwd_apply_kernel, dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream,
-            reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
-            mean_rstd, static_cast<const float*>(coef), reinterpret_cast<__nv_bfloat16*>(dr), dy_row_labels);
+  if (dy_row_labels != nullptr)
+    B2_LAUNCH(gn_bwd_apply_kernel<true>, dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream,
+              reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V,
+              C, mean_rstd, static_cast<const float*>(coef), reinterpret_cast<__nv_bfloat16*>(dr), dy_row_labels);
+  else
+    B2_LAUNCH(gn_bwd_apply_kernel<false>, dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream,
+              reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V,
+              C, mean_rstd, static_cast<const float*>(coef), reinterpret_cast<__nv_bfloat16*>(dr), dy_row_labels);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }
