@@ -7,7 +7,6 @@
 
 namespace b2 {
 
-static constexpr int kMaxC1 = 64;
 
 // One warp per 32 consecutive voxels, lane = voxel.  All 27 neighbour loads are issued before any arithmetic (the
 // round-1 kernel walked the taps one dependent L1 load at a time and was latency-bound at 680 GB/s); a tap is skipped
