@@ -111,7 +111,7 @@ class UNet3D(nn.Module):
         self._layers_cache = None
         # data-parallel hook: called as hook(name_prefix, [grad tensors]) when a level's gradients are ready
         self.grad_ready_hook = None
-        self.pre_head_hook = None
+        self.post_head_hook = None
 
     # ------------------------------------------------------------------------------------------ plumbing
     def __deepcopy__(self, memo):
@@ -445,8 +445,6 @@ class UNet3D(nn.Module):
         save = _Saved()
         with torch.no_grad():
             feat, xss = self._split_feat(self._trunk_forward(x, save, defer_last_apply=True))
-            if self.pre_head_hook is not None:     # CUDA-graph capture: segment boundary before the labels are read
-                self.pre_head_hook()
             fuse13 = x.shape[0] == 1 and any(needs[:42])
             out = ops.head_ce(feat, labels, hw.detach(), hb.detach(), compute_grad=True,
                               eval_softmax=False, grad_scale=float(loss_scale), want_preds=True,
@@ -454,6 +452,8 @@ class UNet3D(nn.Module):
                               db_out=None if chain else outs[43],
                               stat_r=save.rec[13]["r"] if fuse13 else None, pool=save.pool, x_scale_shift=xss,
                               sparse_dx=fuse13)
+            if self.post_head_hook is not None:    # CUDA-graph capture: segment boundary once the loss is final
+                self.post_head_hook()
         if chain:
             head_grads = [None] * len(hp)
             live = [i for i, p in enumerate(hp) if p.requires_grad]

@@ -377,14 +377,14 @@ class UnetPatternSulciLabelling(object):
         with torch.cuda.stream(side):
             if reducer is not None:
                 reducer.segment_cb = cut
-            # the labels are first needed by the head: a cut here lets train_step() overlap their H2D copy with the
-            # trunk forward (replay waits for the copy only after the first segment)
-            self.model.pre_head_hook = lambda: cut(("labels", None))
+            # the loss is final once the head has run: a cut here lets train_step() read it back (and return, and
+            # start the next step's H2D copies) while the backward pass of this step is still running
+            self.model.post_head_hook = lambda: cut(("loss", None))
             begin()
             try:
                 loss = self._eager_step(sx, sy, optimizer, reducer)
             finally:
-                self.model.pre_head_hook = None
+                self.model.post_head_hook = None
                 if reducer is not None:
                     reducer.segment_cb = None
                 g = cur.pop()
@@ -394,14 +394,15 @@ class UnetPatternSulciLabelling(object):
         return segs, loss
 
     def _graphed_step(self, x, y, optimizer, reducer=None):
-        """x, y: device tensors, or HOST tensors (pinned): then x is copied into the graph's static input on the
-        compute stream and the labels on a copy stream, overlapped with the trunk forward.
+        """x, y: device tensors, or HOST tensors (pinned).  Host inputs are software-pipelined: they are copied into
+        staging buffers on a copy stream (this overlaps the PREVIOUS step's backward pass, because train_step()
+        returns as soon as that step's loss is final), then device-to-device into the graph's static inputs.
         Returns the [2] loss tensor (mean, sum) of the step that was just enqueued."""
         cache = self.__dict__.setdefault("_graphs", {})
         seen = self.__dict__.setdefault("_graph_seen", set())
         key = self._graph_key(x.shape, optimizer) + (id(reducer),)
         ent = cache.get(key)
-        labels_ev = None
+        host = None
         if ent is None and not x.is_cuda:
             x = x.to(self.device, non_blocking=True)
             y = y.to(self.device, non_blocking=True)
@@ -420,21 +421,32 @@ class UnetPatternSulciLabelling(object):
                 print("unetsulc_b200: CUDA-graph capture failed (%s); continuing without graphs" % e)
                 self.use_cuda_graph = False
                 return self._eager_step(x, y, optimizer, reducer)
-            ent = cache[key] = (segs, sx, sy, loss)
+            stage = dict(x=torch.empty_like(sx), y=torch.empty_like(sy), free_ev=None, loss_ev=None,
+                         loss_host=torch.empty(2, dtype=torch.float32).pin_memory())
+            ent = cache[key] = (segs, sx, sy, loss, stage)
         else:
-            segs, sx, sy, loss = ent
-            sx.copy_(x, non_blocking=True)
-            if y.is_cuda:
+            segs, sx, sy, loss, stage = ent
+            if x.is_cuda:
+                sx.copy_(x, non_blocking=True)
                 sy.copy_(y, non_blocking=True)
             else:
+                host = stage
                 cs = self.__dict__.get("_copy_stream")
                 if cs is None:
                     cs = self.__dict__["_copy_stream"] = torch.cuda.Stream(device=self.device)
-                cs.wait_stream(torch.cuda.current_stream())   # the previous replay has finished reading sy
+                cur = torch.cuda.current_stream()
                 with torch.cuda.stream(cs):
-                    sy.copy_(y, non_blocking=True)
-                    labels_ev = torch.cuda.Event()
-                    labels_ev.record()
+                    if stage["free_ev"] is not None:      # the previous step has copied the staging buffers out
+                        cs.wait_event(stage["free_ev"])
+                    stage["x"].copy_(x, non_blocking=True)
+                    stage["y"].copy_(y, non_blocking=True)
+                    staged = torch.cuda.Event()
+                    staged.record()
+                cur.wait_event(staged)
+                sx.copy_(stage["x"], non_blocking=True)   # stream order: after the previous replay's last read of sx
+                sy.copy_(stage["y"], non_blocking=True)
+                stage["free_ev"] = torch.cuda.Event()
+                stage["free_ev"].record()
         dbg = os.environ.get("B2_DEBUG_DP") == "1"
         for k, (g, actions) in enumerate(ent[0]):
             if dbg:
@@ -446,9 +458,12 @@ class UnetPatternSulciLabelling(object):
                     torch.cuda.synchronize()
                 if action[0] == "reduce":
                     reducer._launch(action[1])
-                elif action[0] == "labels":
-                    if labels_ev is not None:
-                        torch.cuda.current_stream().wait_event(labels_ev)
+                elif action[0] == "loss":
+                    if host is not None:                  # early read-back: the backward pass keeps running
+                        host["loss_host"].copy_(ent[3], non_blocking=True)
+                        host["loss_ev"] = torch.cuda.Event()
+                        host["loss_ev"].record()
+                        self.__dict__["_pending_loss"] = host
                 else:
                     reducer.finish()
         # the replayed SGD changed the fp32 masters behind PyTorch's back: bump their version counters so that eager
@@ -470,10 +485,14 @@ class UnetPatternSulciLabelling(object):
         backward, gradient all-reduce when data parallel, fused SGD.  Returns the loss as a Python float (one D2H
         read), i.e. what the reference's batch loop does per batch (training.py:198-215)."""
         if self.use_cuda_graph and not inputs.is_cuda and not labels.is_cuda and labels.dtype == torch.int64:
-            # graph replay: the inputs go straight into the graph's static buffers; the labels (2/3 of the bytes) are
-            # copied on a second stream while the trunk forward runs
+            # graph replay, software-pipelined: the loss is read back as soon as the head has run, so this call returns
+            # while the backward pass is still on the GPU and the next call's H2D copies overlap it
             self.model.train()
             loss = self._graphed_step(inputs, labels, optimizer, reducer)
+            pend = self.__dict__.pop("_pending_loss", None)
+            if pend is not None:          # the loss was copied to pinned memory right after the head
+                pend["loss_ev"].synchronize()
+                return float(pend["loss_host"][0])
             return float(loss[0].item())
         x = inputs.to(self.device, non_blocking=True)
         y = labels.to(self.device, non_blocking=True)

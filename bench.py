@@ -293,7 +293,7 @@ def run_ours(args):
         step_e2e(i)
     e_secs, _ = timed(step_e2e, args.steps)
     e2e = {"value": world * args.steps / e_secs, "unit": "volumes/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": 4, "ms_per_step": e_secs / args.steps * 1e3}
+           "d2h_bytes_per_step": 8, "ms_per_step": e_secs / args.steps * 1e3}
 
     # secondary metric of BASELINE.json: inference ms per hemisphere = eval forward + Softmax scores gathered at the
     # skeleton voxels + the cutting / fold-vote pass for thresholds [50, 100, 150] (pattern_class.py:177-245), device
