@@ -203,3 +203,23 @@ def test_num_conv_chain_head_composes_exactly():
     m2.final_conv = make_head(64, 56, 3)
     m2.load_state_dict(m.state_dict())
     assert "final_conv.2.bias" in m.state_dict()
+
+
+def test_gradient_buckets_cover_a_chain_head():
+    """the bucketed reducer's flat buffers follow ordered_parameters(), also with a num_conv > 1 head (42 + 2n
+    tensors): every head tensor lands in bucket 0, views alias the flat buffers, slots are 16-byte aligned"""
+    from unetsulc_b200 import parallel
+    from unetsulc_b200.pattern_class import make_head
+    m = unetsulc_b200.UNet3D(1, 56)
+    m.final_conv = make_head(64, 56, 2)
+    red = parallel.BucketedGradReducer(m)
+    params = m.ordered_parameters()
+    assert len(params) == 46 and len(red.outs()) == 46
+    assert sum(p.numel() for p in params) <= sum(f.numel() for f in red.flat)
+    for i, (p, v, (b, off, n)) in enumerate(zip(params, red.outs(), red.slot)):
+        assert v.shape == p.shape and n == p.numel() and off % 4 == 0
+        assert b == (0 if i >= 42 else parallel._BUCKET_OF_LAYER[i // 3])
+        v.fill_(float(i))
+        assert float(red.flat[b][off]) == float(i)
+    items = parallel.shard_subjects(list(range(5)), 1, 2)
+    assert items == [(1, 1.0), (3, 1.0), (4, 0.0)]
