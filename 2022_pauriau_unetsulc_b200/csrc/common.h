@@ -48,14 +48,14 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 bool pdl_enabled();
 
 #ifdef __CUDACC__
-// ---- exact, order-independent statistics accumulators --------------------------------------------------------------
+// ---- order-independent fixed-point statistics accumulators ---------------------------------------------------------
 // GroupNorm needs per-channel sums over the whole volume; the kernels that PRODUCE a tensor (conv epilogues, pooling /
 // upsampling backward, the head) add their per-block fp32 partial sums into a two-limb fixed-point accumulator
 // (int64 integer part + int64 fraction in units of 2^-32) with integer atomics.  Integer addition is associative, so
-// the total is bit-identical whatever the arrival order (no float atomics, run-to-run deterministic), and it is exact:
-// an fp32 value splits into rintf(p) and a fraction whose 2^32 multiple is an integer.  The kernels that CONSUME the
-// statistics (GroupNorm apply / backward apply) turn the accumulators into mean, rstd and coefficients in their
-// prologue — no partial buffers, no "last block" pass, no finalize launch.
+// the total is bit-identical whatever the arrival order (no float atomics, run-to-run deterministic).  An fp32 value
+// splits into rintf(p) and a fraction that is kept to 2^-32: exact for |p| >= 2^-9, within 2^-33 absolute otherwise.
+// A one-block kernel (gn_finalize_acc / gn_bwd_finalize_acc, norm.cu) turns the accumulators into mean, rstd and the
+// backward coefficients: no per-block partial buffers, no "last block" pass, no statistics pass over the tensor.
 // Layout per channel: [4] = {sum_hi, sum_lo, sq_hi, sq_lo}.
 __device__ __forceinline__ void stat_atomic_add(long long* slot, float p) {
   const float h = rintf(p);

@@ -33,7 +33,7 @@ struct IgemmParams {
   int ldy, y_coff;
   __nv_bfloat16* y;
   float* y32;          // optional fp32 output (same indexing, ld = ldy) instead of bf16
-  long long* stat_acc;  // optional [Cout][4] exact accumulators (common.h): per-channel sum / sum of squares of the
+  long long* stat_acc;  // optional [Cout][4] fixed-point accumulators (common.h): per-channel sum / sum of squares of the
                         // bf16-rounded outputs (GroupNorm statistics fused into the epilogue; N == 1, one N tile)
   const __nv_bfloat16* stat_r;  // when set, the statistics are (sum dy, sum dy*r) with r = this dense [V][Cout]
                                 // tensor: the two per-channel sums GroupNorm backward needs (dgrad launches)
@@ -742,7 +742,7 @@ extern "C" int b2_conv3d_igemm_splitk(const void* x, int ldx, int x_coff, const 
 }
 
 // fprop with the GroupNorm statistics of the stored (bf16-rounded, post-ReLU) output fused into the epilogue.
-// stat_acc: int64 [Cout][4] exact accumulators (zero before the launch; see common.h), consumed by
+// stat_acc: int64 [Cout][4] fixed-point accumulators (zero before the launch; see common.h), consumed by
 // b2_relu_gn_apply_acc.  Batch 1, Cout <= 256.
 extern "C" int b2_conv3d_igemm_stats(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy,
                                      int y_coff, int N, int D, int H, int W, int Cin, int Cout, int relu,

@@ -34,7 +34,7 @@ struct SlabParams {
   int relu;
   int ldy, y_coff;
   __nv_bfloat16* y;
-  long long* stat_acc;   // optional [Cout][4] exact statistics accumulators (see conv_igemm.cu, common.h)
+  long long* stat_acc;   // optional [Cout][4] fixed-point statistics accumulators (see conv_igemm.cu, common.h)
   const __nv_bfloat16* stat_r;   // optional: backward statistics (sum dy, sum dy*r)
   long long total_tiles;
 };

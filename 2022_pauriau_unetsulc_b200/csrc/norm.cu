@@ -142,8 +142,8 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ r, long long V, int C, float* 
   if (threadIdx.x == 0) counters[n] = 0;   // self-resetting ticket
 }
 
-// ---- statistics from the exact accumulators (common.h) --------------------------------------------------------------
-// The producers leave per-channel EXACT sums in int64 [C][4]; one small block turns them into what the apply kernels
+// ---- statistics from the fixed-point accumulators (common.h) --------------------------------------------------------------
+// The producers leave per-channel fixed-point sums in int64 [C][4]; one small block turns them into what the apply kernels
 // read.  Reading C accumulators instead of ~148 x C fp32 partials makes this a ~3 us kernel (one L2 round trip, fp64
 // only for the C conversions and the G group sums; no fp64 division or square root: 1/m comes from the host and rstd
 // is rsqrtf + one Newton step on the well-conditioned variance).
@@ -548,7 +548,7 @@ extern "C" int b2_relu_gn_stats(const void* r, int N, long long V, int C, int G,
   return B2_OK;
 }
 
-// GroupNorm statistics (batch 1) from the exact accumulators a producer kernel filled (b2_conv3d_igemm_stats,
+// GroupNorm statistics (batch 1) from the fixed-point accumulators a producer kernel filled (b2_conv3d_igemm_stats,
 // b2_conv3d_first_fwd_stats): stat_acc int64 [C][4] -> mean_rstd fp32 [C][2], scale_shift fp32 [C][2].
 extern "C" int b2_relu_gn_finalize_acc(const long long* stat_acc, long long V, int C, int G, float eps,
                                        const float* gamma, const float* beta, float* mean_rstd, float* scale_shift,
@@ -615,7 +615,7 @@ extern "C" long long b2_relu_gn_bwd_workspace_bytes(int N, int C) {
   return b2_gn_workspace_bytes(N, C) + (long long)N * C * 6 * (long long)sizeof(float);
 }
 
-// GroupNorm backward (batch 1) when (sum dy, sum dy*r) arrive in the exact accumulators a producer kernel filled
+// GroupNorm backward (batch 1) when (sum dy, sum dy*r) arrive in the fixed-point accumulators a producer kernel filled
 // (b2_conv3d_igemm_bstats, b2_maxpool3d_bwd_add_bstats, b2_upcat_bwd_separable_bstats, b2_head_ce_bstats): a one-block
 // finalize (coefficients, dgamma, dbeta) + the apply pass; no statistics pass over (dy, r).  workspace >= C*16 bytes.
 // dy_row_labels (int64 [V], may be NULL): dy comes from b2_head_ce_bstats with skip_dx_memset — only the rows of

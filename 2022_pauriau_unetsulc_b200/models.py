@@ -240,7 +240,7 @@ class UNet3D(nn.Module):
                 ops.conv3d_first_fwd(xin, layer.conv.weight.detach(), r, relu=True)
                 mr, ss = ops.relu_gn_stats(r, G, layer.norm.eps, gamma, beta)
             elif B == 1 and cout <= 256 and B * d * h * w > ops.SPLITK_MAX_VOXELS:
-                wf, _ = layer.packs()   # GroupNorm statistics come out of the conv epilogue (exact accumulators)
+                wf, _ = layer.packs()   # GroupNorm statistics come out of the conv epilogue (fixed-point accumulators)
                 mr, ss = ops.conv3d_igemm_gn_stats(xin, wf, r, cin, cout, G, layer.norm.eps, gamma, beta, pool)
             else:
                 wf, _ = layer.packs()

@@ -137,7 +137,7 @@ def conv3d_igemm_auto(x, wpack, y, cin, cout, relu):
 
 
 class StatPool(object):
-    """Exact GroupNorm statistics accumulators (int64 [C][4] per layer, see include/unetsulc_b200.h) carved out of
+    """Fixed-point GroupNorm statistics accumulators (int64 [C][4] per layer, see include/unetsulc_b200.h) carved out of
     one buffer that is zeroed with a single fill at the start of a step.  `take(C)` hands out the next slot."""
     SLOT = 512 * 4
 
@@ -179,7 +179,7 @@ def conv3d_igemm_gn_stats(x, wpack, y, cin, cout, groups, eps, gamma, beta, pool
 
 
 def gn_finalize_acc(acc, V, C, groups, eps, gamma, beta):
-    """exact accumulators int64 [C][4] -> (mean_rstd [1,C,2], scale_shift [1,C,2])"""
+    """fixed-point accumulators int64 [C][4] -> (mean_rstd [1,C,2], scale_shift [1,C,2])"""
     lib = _lib.load()
     mean_rstd = torch.empty((1, C, 2), dtype=torch.float32, device=acc.device)
     scale_shift = torch.empty((1, C, 2), dtype=torch.float32, device=acc.device)

@@ -40,8 +40,9 @@ int b2_conv3d_igemm_splitk(const void* x, int ldx, int x_coff, const void* wpack
                            long long workspace_bytes, cudaStream_t stream);
 
 /* ---- statistics accumulators ------------------------------------------------------------------------------------
- * GroupNorm statistics travel between kernels as EXACT, order-independent accumulators: int64 [C][4] per layer =
- * {sum_hi, sum_lo, sq_hi, sq_lo} (integer part + fraction in units of 2^-32), filled with integer atomics by the
+ * GroupNorm statistics travel between kernels as order-independent fixed-point accumulators: int64 [C][4] per layer =
+ * {sum_hi, sum_lo, sq_hi, sq_lo} (integer part + fraction in units of 2^-32: every fp32 contribution is represented
+ * to within 2^-33, exactly when its magnitude is >= 2^-9), filled with integer atomics by the
  * kernel that PRODUCES the tensor and turned into mean / rstd / coefficients by a one-block finalize: no per-block
  * partial buffers, no statistics pass over the tensor, bit-identical run to run.  The caller zeroes the accumulators before the producer runs.
  *
