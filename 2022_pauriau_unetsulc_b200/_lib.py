@@ -51,9 +51,14 @@ SIGNATURES = {
     "b2_pack_conv_weights_multi": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "b2_scatter_volume_workspace_bytes": (_ll, [_i, _i, _i]),
     "b2_scatter_volume": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _vp]),
+    "b2_scatter_volume_rot_workspace_bytes": (_ll, [_i, _i, _i, _i]),
+    "b2_scatter_volume_rot": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _ll, _vp, _vp, _ll, _vp]),
     "b2_fold_vote_workspace_bytes": (_ll, [_ll, _i, _i, _i]),
     "b2_fold_vote": (_i, [_vp, _vp, _ll, _i, _i, _vp, _i, _vp, _vp, _ll, _vp]),
+    "b2_match_voxels_workspace_bytes": (_ll, [_i]),
+    "b2_match_voxels": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _ll, _vp]),
     "b2_esi_counts": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),
+    "b2_step_metrics": (_i, [_vp, _vp, _ll, _i, _vp, _vp, C.c_double, _vp, _vp]),
 }
 
 _lib = None

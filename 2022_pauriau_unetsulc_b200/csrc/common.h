@@ -57,7 +57,15 @@ bool pdl_enabled();
 // A one-block kernel (gn_finalize_acc / gn_bwd_finalize_acc, norm.cu) turns the accumulators into mean, rstd and the
 // backward coefficients: no per-block partial buffers, no "last block" pass, no statistics pass over the tensor.
 // Layout per channel: [4] = {sum_hi, sum_lo, sq_hi, sq_lo}.
+// Non-finite contributions (a diverged run) cannot be represented in fixed point: they POISON the slot instead (the
+// fraction limb is raised to >= 2^60, far above anything finite contributions can accumulate: < 2^31 each), and
+// stat_read() then returns NaN, so the finalize kernels propagate NaN like a floating-point reduction would.
+static constexpr long long kStatPoison = 1ll << 60;
 __device__ __forceinline__ void stat_atomic_add(long long* slot, float p) {
+  if (!isfinite(p)) {
+    atomicMax(slot + 1, kStatPoison);
+    return;
+  }
   const float h = rintf(p);
   const long long hi = (long long)h;
   const long long lo = __float2ll_rn((p - h) * 4294967296.f);
@@ -65,7 +73,9 @@ __device__ __forceinline__ void stat_atomic_add(long long* slot, float p) {
   if (lo != 0) atomicAdd(reinterpret_cast<unsigned long long*>(slot + 1), (unsigned long long)lo);
 }
 __device__ __forceinline__ double stat_read(const long long* slot) {
-  return (double)__ldcg(slot) + (double)__ldcg(slot + 1) * (1.0 / 4294967296.0);
+  const long long lo = __ldcg(slot + 1);
+  if (lo >= (kStatPoison >> 1)) return __longlong_as_double(0x7ff8000000000000ll);
+  return (double)__ldcg(slot) + (double)lo * (1.0 / 4294967296.0);
 }
 
 __device__ __forceinline__ void pdl_prologue() {

@@ -6,6 +6,7 @@
 // order-independent), pass 2 lets exactly that point write — bit-identical volumes, and only 16 bytes per point cross
 // PCIe instead of 12 bytes per voxel.
 #include "common.h"
+#include <limits.h>
 
 namespace b2 {
 
@@ -48,6 +49,73 @@ scatter_write_kernel(const int* __restrict__ pts, const int* __restrict__ point_
   }
 }
 
+// ---- rotation augmentation on the device (reference dataset.py:33-43, 304-326) -----------------------------------
+// The host keeps the random draws (axis, angle -> R, t in float64, same order as the reference); the device applies
+// p' = trunc(R p + t) to the resident base point list in float64 (one rounding per operation, no contraction), finds
+// min(p') with integer atomics and scatters p' - min.  16 bytes per point cross PCIe once per subject, 96 bytes per
+// sample afterwards.
+struct RigidXform { double r[9]; double t[3]; };
+
+__global__ void __launch_bounds__(256)
+rotate_points_kernel(const int* __restrict__ base, int n, RigidXform xf, int* __restrict__ out, int* __restrict__ mn) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int q[3] = {INT_MAX, INT_MAX, INT_MAX};
+  if (i < n) {
+    const double p0 = (double)base[3 * i], p1 = (double)base[3 * i + 1], p2 = (double)base[3 * i + 2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double v = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(p0, xf.r[3 * k]), __dmul_rn(p1, xf.r[3 * k + 1])),
+                                           __dmul_rn(p2, xf.r[3 * k + 2])), xf.t[k]);
+      q[k] = (int)v;                            // truncation toward zero, like ndarray.astype(int)
+      out[3 * i + k] = q[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int m = q[k];
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0 && m != INT_MAX) atomicMin(mn + k, m);
+  }
+}
+
+// out-of-volume points are COUNTED (oob[0]): the reference's index_put raises IndexError for them; the host checks the
+// counter at the end of the phase instead of synchronising every sample
+__device__ __forceinline__ long long point_voxel_off(const int* __restrict__ pts, int i, const int* __restrict__ mn,
+                                                     int D, int H, int W) {
+  const int a = pts[3 * i] - mn[0], b = pts[3 * i + 1] - mn[1], c = pts[3 * i + 2] - mn[2];
+  if ((unsigned)a >= (unsigned)D || (unsigned)b >= (unsigned)H || (unsigned)c >= (unsigned)W) return -1;
+  return ((long long)a * H + b) * W + c;
+}
+__global__ void __launch_bounds__(256)
+scatter_claim_off_kernel(const int* __restrict__ pts, int n, const int* __restrict__ mn, int D, int H, int W,
+                         int* __restrict__ winner, int* __restrict__ oob) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long v = point_voxel_off(pts, i, mn, D, H, W);
+  if (v >= 0) atomicMax(winner + v, i);
+  else atomicAdd(oob, 1);
+}
+__global__ void __launch_bounds__(256)
+scatter_write_off_kernel(const int* __restrict__ pts, const int* __restrict__ point_labels, int n,
+                         const int* __restrict__ mn, int D, int H, int W, const int* __restrict__ winner,
+                         float* __restrict__ x, long long* __restrict__ labels) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long v = point_voxel_off(pts, i, mn, D, H, W);
+  if (v >= 0 && winner[v] == i) {
+    x[v] = 1.f;
+    labels[v] = (long long)point_labels[i];
+  }
+}
+__global__ void init_min_kernel(int* mn) {
+  pdl_prologue();
+  if (threadIdx.x < 3) mn[threadIdx.x] = INT_MAX;
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -76,6 +144,46 @@ extern "C" int b2_scatter_volume(const int* pts, const int* point_labels, int n,
     B2_CHECK_CUDA(cudaGetLastError());
     B2_LAUNCH(scatter_write_kernel, (n + 255) / 256, 256, 0, stream, pts, point_labels, n, D, H, W,
               static_cast<const int*>(winner), x, labels);
+    B2_CHECK_CUDA(cudaGetLastError());
+  }
+  return B2_OK;
+}
+
+// SulciDataset.__getitem__ with the rotation augmentation applied on the device.  base_pts int32 [n][3]: the subject's
+// point list minus its minimum (device resident); xform: HOST double [12] = R (row major) then t, built on the host
+// from the reference's random draws; the volume receives trunc(R p + t) - min over points (dataset.py:33-43).
+// oob (device int32 [1], accumulated): number of points that fell outside [0,D)x[0,H)x[0,W).
+// workspace: b2_scatter_volume_rot_workspace_bytes(n, D, H, W).
+extern "C" long long b2_scatter_volume_rot_workspace_bytes(int n, int D, int H, int W) {
+  return (long long)D * H * W * (long long)sizeof(int) + ((long long)n * 3 + 4) * (long long)sizeof(int);
+}
+extern "C" int b2_scatter_volume_rot(const int* base_pts, const int* point_labels, int n, const double* xform, int D,
+                                     int H, int W, float* x, long long* labels, long long background, int* oob,
+                                     void* workspace, long long workspace_bytes, cudaStream_t stream) {
+  B2_REQUIRE(x && labels && workspace && xform && oob && (n == 0 || (base_pts && point_labels)),
+             "b2_scatter_volume_rot: null pointer");
+  B2_REQUIRE(D > 0 && H > 0 && W > 0 && n >= 0, "b2_scatter_volume_rot: bad shape");
+  B2_REQUIRE(workspace_bytes >= b2_scatter_volume_rot_workspace_bytes(n, D, H, W),
+             "b2_scatter_volume_rot: workspace too small");
+  const long long V = (long long)D * H * W;
+  int* winner = reinterpret_cast<int*>(workspace);
+  int* mn = winner + V;
+  int* rot = mn + 4;
+  long long fb = (V + 255) / 256;
+  if (fb > num_sms() * 16) fb = num_sms() * 16;
+  B2_LAUNCH(scatter_fill_kernel, (unsigned)fb, 256, 0, stream, x, labels, winner, V, background);
+  B2_CHECK_CUDA(cudaGetLastError());
+  if (n > 0) {
+    RigidXform xf;
+    for (int i = 0; i < 9; ++i) xf.r[i] = xform[i];
+    for (int i = 0; i < 3; ++i) xf.t[i] = xform[9 + i];
+    B2_LAUNCH(init_min_kernel, 1, 32, 0, stream, mn);
+    B2_LAUNCH(rotate_points_kernel, (n + 255) / 256, 256, 0, stream, base_pts, n, xf, rot, mn);
+    B2_CHECK_CUDA(cudaGetLastError());
+    B2_LAUNCH(scatter_claim_off_kernel, (n + 255) / 256, 256, 0, stream, static_cast<const int*>(rot), n,
+              static_cast<const int*>(mn), D, H, W, winner, oob);
+    B2_LAUNCH(scatter_write_off_kernel, (n + 255) / 256, 256, 0, stream, static_cast<const int*>(rot), point_labels, n,
+              static_cast<const int*>(mn), D, H, W, static_cast<const int*>(winner), x, labels);
     B2_CHECK_CUDA(cudaGetLastError());
   }
   return B2_OK;

@@ -77,6 +77,31 @@ esi_counts_kernel(const int* __restrict__ y_true, const int* __restrict__ y_pred
   }
 }
 
+// Per-step epoch metrics of the training loop (reference training.py:215-225), kept on the device: TP/FP/FN counters
+// from the int64 label volume and the int32 predictions of the head kernel (-1 where unlabelled), plus the running
+// loss sum.  One launch per step, capturable in the step's CUDA graph; the host reads the totals once per phase.
+__global__ void __launch_bounds__(256)
+step_metrics_kernel(const long long* __restrict__ labels, const int* __restrict__ preds, long long n, int C,
+                    unsigned long long* __restrict__ counts, const float* __restrict__ loss, double loss_weight,
+                    double* __restrict__ loss_acc) {
+  pdl_prologue();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss != nullptr) {   // the only writer; launches are stream-ordered
+    loss_acc[0] += (double)loss[0] * loss_weight;
+    loss_acc[1] += loss_weight;
+  }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = labels[i];
+    if (t < 0) continue;                       // unlabelled voxel: the reference masks it out (labels != -1)
+    const int p = preds[i];
+    if (t == (long long)p) {
+      if (t < C) atomicAdd(&counts[t], 1ull);
+    } else {
+      if (p >= 0 && p < C) atomicAdd(&counts[C + p], 1ull);
+      if (t < C) atomicAdd(&counts[2 * C + t], 1ull);
+    }
+  }
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -116,6 +141,21 @@ extern "C" int b2_esi_counts(const int* y_true, const int* y_pred, long long n, 
   int blocks = (int)((n + 255) / 256);
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   B2_LAUNCH(esi_counts_kernel, blocks, 256, 0, stream, y_true, y_pred, n, C, counts);
+  B2_CHECK_CUDA(cudaGetLastError());
+  return B2_OK;
+}
+
+// labels int64 [n] (-1 = unlabelled), preds int32 [n]; counts uint64 [3][C] accumulated; loss (may be NULL): fp32 device
+// scalar of this step, loss_acc double [2] += {loss * loss_weight, loss_weight}
+extern "C" int b2_step_metrics(const long long* labels, const int* preds, long long n, int C,
+                               unsigned long long* counts, const float* loss, double loss_weight, double* loss_acc,
+                               cudaStream_t stream) {
+  B2_REQUIRE(labels && preds && counts && C > 0 && n >= 0, "b2_step_metrics: null pointer");
+  B2_REQUIRE(loss == nullptr || loss_acc != nullptr, "b2_step_metrics: loss without loss_acc");
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  if (blocks < 1) blocks = 1;
+  B2_LAUNCH(step_metrics_kernel, blocks, 256, 0, stream, labels, preds, n, C, counts, loss, loss_weight, loss_acc);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
 }

@@ -112,6 +112,9 @@ class UNet3D(nn.Module):
         # data-parallel hook: called as hook(name_prefix, [grad tensors]) when a level's gradients are ready
         self.grad_ready_hook = None
         self.post_head_hook = None
+        # CUDA-graph capture: re-pack the bf16 weights of every trainable layer even when the packs are fresh, so that
+        # the recorded step always contains the re-pack its replays need after each SGD update
+        self.force_repack = False
 
     # ------------------------------------------------------------------------------------------ plumbing
     def __deepcopy__(self, memo):
@@ -201,7 +204,8 @@ class UNet3D(nn.Module):
         (r, scale_shift) = its relu(conv) and fp32 [1,f,2] coefficients for the head kernels, which apply it to the
         rows they gather (labelled / skeleton voxels, 2-4 % of the volume)."""
         L = self._layers()
-        stale = [l for l in L if l.stale()]
+        force = self.__dict__.get("force_repack", False)
+        stale = [l for l in L if l.stale() or (force and l.cin != 1 and l.conv.weight.requires_grad)]
         if stale:   # one launch re-packs every layer whose fp32 master changed (optimiser step, load_state_dict, .to())
             for l, (wf, wd) in zip(stale, ops.pack_conv_weights_multi([l.conv.weight for l in stale])):
                 l.wf, l.wd, l._key = wf, wd, l.key()
@@ -480,10 +484,12 @@ class UNet3D(nn.Module):
         """The parameters in the order forward_backward() reports gradients (42 trunk + 2 per head conv)."""
         return list(self.trunk_parameters()) + self.head_parameters()
 
-    def scores_at(self, x, index):
+    def scores_at(self, x, index, exact=False):
         """Eval forward + Softmax scores gathered at linear voxel indices (labeling(), pattern_class.py:266-277).
-        Returns (scores fp32 [n, C], preds int32 [n])."""
+        Returns (scores fp32 [n, C], preds int32 [n]).  exact: the split-precision forward (see _exact_forward)."""
         x = self._check_input(x)
+        if exact:
+            return self._exact_scores_at(x, index)
         with torch.no_grad():
             hw, hb = self._head_effective()
             feat, xss = self._split_feat(self._trunk_forward(x, None, defer_last_apply=True))

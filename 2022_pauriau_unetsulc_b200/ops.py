@@ -56,8 +56,13 @@ def _need_cuda(*ts):
 
 
 class Workspace(object):
-    """Grow-only scratch buffer per device (the C-ABI never allocates)."""
+    """Grow-only scratch buffer per device (the C-ABI never allocates).
+
+    A captured CUDA graph bakes the buffer's address into its kernel nodes, so a buffer that has to be replaced by a
+    larger one is RETIRED (kept alive), never freed: graphs captured earlier keep reading / writing valid, private
+    scratch memory instead of memory the caching allocator may have handed to somebody else."""
     _bufs = {}
+    _retired = []
 
     @classmethod
     def get(cls, nbytes, device, tag="ws"):
@@ -65,6 +70,8 @@ class Workspace(object):
         buf = cls._bufs.get(key)
         nbytes = int(nbytes)
         if buf is None or buf.numel() < nbytes:
+            if buf is not None:
+                cls._retired.append(buf)
             buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
             cls._bufs[key] = buf
         return buf
@@ -533,6 +540,92 @@ def scatter_volume(points, point_labels, size, device, background=-1):
     return x, labels
 
 
+class ResidentPoints(object):
+    """A subject's point list: base points (minus their minimum) int32 [n,3] + label ids int32 [n], held in pinned
+    host memory and — after the first `on(device)` with keep=True — on the device."""
+    __slots__ = ("h_pts", "h_lab", "n", "pts", "lab")
+
+    def __init__(self, pts_host, lab_host):
+        import numpy as np
+        pts = np.ascontiguousarray(np.asarray(pts_host, dtype=np.int32).reshape(-1, 3))
+        lab = np.ascontiguousarray(np.asarray(lab_host, dtype=np.int32).reshape(-1))
+        self.n = pts.shape[0]
+        self.h_pts, self.h_lab = torch.from_numpy(pts), torch.from_numpy(lab)
+        if torch.cuda.is_available():
+            self.h_pts, self.h_lab = self.h_pts.pin_memory(), self.h_lab.pin_memory()
+        self.pts = self.lab = None
+
+    def on(self, device, keep=True):
+        """(pts, lab) on `device`; keep=False uploads them again on every call (16 bytes per point, asynchronous)"""
+        if self.pts is not None and self.pts.device == torch.device(device):
+            return self.pts, self.lab
+        pts = self.h_pts.to(device, non_blocking=True)
+        lab = self.h_lab.to(device, non_blocking=True)
+        if keep:
+            self.pts, self.lab = pts, lab
+        return pts, lab
+
+
+_OOB = {}
+
+
+def oob_counter(device):
+    """device int32 [1]: points that fell outside their volume since the last check (see scatter_volume_rot)"""
+    key = str(torch.device(device))
+    t = _OOB.get(key)
+    if t is None:
+        t = _OOB[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return t
+
+
+def check_oob(device):
+    """One D2H read: raises IndexError (what the reference's index_put raises per sample) if any point of the samples
+    built since the last check fell outside its volume."""
+    t = _OOB.get(str(torch.device(device)))
+    if t is None:
+        return
+    n = int(t.item())
+    if n:
+        t.zero_()
+        raise IndexError("scatter_volume: %d point(s) outside the volume (img_size too small for the rotated "
+                         "skeleton)" % n)
+
+
+def scatter_volume_rot(res, xform, size, device, background=-1, keep=True):
+    """res: ResidentPoints; xform: 12 floats (R row-major, t) or None for the identity; size: (D, H, W).
+    Returns (x fp32 [1, D, H, W], labels int64 [D, H, W]): the dense volumes of the rotated, truncated, min-shifted
+    point list (reference dataset.py:33-43, 66-88), built entirely on the device.  keep: see ResidentPoints.on."""
+    lib = _lib.load()
+    D, H, W = int(size[0]), int(size[1]), int(size[2])
+    dev = torch.device(device)
+    pts, lab = res.on(dev, keep)
+    x = torch.empty((1, D, H, W), dtype=torch.float32, device=dev)
+    labels = torch.empty((D, H, W), dtype=torch.int64, device=dev)
+    ws = Workspace.get(lib.b2_scatter_volume_rot_workspace_bytes(res.n, D, H, W), dev, "scatter")
+    if xform is None:
+        xform = (1., 0., 0., 0., 1., 0., 0., 0., 1., 0., 0., 0.)
+    xf = (C.c_double * 12)(*[float(v) for v in xform])
+    _lib.check(lib.b2_scatter_volume_rot(_p(pts), _p(lab), res.n, xf, D, H, W, _p(x), _p(labels),
+                                         int(background), _p(oob_counter(dev)), _p(ws), ws.numel(), _s()),
+               "b2_scatter_volume_rot")
+    _count(5 if res.n else 1)
+    return x, labels
+
+
+def step_metrics(labels, preds, n_classes, counts, loss=None, loss_weight=1.0, loss_acc=None):
+    """labels int64 [...], preds int32 [...] (same numel); counts int64 [3, n_classes] += TP/FP/FN over the labelled
+    voxels; loss_acc float64 [2] += (loss[0] * loss_weight, loss_weight).  No host synchronisation."""
+    lib = _lib.load()
+    _need_cuda(labels, preds, counts)
+    if labels.dtype != torch.int64 or not labels.is_contiguous():
+        labels = labels.to(torch.int64).contiguous()
+    if preds.dtype != torch.int32 or not preds.is_contiguous():
+        preds = preds.to(torch.int32).contiguous()
+    _lib.check(lib.b2_step_metrics(_p(labels), _p(preds), labels.numel(), n_classes, _p(counts), _p(loss),
+                                   float(loss_weight), _p(loss_acc), _s()), "b2_step_metrics")
+    _count(1)
+
+
 def fold_vote(scores, fold_dense, n_folds, thresholds):
     """scores fp32 [n, C] cuda; fold_dense int32 [n] in [0, n_folds); thresholds: list of ints.
     Returns int32 [T, n]."""
@@ -549,6 +642,22 @@ def fold_vote(scores, fold_dense, n_folds, thresholds):
     _lib.check(lib.b2_fold_vote(_p(scores.contiguous()), _p(fold_dense.contiguous()), n, Cc, n_folds, _p(th), T,
                                 _p(out), _p(ws), ws.numel(), _s()), "b2_fold_vote")
     _count(3)
+    return out
+
+
+def match_voxels(pts_a, pts_b, val_b):
+    """pts_a, pts_b: int32 cuda [n, 3] (same voxel set, two orders); val_b int32 cuda [n].  Returns int32 [n]:
+    val_b re-ordered to list a by pairing equal ranks of the stable (x, y, z) sorts (pattern_class.py:205-228)."""
+    lib = _lib.load()
+    _need_cuda(pts_a, pts_b, val_b)
+    n = pts_a.shape[0]
+    out = torch.empty(n, dtype=torch.int32, device=pts_a.device)
+    if n == 0:
+        return out
+    ws = Workspace.get(lib.b2_match_voxels_workspace_bytes(n), pts_a.device, "match")
+    _lib.check(lib.b2_match_voxels(_p(pts_a.contiguous()), _p(pts_b.contiguous()), _p(val_b.contiguous()), n, _p(out),
+                                   _p(ws), ws.numel(), _s()), "b2_match_voxels")
+    _count(5)
     return out
 
 

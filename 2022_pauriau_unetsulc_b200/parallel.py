@@ -31,13 +31,17 @@ def layer_of_param(i):
 
 
 class BucketedGradReducer(object):
-    def __init__(self, model, process_group=None, average=True):
+    def __init__(self, model, process_group=None, average=True, sync_params=True):
         self.model = model
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.average = average
         params = model.ordered_parameters()
         dev = params[0].device
+        if self.world > 1 and sync_params:
+            # every process built (and randomly initialised) its own network: replicas must start from rank 0's
+            # weights or the averaged gradients are taken at different points and the replicas never agree
+            broadcast_parameters(model, process_group)
         self.params = params
         sizes = [0, 0, 0, 0]
         self.slot = []
@@ -115,6 +119,25 @@ class BucketedGradReducer(object):
             torch.cuda.current_stream().wait_event(ev)
         self._pending = []
         return self.views
+
+
+def broadcast_parameters(model, group=None, src=0):
+    """rank `src`'s parameters and buffers -> every rank (in place; version counters bumped so that the bf16 weight
+    packs are rebuilt)"""
+    with torch.no_grad():
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
+            torch.autograd.graph.increment_version(t)
+
+
+def parameters_in_sync(model, group=None):
+    """True when every rank holds bit-identical parameters (compares per-tensor fp64 sums and abs-sums)"""
+    chk = torch.stack([torch.stack((p.detach().double().sum(), p.detach().double().abs().sum()))
+                       for p in model.parameters()])
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    return bool(torch.equal(lo, hi))
 
 
 def shard_subjects(items, rank, world):

@@ -18,12 +18,11 @@ import torch
 import torch.nn as nn
 
 from . import ops, parallel
-from .cutting import cutting_multi
 from .dataset import SulciDataset, extract_data
 from .early_stopping import EarlyStopping
 from .models import UNet3D
 from .optim import SGD
-from .stats import esi_from_counts, esi_score
+from .stats import esi_from_counts
 
 _BV_MODELS = '/casa/host/build/share/brainvisa-share-5.1/models/models_2019/cnn_models/'
 
@@ -81,6 +80,16 @@ class UnetPatternSulciLabelling(object):
             else:
                 setattr(self, attr, default)
         self.num_conv = dict_model.get('num_conv', 1)
+        # B200 extension (not in the reference's dict_model): a fixed volume size for batch_size 1 as well — the
+        # reference only fixes it for batch_size > 1 (training.py:119-134) or through labeling(imgsize=...).  With a
+        # fixed size the whole training step is replayed from a CUDA graph and the samples are built on the device.
+        self.img_size = dict_model.get('img_size')
+        # optional hook called as step_callback(phase, step, loss_float) after every training step (one D2H read
+        # per step, taken right after the head so that it overlaps the backward pass); None = no per-step host sync
+        self.step_callback = None
+        # keep every subject's point list on the device after its first use (False: upload it again every sample)
+        self.resident_points = True
+        self.timings = {}
 
         self.results = {}
         self.dict_scores = {}
@@ -145,61 +154,116 @@ class UnetPatternSulciLabelling(object):
         return dict_model
 
     # ------------------------------------------------------------------------------------------ inference
-    def labeling(self, gfile, bck2=None, names=None, imgsize=None):
-        """Returns (ytrue, ypred, yscores): lists over the skeleton points and a float64 [Npoints, C] array."""
-        print('Labeling', gfile)
+    def _subject_arrays(self, gfile, bck2, names):
+        """(points minus their minimum int64 [n,3], label ids int32 [n]) of a subject, converted from the Python lists
+        of dict_bck2 / dict_names once (the reference converts them on every call, dataset.py:47-49, 82-86)."""
+        cache = self.__dict__.setdefault("_subject_cache", {})
+        c = cache.get(gfile)
+        if c is None or c[0] is not bck2 or c[1] is not names:
+            pts = np.asarray(bck2).reshape(-1, 3).astype(np.int64)
+            ids = np.asarray([self.dict_sulci[n] for n in names], dtype=np.int32)
+            c = cache[gfile] = (bck2, names, pts - np.min(pts, axis=0), ids)
+        return c[2], c[3]
+
+    def _labeling_device(self, gfile, bck2=None, names=None, imgsize=None, exact=None):
+        """The device half of labeling(): eval forward + Softmax scores gathered at the skeleton points.
+        Returns (scores fp32 [n, C], preds int32 [n], ytrue int64 [n]) as DEVICE tensors."""
         self.model = self.model.to(self.device)
         self.model.eval()
         if bck2 is None:
             bck2 = self.dict_bck2[gfile]
         if names is None:
             names = self.dict_names[gfile]
-        dataset = SulciDataset([gfile], self.dict_sulci, train=False, translation_file=self.trfile,
-                               dict_bck2={gfile: bck2}, dict_names={gfile: names}, img_size=imgsize)
-        inputs, labels = dataset[0]
-        pts = np.asarray(bck2) - np.min(bck2, axis=0)
+        if self.device.type == "cuda":
+            # same volumes as SulciDataset(train=False)[0] (dataset.py:45-88) from per-subject cached arrays
+            pts, ids = self._subject_arrays(gfile, bck2, names)
+            size = (np.max(pts, axis=0) + 1) if imgsize is None else imgsize
+            inputs, labels = ops.scatter_volume(pts, ids, size, self.device, background=self.dict_sulci['background'])
+        else:
+            dataset = SulciDataset([gfile], self.dict_sulci, train=False, translation_file=self.trfile,
+                                   dict_bck2={gfile: bck2}, dict_names={gfile: names}, img_size=imgsize,
+                                   device=self.device if self.device.type == "cuda" else None)
+            inputs, labels = dataset[0]
+            pts = np.asarray(bck2) - np.min(bck2, axis=0)
         D, H, W = labels.shape
-        lin = torch.as_tensor((pts[:, 0] * H + pts[:, 1]) * W + pts[:, 2], dtype=torch.long)
+        lin = torch.as_tensor((pts[:, 0] * H + pts[:, 1]) * W + pts[:, 2], dtype=torch.long).to(self.device)
+        exact = self.exact_inference if exact is None else exact
         with torch.no_grad():
             x = inputs.unsqueeze(0).to(self.device)
-            scores, preds = self.model.scores_at(x, lin.to(self.device))
-        ypred = preds.cpu().tolist()
-        ytrue = labels.reshape(-1)[lin].tolist()
-        yscores = scores.cpu().numpy().astype(np.float64)
-        return ytrue, ypred, yscores
+            scores, preds = self.model.scores_at(x, lin, exact=exact)
+        return scores, preds, labels.to(self.device).reshape(-1)[lin]
+
+    # exact_inference (B200 extension): labeling() runs the split-precision forward (bf16x3 tensor-core convolutions,
+    # fp32 activations; models.UNet3D.scores_at(exact=True)) whose per-voxel arg-max equals the fp32 reference's
+    # wherever the reference's top-2 margin exceeds the documented epsilon.  About 3x the inference time.
+    exact_inference = False
+
+    def labeling(self, gfile, bck2=None, names=None, imgsize=None):
+        """Returns (ytrue, ypred, yscores): lists over the skeleton points and a float64 [Npoints, C] array."""
+        print('Labeling', gfile)
+        scores, preds, ytrue = self._labeling_device(gfile, bck2, names, imgsize)
+        return ytrue.cpu().tolist(), preds.cpu().tolist(), scores.cpu().numpy().astype(np.float64)
 
     def test_thresholds(self, gfile_list_test, gfile_list_notcut_test, threshold_range, save_results=True):
+        """Threshold sweep of the cutting pass (pattern_class.py:177-245).  Per graph everything between the forward
+        pass and the per-threshold ESI stays on the device: scores -> voxel matching (b2_match_voxels) -> fold vote
+        for all thresholds (b2_fold_vote) -> TP/FP/FN counters (b2_esi_counts); one small D2H read per graph.
+        With torch.distributed initialised, graphs are dealt round-robin to the ranks (no collective on the data
+        path) and the per-graph scores are gathered at the end, so every rank returns the reference's result."""
         print('test thresholds')
         since = time.time()
         threshold_range = list(threshold_range)
         for th in threshold_range:
             self.dict_scores[th] = []
-        for gfile, gfile_notcut in zip(gfile_list_test, gfile_list_notcut_test):
+        rank, world = self._dist()
+        n_classes = len(self.sulci_side_list)
+        keep = [self.dict_sulci[ss] for ss in self.sslist]
+        mine = {}                                   # graph position -> [score per threshold] or None (ignored)
+        pairs = list(zip(gfile_list_test, gfile_list_notcut_test))
+        for k, (gfile, gfile_notcut) in enumerate(pairs):
+            if k % world != rank:
+                continue
             data = self._graph_data(gfile)
-            nbck = np.asarray(data['nbck'])
-            bck2 = np.asarray(data['bck2'])
-            names = np.asarray(data['names'])
             data_nc = self._graph_data(gfile_notcut)
-            nbck_nc = np.asarray(data_nc['nbck'])
-            vert_nc = np.asarray(data_nc['vert'])
+            nbck = np.asarray(data['nbck'], dtype=np.int32).reshape(-1, 3)
+            nbck_nc = np.asarray(data_nc['nbck'], dtype=np.int32).reshape(-1, 3)
+            vert_nc = np.asarray(data_nc['vert']).reshape(-1)
 
-            _, _, yscores = self.labeling(gfile)
+            print('Labeling', gfile)
+            scores, _, _ = self._labeling_device(gfile)
 
             if len(nbck) != len(nbck_nc):
                 print()
                 print('ERROR no matches between %s and %s' % (gfile, gfile_notcut))
                 print('--- Files ignored to fix the threshold')
                 print()
+                mine[k] = None
                 continue
-            # match the voxels of the cut and not-cut graphs: both sorted by native (x, y, z)
-            order = np.lexsort((nbck[:, 2], nbck[:, 1], nbck[:, 0]))
-            order_nc = np.lexsort((nbck_nc[:, 2], nbck_nc[:, 1], nbck_nc[:, 0]))
-            vert_for_point = np.empty(len(nbck), dtype=vert_nc.dtype)
-            vert_for_point[order] = vert_nc[order_nc]
-            cut = cutting_multi(yscores, vert_for_point, bck2, threshold_range, device=self.device)
-            for th, ypred_cut in zip(threshold_range, cut):
-                pred_names = [self.sulci_side_list[y] for y in ypred_cut]
-                self.dict_scores[th].append((1 - esi_score(names, pred_names, self.sslist)) * 100)
+            # elementary-fold ids: the not-cut graph's vertex ids used directly when they are small non-negative
+            # integers (they are vertex indices), else compacted on the host
+            if len(vert_nc) and (vert_nc.min() < 0 or vert_nc.max() >= (1 << 20)):
+                vert_nc = np.unique(vert_nc, return_inverse=True)[1]
+            n_folds = int(vert_nc.max()) + 1 if len(vert_nc) else 1
+            dev = self.device
+            fold = ops.match_voxels(torch.from_numpy(nbck).to(dev), torch.from_numpy(nbck_nc).to(dev),
+                                    torch.from_numpy(vert_nc.astype(np.int32)).to(dev))
+            cut = ops.fold_vote(scores, fold, n_folds, [int(t) for t in threshold_range])     # int32 [T, n]
+            true_ids = torch.as_tensor([self.dict_sulci.get(nm, -2) for nm in data['names']], dtype=torch.int32,
+                                       device=dev)
+            counts = torch.zeros((len(threshold_range), 3, n_classes), dtype=torch.int64, device=dev)
+            for t in range(len(threshold_range)):
+                ops.esi_counts(true_ids, cut[t], n_classes, counts[t])
+            counts = counts.cpu()
+            mine[k] = [(1 - esi_from_counts(counts[t], keep)) * 100 for t in range(len(threshold_range))]
+        if world > 1:
+            import torch.distributed as dist
+            parts = [None] * world
+            dist.all_gather_object(parts, mine)
+            mine = {k: v for part in parts for k, v in part.items()}
+        for k in sorted(mine):
+            if mine[k] is not None:
+                for th, sc in zip(threshold_range, mine[k]):
+                    self.dict_scores[th].append(sc)
         if save_results:
             store = self.results.setdefault('threshold_scores', {})
             for th, sc in self.dict_scores.items():
@@ -276,7 +340,8 @@ class UnetPatternSulciLabelling(object):
             # volumes are built on the device from the point list (b2_scatter_volume)
             return SulciDataset(files, self.dict_sulci, train=train, translation_file=self.trfile,
                                 dict_bck2=self.dict_bck2, dict_names=self.dict_names, img_size=img_size,
-                                device=self.device if self.device.type == "cuda" else None)
+                                device=self.device if self.device.type == "cuda" else None,
+                                resident=self.resident_points)
 
         def loader(ds):
             return torch.utils.data.DataLoader(ds, batch_size=batch_size, shuffle=False, num_workers=0)
@@ -284,21 +349,22 @@ class UnetPatternSulciLabelling(object):
         def max_size(ds, passes):
             size = [0, 0, 0]
             for _ in range(passes):
-                for vol, _ in ds:
-                    size = [max(size[i], vol.shape[i + 1]) for i in range(3)]
+                for k in range(len(ds)):                 # same random draws as building the samples, no volumes
+                    shp = ds.item_size(k)
+                    size = [max(size[i], shp[i]) for i in range(3)]
             return size
 
         sizes = {}
         print('Extract validation dataloader...')
         if batch_size == 1:
-            valloader = loader(make(gfile_list_test, False))
+            valloader = loader(make(gfile_list_test, False, self.img_size))
         else:
             sizes['val'] = max_size(make(gfile_list_test, False), 1)
             print('Val dataset image size:', sizes['val'], sep=' ')
             valloader = loader(make(gfile_list_test, False, sizes['val']))
         print('Extract train dataloader...')
         if batch_size == 1:
-            trainloader = loader(make(gfile_list_train, True))
+            trainloader = loader(make(gfile_list_train, True, self.img_size))
         else:
             random.seed(42)
             np.random.seed(42)
@@ -316,32 +382,51 @@ class UnetPatternSulciLabelling(object):
         return 0, 1
 
     # -- CUDA-graph replay of the whole step ---------------------------------------------------------------------
-    # A step is ~125 kernel launches; enqueueing them from Python costs ~5 ms against ~8 ms of GPU time.  When the
-    # same volume shape comes back (fixed img_size, batch > 1 padding, benchmarks) the step is captured once into
-    # CUDA graphs and replayed.  Off by default for learning() because every subject of a real cohort has its own
-    # bounding box; `use_cuda_graph = True` turns it on.
+    # A step is ~125 kernel launches; enqueueing them from Python costs ~5 ms against ~7 ms of GPU time.  When the
+    # same volume shape keeps coming back (dict_model['img_size'], the batch > 1 padding of training.py:119-134,
+    # benchmarks) the step — forward, loss, backward, SGD and the epoch-metric counters — is captured once into CUDA
+    # graphs and replayed; shapes that do not repeat (every subject of a cohort trained with batch 1 and no img_size
+    # has its own bounding box) keep running eagerly.  `use_cuda_graph = False` turns replay off.
     # Data parallel: NCCL is NOT captured.  The step is cut into graph segments at the points where a gradient bucket
     # closes; between the replays of two segments the bucket's all-reduce is enqueued eagerly on the communication
     # stream, so it still overlaps the rest of the backward pass; the last segment (fused SGD) is replayed after the
-    # compute stream has waited for every all-reduce.  One rank: a single segment.  Measured on 2 x B200 (round 1):
-    # 7.21 ms/step against 7.13 ms on one GPU.
-    use_cuda_graph = False
-    _graph_cache_limit = 2
+    # compute stream has waited for every all-reduce.
+    use_cuda_graph = True
+    _graph_cache_limit = 8
+    _graph_capture_after = 2      # eager sightings of a (shape, optimiser, mask) key before it is captured
 
     def _graph_key(self, shape, optimizer):
         mask = tuple(bool(p.requires_grad) for p in self.model.ordered_parameters())
         return (tuple(shape), id(optimizer), float(optimizer.param_groups[0]["lr"]), float(optimizer.momentum), mask)
 
-    def _eager_step(self, x, y, optimizer, reducer):
+    def _step_metrics(self):
+        """Persistent device accumulators of the epoch metrics (training.py:215-225): TP/FP/FN int64 [3, C] and
+        float64 [2] = (sum of batch-mean loss x batch size, samples).  Static addresses: the captured step adds to them."""
+        m = self.__dict__.get("_metrics")
+        n_classes = len(self.sulci_side_list)
+        if m is None or m["counts"].shape[1] != n_classes or m["counts"].device != self.device:
+            m = self.__dict__["_metrics"] = dict(
+                counts=torch.zeros((3, n_classes), dtype=torch.int64, device=self.device),
+                loss=torch.zeros(2, dtype=torch.float64, device=self.device), n_classes=n_classes)
+        return m
+
+    def _eager_step(self, x, y, optimizer, reducer, metrics=None, loss_scale=1.0):
+        """forward + loss + backward (+ bucketed all-reduce) + SGD, enqueued kernel by kernel.  loss_scale 0 = the
+        zero-weight padding step of an uneven data-parallel tail: same collectives, zero gradient contribution, no
+        metrics."""
         if reducer is not None:
             reducer.begin()
-        loss, _, _, grads = self.model.forward_backward(x, y, outs=reducer.outs() if reducer is not None else None)
+        loss, _, preds, grads = self.model.forward_backward(x, y, outs=reducer.outs() if reducer is not None else None,
+                                                            loss_scale=loss_scale)
         if reducer is not None:
             grads = [g if n is not None else None for g, n in zip(reducer.finish(), grads)]
         optimizer.step(grads=grads)
+        if metrics is not None and loss_scale != 0:
+            ops.step_metrics(y, preds, metrics["n_classes"], metrics["counts"], loss, float(x.shape[0]),
+                             metrics["loss"])
         return loss
 
-    def _capture_segments(self, sx, sy, optimizer, reducer):
+    def _capture_segments(self, sx, sy, optimizer, reducer, metrics):
         """Records one eager step into a list of (CUDAGraph, actions) segments; actions = list of ("reduce", bucket)
         / ("finish", None): what has to be enqueued eagerly after that segment's replay."""
         import gc
@@ -380,10 +465,14 @@ class UnetPatternSulciLabelling(object):
             # the loss is final once the head has run: a cut here lets train_step() read it back (and return, and
             # start the next step's H2D copies) while the backward pass of this step is still running
             self.model.post_head_hook = lambda: cut(("loss", None))
+            # the captured step must contain the bf16 re-pack of every trainable layer even if the packs happen to be
+            # fresh right now (an eval / labeling pass since the last SGD step): replays follow SGD steps
+            self.model.force_repack = True
             begin()
             try:
-                loss = self._eager_step(sx, sy, optimizer, reducer)
+                loss = self._eager_step(sx, sy, optimizer, reducer, metrics)
             finally:
+                self.model.force_repack = False
                 self.model.post_head_hook = None
                 if reducer is not None:
                     reducer.segment_cb = None
@@ -393,34 +482,37 @@ class UnetPatternSulciLabelling(object):
         torch.cuda.current_stream().wait_stream(side)
         return segs, loss
 
-    def _graphed_step(self, x, y, optimizer, reducer=None):
+    def _graphed_step(self, x, y, optimizer, reducer=None, metrics=None, read_loss=False):
         """x, y: device tensors, or HOST tensors (pinned).  Host inputs are software-pipelined: they are copied into
         staging buffers on a copy stream (this overlaps the PREVIOUS step's backward pass, because train_step()
         returns as soon as that step's loss is final), then device-to-device into the graph's static inputs.
+        read_loss: the loss is copied to pinned host memory right after the head (see _take_loss).
         Returns the [2] loss tensor (mean, sum) of the step that was just enqueued."""
         cache = self.__dict__.setdefault("_graphs", {})
-        seen = self.__dict__.setdefault("_graph_seen", set())
-        key = self._graph_key(x.shape, optimizer) + (id(reducer),)
+        seen = self.__dict__.setdefault("_graph_seen", {})
+        key = self._graph_key(x.shape, optimizer) + (id(reducer), id(metrics) if metrics is not None else 0)
         ent = cache.get(key)
-        host = None
         if ent is None and not x.is_cuda:
             x = x.to(self.device, non_blocking=True)
             y = y.to(self.device, non_blocking=True)
         if ent is None:
-            if key not in seen:          # first time: a real eager step (creates workspaces / momentum buffers)
-                seen.add(key)
-                return self._eager_step(x, y, optimizer, reducer)
+            n_seen = seen.get(key, 0)
+            if n_seen < self._graph_capture_after:   # real eager steps first (workspaces, momentum buffers; and the
+                if len(seen) > 4096:                  # shape has to prove that it comes back)
+                    seen.clear()
+                seen[key] = n_seen + 1
+                return self._eager_step(x, y, optimizer, reducer, metrics)
             if len(cache) >= self._graph_cache_limit:
                 cache.pop(next(iter(cache)))
             sx, sy = torch.empty_like(x), torch.empty_like(y)
             sx.copy_(x)
             sy.copy_(y)
             try:
-                segs, loss = self._capture_segments(sx, sy, optimizer, reducer)   # records, does not execute
+                segs, loss = self._capture_segments(sx, sy, optimizer, reducer, metrics)   # records, does not execute
             except Exception as e:
                 print("unetsulc_b200: CUDA-graph capture failed (%s); continuing without graphs" % e)
                 self.use_cuda_graph = False
-                return self._eager_step(x, y, optimizer, reducer)
+                return self._eager_step(x, y, optimizer, reducer, metrics)
             stage = dict(x=torch.empty_like(sx), y=torch.empty_like(sy), free_ev=None, loss_ev=None,
                          loss_host=torch.empty(2, dtype=torch.float32).pin_memory())
             ent = cache[key] = (segs, sx, sy, loss, stage)
@@ -430,7 +522,6 @@ class UnetPatternSulciLabelling(object):
                 sx.copy_(x, non_blocking=True)
                 sy.copy_(y, non_blocking=True)
             else:
-                host = stage
                 cs = self.__dict__.get("_copy_stream")
                 if cs is None:
                     cs = self.__dict__["_copy_stream"] = torch.cuda.Stream(device=self.device)
@@ -459,11 +550,11 @@ class UnetPatternSulciLabelling(object):
                 if action[0] == "reduce":
                     reducer._launch(action[1])
                 elif action[0] == "loss":
-                    if host is not None:                  # early read-back: the backward pass keeps running
-                        host["loss_host"].copy_(ent[3], non_blocking=True)
-                        host["loss_ev"] = torch.cuda.Event()
-                        host["loss_ev"].record()
-                        self.__dict__["_pending_loss"] = host
+                    if read_loss:                         # early read-back: the backward pass keeps running
+                        stage["loss_host"].copy_(ent[3], non_blocking=True)
+                        stage["loss_ev"] = torch.cuda.Event()
+                        stage["loss_ev"].record()
+                        self.__dict__["_pending_loss"] = stage
                 else:
                     reducer.finish()
         # the replayed SGD changed the fp32 masters behind PyTorch's back: bump their version counters so that eager
@@ -472,6 +563,14 @@ class UnetPatternSulciLabelling(object):
             if p.requires_grad:
                 torch.autograd.graph.increment_version(p)
         return ent[3]
+
+    def _take_loss(self, loss):
+        """the step's loss as a Python float: from the pinned early read-back when there is one, else a D2H read"""
+        pend = self.__dict__.pop("_pending_loss", None)
+        if pend is not None:
+            pend["loss_ev"].synchronize()
+            return float(pend["loss_host"][0])
+        return float(loss[0].item())
 
     def train_step_device(self, x, y, optimizer, reducer=None):
         """One training step on DEVICE tensors, no host synchronisation.  Returns the [2] loss tensor (mean, sum)."""
@@ -488,51 +587,91 @@ class UnetPatternSulciLabelling(object):
             # graph replay, software-pipelined: the loss is read back as soon as the head has run, so this call returns
             # while the backward pass is still on the GPU and the next call's H2D copies overlap it
             self.model.train()
-            loss = self._graphed_step(inputs, labels, optimizer, reducer)
-            pend = self.__dict__.pop("_pending_loss", None)
-            if pend is not None:          # the loss was copied to pinned memory right after the head
-                pend["loss_ev"].synchronize()
-                return float(pend["loss_host"][0])
-            return float(loss[0].item())
+            return self._take_loss(self._graphed_step(inputs, labels, optimizer, reducer, read_loss=True))
         x = inputs.to(self.device, non_blocking=True)
         y = labels.to(self.device, non_blocking=True)
         loss = self.train_step_device(x, y, optimizer, reducer)
         return float(loss[0].item())
 
+    @staticmethod
+    def _iter_batches(loader, rank, world, pad):
+        """Batches of `loader` for this rank as (inputs, labels, weight).  One rank: the DataLoader as is.  Data
+        parallel over subjects: batch b goes to rank b % world; the random draws of the other ranks'
+        subjects are consumed so that every rank follows the seeded sequence of a single-process run; when the number
+        of batches is not a multiple of `world` and `pad` is set, the ranks without a batch re-run their last batch
+        with weight 0, so that every rank issues the same collectives."""
+        if world == 1:
+            for inputs, labels in loader:
+                yield inputs, labels, 1.0
+            return
+        import random
+        ds = loader.dataset
+        bs = loader.batch_size or 1
+        n = len(ds)
+        n_batches = (n + bs - 1) // bs
+        last = None
+        for step in range((n_batches + world - 1) // world):
+            mine = None
+            for r in range(world):
+                b = step * world + r
+                idx = range(b * bs, min((b + 1) * bs, n)) if b < n_batches else ()
+                if r == rank and len(idx):
+                    items = [ds[i] for i in idx]
+                    mine = (torch.stack([it[0] for it in items]), torch.stack([it[1] for it in items]))
+                elif hasattr(ds, "consume_draws"):
+                    for i in idx:
+                        ds.consume_draws(i)
+            if mine is not None:
+                last = mine
+                yield mine[0], mine[1], 1.0
+            elif pad:
+                if last is None:   # fewer batches than ranks: any real sample will do (its draws are rolled back)
+                    st, nst = random.getstate(), np.random.get_state()
+                    item = ds[0]
+                    random.setstate(st)
+                    np.random.set_state(nst)
+                    last = (item[0].unsqueeze(0), item[1].unsqueeze(0))
+                yield last[0], last[1], 0.0
+
     def _run_phase(self, phase, loader, optimizer, reducer, before_step=None):
         """One pass over `loader`.  Returns (epoch_loss, epoch_acc).  Losses and ESI counters stay on the device
-        until the end of the phase (one D2H read per phase instead of three per batch)."""
+        until the end of the phase (one D2H read per phase instead of three per batch, training.py:215-217)."""
         train = phase == 'train'
         self.model.train() if train else self.model.eval()
         rank, world = self._dist()
-        n_classes = len(self.sulci_side_list)
-        counts = torch.zeros((3, n_classes), dtype=torch.int64, device=self.device)
-        loss_sum = torch.zeros((), dtype=torch.float64, device=self.device)
-        n_seen = 0
-        for batch, (inputs, labels) in enumerate(loader):
-            if world > 1 and batch % world != rank:
-                continue                           # data parallel over subjects: rank r takes batches r, r+W, ...
+        cuda = self.device.type == "cuda"
+        metrics = self._step_metrics()
+        metrics["counts"].zero_()
+        metrics["loss"].zero_()
+        if cuda:
+            torch.cuda.synchronize(self.device)
+        t0 = time.time()
+        steps = 0
+        for inputs, labels, weight in self._iter_batches(loader, rank, world, pad=train):
             inputs = inputs.to(self.device, non_blocking=True)
             labels = labels.to(self.device, non_blocking=True)
             if train:
                 if before_step is not None:
                     before_step()
-                if reducer is not None:
-                    reducer.begin()
-                loss, _, preds, grads = self.model.forward_backward(
-                    inputs, labels, outs=reducer.outs() if reducer is not None else None)
-                if reducer is not None:
-                    grads = [g if n is not None else None for g, n in zip(reducer.finish(), grads)]
-                optimizer.step(grads=grads)
-                loss = loss[0]
-            else:
+                want_loss = self.step_callback is not None and weight > 0
+                if self.use_cuda_graph and cuda and weight == 1.0:
+                    loss = self._graphed_step(inputs, labels, optimizer, reducer, metrics, read_loss=want_loss)
+                else:
+                    loss = self._eager_step(inputs, labels, optimizer, reducer, metrics, loss_scale=weight)
+                if want_loss:
+                    self.step_callback(phase, steps, self._take_loss(loss))
+            elif weight > 0:
                 with torch.no_grad():
                     loss, preds = self.model.loss_and_preds(inputs, labels)
-            loss_sum += loss.double() * inputs.size(0)
-            n_seen += inputs.size(0)
-            ops.esi_counts(labels.reshape(-1).to(torch.int32), preds.reshape(-1), n_classes, counts)
+                ops.step_metrics(labels, preds, metrics["n_classes"], metrics["counts"], loss.reshape(1),
+                                 float(inputs.size(0)), metrics["loss"])
+            steps += 1
         total = len(loader.dataset)
-        counts, loss_total, _ = parallel.allreduce_metrics(counts, float(loss_sum), n_seen)
+        if cuda:
+            ops.check_oob(self.device)       # samples built on the device report out-of-volume points here
+        loss_sum, n_seen = (float(v) for v in metrics["loss"].cpu())          # the phase's one D2H read
+        counts, loss_total, _ = parallel.allreduce_metrics(metrics["counts"].clone(), loss_sum, int(round(n_seen)))
+        self.timings.setdefault(phase, []).append({"seconds": time.time() - t0, "steps": steps})
         epoch_loss = loss_total / total
         epoch_acc = 1 - esi_from_counts(counts, [self.dict_sulci[ss] for ss in self.sslist])
         return epoch_loss, epoch_acc
@@ -544,6 +683,7 @@ class UnetPatternSulciLabelling(object):
         _, world = self._dist()
         ordered = self.model.ordered_parameters()
         state = {'lr': lr, 'optimizer': SGD(ordered, lr=lr, momentum=momentum, weight_decay=0)}
+        # data parallel: the reducer first broadcasts rank 0's parameters (every process initialised its own network)
         reducer = parallel.BucketedGradReducer(self.model) if world > 1 else None
         writer = _summary_writer(tb_dir) if save_results else None
         es_stop = EarlyStopping(patience=patience['early_stopping']) if 'early_stopping' in patience else None
@@ -596,5 +736,8 @@ class UnetPatternSulciLabelling(object):
                 writer.close()
         if reducer is not None:
             self.model.grad_ready_hook = None
+        # the captured steps of this training reference its optimiser and buckets: release them (and their pools)
+        self.__dict__.pop("_graphs", None)
+        self.__dict__.pop("_graph_seen", None)
         self.model.load_state_dict(best_wts)
         return elapsed

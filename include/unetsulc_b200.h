@@ -158,15 +158,34 @@ long long b2_scatter_volume_workspace_bytes(int D, int H, int W);
 int b2_scatter_volume(const int* pts, const int* point_labels, int n, int D, int H, int W, float* x,
                       long long* labels, long long background, void* workspace, long long workspace_bytes,
                       cudaStream_t stream);
+/* same with the rotation augmentation (dataset.py:33-43, 304-326) applied on the device: base_pts = the subject's
+ * resident point list minus its minimum; xform = HOST double [12], R (row major) then t, built by the host from the
+ * reference's random draws; the points scattered are trunc(R p + t) - min.  oob: device int32 [1], += number of
+ * points outside the volume (the reference raises IndexError there; the host checks once per phase).                */
+long long b2_scatter_volume_rot_workspace_bytes(int n, int D, int H, int W);
+int b2_scatter_volume_rot(const int* base_pts, const int* point_labels, int n, const double* xform, int D, int H,
+                          int W, float* x, long long* labels, long long background, int* oob, void* workspace,
+                          long long workspace_bytes, cudaStream_t stream);
 
 /* ---- post-inference integer pass: cutting(yscores, vert_notcut, bck2, threshold) (pattern_class.py:230) ---------
  * fold: dense ids in [0,F); thresholds: device int32 [T]; out: int32 [T][n].                                      */
 long long b2_fold_vote_workspace_bytes(long long n, int C, int F, int T);
 int b2_fold_vote(const float* scores, const int* fold, long long n, int C, int F, const int* thresholds, int T,
                  int* out, void* workspace, long long workspace_bytes, cudaStream_t stream);
+/* test_thresholds() voxel matching (pattern_class.py:205-228): pts_a / pts_b int32 [n][3] = the native coordinates of
+ * the same voxel set in the cut / not-cut graph order (|coordinate| < 2^20); out_a[i] = val_b[j] for the voxels i, j
+ * of equal rank in the stable (x, y, z) sort of the two lists (the reference sorts both with pandas and zips).       */
+long long b2_match_voxels_workspace_bytes(int n);
+int b2_match_voxels(const int* pts_a, const int* pts_b, const int* val_b, int n, int* out_a, void* workspace,
+                    long long workspace_bytes, cudaStream_t stream);
 /* esi_score counters (training.py:223): counts uint64 [3][C] = TP, FP, FN, accumulated                            */
 int b2_esi_counts(const int* y_true, const int* y_pred, long long n, int C, unsigned long long* counts,
                   cudaStream_t stream);
+/* per-step epoch metrics of the batch loop (training.py:215-225) without leaving the device: labels int64 [n] (-1 =
+ * unlabelled), preds int32 [n] (head kernel output) -> counts += TP/FP/FN; loss (fp32 device scalar, may be NULL):
+ * loss_acc double [2] += {loss * loss_weight, loss_weight}.  One launch, capturable in the step's CUDA graph.        */
+int b2_step_metrics(const long long* labels, const int* preds, long long n, int C, unsigned long long* counts,
+                    const float* loss, double loss_weight, double* loss_acc, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -208,3 +208,123 @@ def test_cuda_graph_step_matches_eager_step(tmp_path, segmented):
     assert results[0][1] == results[1][1]
     for a, b in zip(results[0][2], results[1][2]):
         assert torch.equal(a, b)
+
+
+def test_graph_capture_after_an_eval_pass_still_repacks_weights(tmp_path):
+    """if an eval pass refreshed the bf16 packs right before the step that gets captured, the
+    captured step used to contain no re-pack and every replay ran on frozen bf16 weights.  Sequence step, step, eval,
+    step(capture), step, step must equal the eager run bit for bit."""
+    from unetsulc_b200.training import UnetTrainingSulciLabelling
+    from unetsulc_b200.optim import SGD
+    from oracle.synth import synth_volume
+    sslist = ['S%02d_left' % i for i in range(8)]
+    x, l = synth_volume((16, 24, 32), 8, 100, occupancy=0.06)
+    x, l = x.unsqueeze(0).cuda(), l.unsqueeze(0).cuda()
+    runs = []
+    for use_graph in (False, True):
+        torch.manual_seed(11)
+        with _quiet():
+            t = UnetTrainingSulciLabelling([], 'L', cuda=0, working_path=str(tmp_path), dict_model={'name': 'g'},
+                                           dict_names={}, dict_bck2={}, sulci_side_list=sslist)
+            t.load_network()
+        t.use_cuda_graph = use_graph
+        opt = SGD(t.model.ordered_parameters(), lr=5e-2, momentum=0.9)
+        losses = []
+        for i in range(5):
+            if i == t._graph_capture_after:          # the packs are fresh when the capture step starts
+                t.model.eval()
+                with torch.no_grad():
+                    t.model.loss_and_preds(x, l)
+            losses.append(float(t.train_step_device(x, l, opt)[0]))
+        if use_graph:
+            assert len(t._graphs) == 1
+        runs.append(losses)
+    assert runs[0] == runs[1], runs
+    assert runs[0][-1] < runs[0][0]
+
+
+def test_learning_fixed_img_size_graph_replay_equals_eager(tmp_path):
+    """learning() with dict_model['img_size'] (B200 extension): samples are built on the device from the resident
+    point lists (rotation included), the step incl. the epoch-metric counters is replayed from a CUDA graph; results
+    are identical to the eager run, step_callback sees every step's loss, timings are recorded."""
+    from unetsulc_b200.training import UnetTrainingSulciLabelling
+    bck2, names, sslist = harness.synthetic_cohort(n_subjects=5, shape=(14, 16, 12), n_classes=6, seed=2)
+    files = sorted(bck2)
+    out = []
+    for use_graph in (False, True):
+        random.seed(7); np.random.seed(7); torch.manual_seed(7)
+        seen = []
+        with _quiet():
+            m = UnetTrainingSulciLabelling(files, 'L', cuda=0, working_path=str(tmp_path),
+                                           dict_model={'name': 'fx', 'img_size': [24, 24, 24]},
+                                           dict_names=names, dict_bck2=bck2, sulci_side_list=sslist)
+            m.use_cuda_graph = use_graph
+            m.step_callback = lambda phase, step, loss: seen.append(loss)
+            m.learning(1e-2, 0.9, 3, files[:4], files[4:], batch_size=1)
+        r = m.results
+        out.append((r['epoch_loss_train'], r['epoch_loss_val'], r['epoch_acc_train'], r['epoch_acc_val'], list(seen)))
+        assert len(seen) == 12 and len(m.timings['train']) == 3 and m.timings['train'][-1]['steps'] == 4
+        assert abs(np.mean(seen[-4:]) - r['epoch_loss_train'][0][-1]) < 1e-5
+    assert out[0] == out[1]
+
+
+def test_device_rotation_equals_host_rotation():
+    """b2_scatter_volume_rot (rotation + truncation + min shift + scatter on the device from the resident point list)
+    builds the same volumes as the host numpy path of SulciDataset for the same seeded draws; out-of-volume points
+    are counted and reported as IndexError by check_oob."""
+    from unetsulc_b200 import dataset as ds_mod, ops
+    bck2, names, sslist = harness.synthetic_cohort(n_subjects=3, shape=(20, 24, 18), n_classes=5, seed=9)
+    dict_sulci = {s: i for i, s in enumerate(sslist)}
+    files = sorted(bck2)
+    for resident in (True, False):
+        random.seed(3); np.random.seed(3)
+        host = ds_mod.SulciDataset(files, dict(dict_sulci), train=True, dict_bck2=bck2, dict_names=names,
+                                   img_size=[40, 40, 40])
+        want = [host[i % 3] for i in range(9)]
+        random.seed(3); np.random.seed(3)
+        dev = ds_mod.SulciDataset(files, dict(dict_sulci), train=True, dict_bck2=bck2, dict_names=names,
+                                  img_size=[40, 40, 40], device="cuda", resident=resident)
+        for i in range(9):
+            x, y = dev[i % 3]
+            assert torch.equal(x.cpu(), want[i][0]) and torch.equal(y.cpu(), want[i][1]), (resident, i)
+        ops.check_oob("cuda")
+    small = ds_mod.SulciDataset(files, dict(dict_sulci), train=False, dict_bck2=bck2, dict_names=names,
+                                img_size=[8, 8, 8], device="cuda")
+    small[0]
+    with pytest.raises(IndexError):
+        ops.check_oob("cuda")
+    ops.check_oob("cuda")     # the counter was cleared
+
+
+def test_match_voxels_equals_lexsort_matching():
+    from unetsulc_b200 import ops
+    rng = np.random.RandomState(4)
+    pts = rng.randint(0, 40, size=(5000, 3)).astype(np.int32)
+    pts[100:120] = pts[0:20]                      # duplicated voxels: ties keep list order (stable)
+    perm = rng.permutation(len(pts))
+    a, b = pts, pts[perm]
+    val_b = rng.randint(0, 1000, size=len(pts)).astype(np.int32)
+    got = ops.match_voxels(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(val_b).cuda())
+    oa = np.lexsort((a[:, 2], a[:, 1], a[:, 0]))
+    ob = np.lexsort((b[:, 2], b[:, 1], b[:, 0]))
+    want = np.empty(len(pts), dtype=np.int32)
+    want[oa] = val_b[ob]
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_step_metrics_equal_host_esi_and_loss():
+    from unetsulc_b200 import ops, stats
+    from oracle.stats_ref import esi_score_ref
+    g = torch.Generator().manual_seed(1)
+    labels = torch.randint(-1, 9, (2, 6, 7, 8), generator=g)
+    preds = torch.randint(0, 9, (2, 6, 7, 8), generator=g).to(torch.int32)
+    preds[labels < 0] = -1
+    counts = torch.zeros((3, 9), dtype=torch.int64, device="cuda")
+    acc = torch.zeros(2, dtype=torch.float64, device="cuda")
+    loss = torch.tensor([0.75, 3.0], device="cuda")
+    for rep in range(2):
+        ops.step_metrics(labels.cuda(), preds.cuda(), 9, counts, loss, 2.0, acc)
+    m = labels >= 0
+    want = esi_score_ref(labels[m].tolist() * 2, preds[m].tolist() * 2, list(range(9)))
+    assert abs(stats.esi_from_counts(counts, list(range(9))) - want) < 1e-12
+    assert acc.tolist() == [3.0, 4.0]

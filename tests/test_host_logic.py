@@ -244,3 +244,65 @@ def test_two_limb_statistics_accumulator_is_exact_and_order_independent():
     total = float(hi.sum()) + float(lo.sum()) / 4294967296.0
     ref = float(np.sum(p.astype(np.float64)))
     assert abs(total - ref) <= p.size * 2.0 ** -33 + 1e-12 * abs(ref)
+
+
+def test_data_parallel_batches_uneven_cohort_and_seeded_draws():
+    """Data parallel over subjects: every rank runs ceil(batches / world) steps (the tail is padded
+    with a zero-weight repeat), the union of the weight-1 batches is the cohort, and every rank's samples
+    are exactly the ones a single-process run draws (the other ranks' random draws are consumed, not skipped)."""
+    bck2, names, sslist = harness.synthetic_cohort(n_subjects=5, shape=(12, 14, 10), n_classes=5, seed=3)
+    dict_sulci = {s: i for i, s in enumerate(sslist)}
+    files = sorted(bck2)
+
+    def make():
+        random.seed(21); np.random.seed(21)
+        ds = ds_mod.SulciDataset(files, dict(dict_sulci), train=True, dict_bck2=bck2, dict_names=names)
+        return torch.utils.data.DataLoader(ds, batch_size=1, shuffle=False, num_workers=0)
+
+    single = [(x.clone(), y.clone()) for x, y, w in UnetPatternSulciLabelling._iter_batches(make(), 0, 1, True)]
+    assert len(single) == 5
+    for world in (2, 3, 4, 8):
+        seen = {}
+        for rank in range(world):
+            got = list(UnetPatternSulciLabelling._iter_batches(make(), rank, world, True))
+            assert len(got) == -(-5 // world), (world, rank, len(got))     # same number of steps on every rank
+            real = [(x, y) for x, y, w in got if w == 1.0]
+            assert all(w in (0.0, 1.0) for _, _, w in got)
+            assert len(real) == len(range(rank, 5, world))
+            for k, (x, y) in zip(range(rank, 5, world), real):
+                assert torch.equal(x, single[k][0]) and torch.equal(y, single[k][1]), (world, rank, k)
+                seen[k] = True
+            for x, y, w in got:                   # padding steps carry a real (labelled) sample
+                assert (y >= 0).any()
+            # validation never pads
+            assert len(list(UnetPatternSulciLabelling._iter_batches(make(), rank, world, False))) == len(real)
+        assert sorted(seen) == list(range(5))
+
+
+def test_item_size_follows_the_same_draws_as_getitem():
+    bck2, names, sslist = harness.synthetic_cohort(n_subjects=3, shape=(12, 14, 10), n_classes=5, seed=3)
+    dict_sulci = {s: i for i, s in enumerate(sslist)}
+    files = sorted(bck2)
+    random.seed(5); np.random.seed(5)
+    d = ds_mod.SulciDataset(files, dict(dict_sulci), train=True, dict_bck2=bck2, dict_names=names)
+    shapes = [tuple(d[i][0].shape[1:]) for i in range(3)]
+    random.seed(5); np.random.seed(5)
+    assert [d.item_size(i) for i in range(3)] == shapes
+    random.seed(5); np.random.seed(5)
+    for i in range(3):
+        d.consume_draws(i)
+    a = (random.random(), np.random.rand())
+    random.seed(5); np.random.seed(5)
+    for i in range(3):
+        d[i]
+    assert a == (random.random(), np.random.rand())
+
+
+def test_workspace_regrowth_retires_instead_of_freeing():
+    """A captured CUDA graph keeps the address of the workspace it recorded: regrowing a workspace must
+    not free the old buffer."""
+    from unetsulc_b200 import ops
+    a = ops.Workspace.get(1 << 20, "cpu", "t_regrow")
+    b = ops.Workspace.get(4 << 20, "cpu", "t_regrow")
+    assert b.numel() >= 4 << 20 and any(r is a for r in ops.Workspace._retired)
+    assert ops.Workspace.get(1 << 20, "cpu", "t_regrow") is b

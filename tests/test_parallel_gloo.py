@@ -17,9 +17,11 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import unetsulc_b200
     from unetsulc_b200 import parallel
-    torch.manual_seed(0)
+    torch.manual_seed(rank)                    # every process initialises its own network ...
     model = unetsulc_b200.UNet3D(1, 56)
-    red = parallel.BucketedGradReducer(model)
+    assert not parallel.parameters_in_sync(model)
+    red = parallel.BucketedGradReducer(model)  # ... the reducer broadcasts rank 0's parameters
+    assert parallel.parameters_in_sync(model)
     assert sum(f.numel() for f in red.flat) == 16321496
     params = model.ordered_parameters()
     for phase_layers in (None, ['final_conv', 'decoders.2', 'decoders.1', 'decoders.0']):
