@@ -585,6 +585,18 @@ int make_act_tmap(CUtensorMap* map, const void* base, int N, int D, int H, int W
   return encode_tmap_bf16(map, b, 5, dims, strides, box, box_c * 2);
 }
 
+// same 5-D NDHWC channel-window map without shared-memory swizzle (bandwidth kernels that read the box with plain LDS)
+int make_act_tmap_plain(CUtensorMap* map, const void* base, int N, int D, int H, int W, int C, int ld, int coff,
+                        int box_c, int bw, int bh, int bd) {
+  const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+  const uint64_t e = 2;
+  const uint64_t strides[4] = {(uint64_t)ld * e, (uint64_t)W * ld * e, (uint64_t)H * W * ld * e,
+                               (uint64_t)D * H * W * ld * e};
+  const uint32_t box[5] = {(uint32_t)box_c, (uint32_t)bw, (uint32_t)bh, (uint32_t)bd, 1};
+  const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(base) + coff;
+  return encode_tmap_bf16(map, b, 5, dims, strides, box, 0);
+}
+
 }  // namespace b2
 
 using namespace b2;

@@ -275,6 +275,50 @@ wgrad_reduce_swapped_kernel(const float* __restrict__ ws, float* __restrict__ dw
   }
 }
 
+// Split reduction for the layers with many splits (37..148 partial tiles per element, ~33 MB of fp32 partials per
+// layer).  Round 1 summed all splits of an element in ONE thread: a chain of up to 148 dependent-latency loads per
+// thread on only ~200 blocks (14.7 us per launch, 2 TB/s).  Here a block owns 32 consecutive elements and its 8 warps
+// take the splits s = warp, warp + 8, ... (coalesced 128-byte rows, 4 loads in flight per thread); the 8 partial sums
+// are combined through shared memory in a fixed order: deterministic, 8x the memory-level parallelism.
+// swapped = 0: ws[s][tap][ci][co] -> dW[co][ci][tap];  swapped = 1 (roles swapped, see b2_conv3d_wgrad):
+// ws[s][26 - tap][co][ci] -> dW[co][ci][tap].
+template <int SWAPPED>
+__global__ void __launch_bounds__(256)
+wgrad_reduce_par_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int Cin, int Cout) {
+  pdl_prologue();
+  __shared__ float part[8][32];
+  const long long total = 27LL * Cin * Cout;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (i < total) {
+    int s = warp;
+    for (; s + 24 < splits; s += 32)
+      acc += (ws[(long long)s * total + i] + ws[(long long)(s + 8) * total + i]) +
+             (ws[(long long)(s + 16) * total + i] + ws[(long long)(s + 24) * total + i]);
+    for (; s < splits; s += 8) acc += ws[(long long)s * total + i];
+  }
+  part[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && i < total) {
+    const float r = ((part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane])) +
+                    ((part[4][lane] + part[5][lane]) + (part[6][lane] + part[7][lane]));
+    if (SWAPPED) {
+      const int ci = (int)(i % Cin);
+      const long long q = i / Cin;
+      const int co = (int)(q % Cout);
+      const int tapf = (int)(q / Cout);
+      dw[((long long)co * Cin + ci) * 27 + (26 - tapf)] = r;
+    } else {
+      const int co = (int)(i % Cout);
+      const long long q = i / Cout;
+      const int ci = (int)(q % Cin);
+      const int tap = (int)(q / Cin);
+      dw[((long long)co * Cin + ci) * 27 + tap] = r;
+    }
+  }
+}
+
 // Which operand is shifted per tap?  The shifted operand is re-loaded for every tap, the other one once per
 // 128-voxel K-step, so shifting the NARROW one and keeping the wide one as the N dimension halves the TMA traffic
 // per tensor-cycle when Cout = 64 and Cin >= 128 (decoders.2.conv1: 133 -> 73 B/clk/SM).
@@ -373,13 +417,15 @@ extern "C" int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* d
   dim3 grid((unsigned)(p.n_gchunks * p.n_cout_tiles), (unsigned)p.splits);
   B2_LAUNCH(conv3d_wgrad_kernel, grid, kWgThreads, smem_bytes, stream, tx, ty, p);
   B2_CHECK_CUDA(cudaGetLastError());
-  if (swap) {
-    const long long total = 27LL * Cin * Cout;
+  const long long total = 27LL * Cin * Cout;
+  if (p.splits >= 32 && !swap) {
+    // few elements, many splits (enc0.conv2 148, enc1.conv1 / dec2.conv2 74, enc1.conv2 37): split-parallel reduce
+    B2_LAUNCH(wgrad_reduce_par_kernel<0>, (unsigned)((total + 31) / 32), 256, 0, stream, p.ws, dw, p.splits, Cin, Cout);
+  } else if (swap) {
     B2_LAUNCH(wgrad_reduce_swapped_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, p.ws, dw, p.splits, Cin, Cout);
   } else if ((Cout / 32) * (Cin / 8) >= 2 * num_sms()) {
     B2_LAUNCH(wgrad_reduce_kernel, dim3(Cout / 32, Cin / 8), 256, 0, stream, p.ws, dw, p.splits, Cin, Cout);
   } else {
-    const long long total = 27LL * Cin * Cout;
     B2_LAUNCH(wgrad_reduce_simple_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, p.ws, dw, p.splits, Cin, Cout);
   }
   B2_CHECK_CUDA(cudaGetLastError());

@@ -2,7 +2,9 @@
 // [coff, coff+C) of the pre-allocated concat buffer whose first channels already hold the skip tensor) and its
 // backward.  NDHWC bf16; one 16-byte channel octet per thread; HBM/L2-bandwidth bound.
 #include "common.h"
+#include "ptx.cuh"
 #include "vec.cuh"
+#include <stdlib.h>
 
 namespace b2 {
 
@@ -417,6 +419,146 @@ upsample_bwd_hd_kernel(const __nv_bfloat16* __restrict__ t, int Do, int Ho, __nv
   }
 }
 
+// ---- exact-2x trilinear adjoint in ONE pass -------------------------------------------------------------------------
+// Every level of a volume whose sides are multiples of 8 is an exact 2x upsampling (src = dst/2 - 0.25): the adjoint is a
+// fixed 4-tap stencil per axis,
+//     dx[i] = .25 g[2i-1] + .75 g[2i] + .75 g[2i+1] + .25 g[2i+2],   with weight 1 for g[0] and g[2n-1]
+// (fine sample 0 copies coarse 0; the last fine sample puts both of its weights on the clamped last coarse sample;
+// g[-1] and g[2n] do not exist: TMA zero-fills them).  The two-pass separable form moved 1.9x the algorithmic bytes
+// through a bf16 intermediate (round 1: 1.33 TB/s); here a CTA owns a coarse tile of kUbTH x kUbTW voxels x 64 channels,
+// marches along D over a segment of coarse planes and streams the fine planes of its (2 kUbTH + 2) x (2 kUbTW + 2) x 64
+// window through a TMA ring: every fine value crosses L2 -> SM once per tile (halo 1.2-1.4x, from L2), DRAM sees
+// the fine tensor once, the coarse tensor is written once, and the GroupNorm-backward statistics of the result are
+// accumulated on the way out.  Thread = (coarse h, coarse w, channel octet): 16 x LDS.128 + 128 FMA per fine plane
+// reduce H and W; the D taps are a two-register rolling combination (a fine plane pair (2j-1, 2j) finishes coarse
+// plane j-1 and opens j).
+static constexpr int kUbTH = 4, kUbTW = 8, kUbC = 64, kUbStages = 4;
+static constexpr int kUbThreads = kUbTH * kUbTW * (kUbC / 8);                                  // 256
+static constexpr int kUbPlaneBytes = (2 * kUbTH + 2) * (2 * kUbTW + 2) * kUbC * 2;            // 23 040
+
+__device__ __forceinline__ float ub_weight(int f, int k, int n_fine) {
+  // tap k (0..3) of a coarse sample reads fine index f = 2i - 1 + k
+  const float base = (k == 0 || k == 3) ? 0.25f : 0.75f;
+  return (f == 0 || f == n_fine - 1) ? 1.f : base;
+}
+
+__global__ void __launch_bounds__(kUbThreads, 2)
+upsample2x_bwd_kernel(const __grid_constant__ CUtensorMap tmap, __nv_bfloat16* __restrict__ dx, int Di, int Hi, int Wi,
+                      int C, int tiles_h, int tiles_w, int n_slices, int Ds, int n_dseg, int n_items,
+                      const __nv_bfloat16* __restrict__ stat_r, long long* __restrict__ stat_acc) {
+  pdl_prologue();
+  extern __shared__ uint8_t ub_smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ub_smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ uint64_t full[kUbStages];
+  __shared__ float red[kUbTH * kUbTW][kUbC][2];
+  const int tid = threadIdx.x;
+  const int oct = tid & 7, lw = (tid >> 3) % kUbTW, lh = tid / (8 * kUbTW);
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int s = 0; s < kUbStages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  float st_s[8], st_q[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { st_s[k] = 0.f; st_q[k] = 0.f; }
+  const int Ho = 2 * Hi, Wo = 2 * Wi, Do = 2 * Di;
+  uint32_t gp = 0;   // planes consumed so far by this CTA (ring position / parity), identical in every thread
+  int slice = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int t = item;
+    slice = t % n_slices; t /= n_slices;     // gridDim.x is a multiple of n_slices: a CTA keeps its channel slice
+    const int tw = t % tiles_w; t /= tiles_w;
+    const int th = t % tiles_h; t /= tiles_h;
+    const int dseg = t % n_dseg;
+    const int n = t / n_dseg;
+    const int h0 = th * kUbTH, w0 = tw * kUbTW, d0 = dseg * Ds;
+    const int d1 = min(d0 + Ds, Di);
+    const int n_planes = 2 * (d1 - d0 + 1);            // fine planes 2 d0 - 1 .. 2 d1
+    const int h = h0 + lh, w = w0 + lw;
+    unsigned short whw[4][4];   // bf16 bits of wh[a] * ww[b]: products of {.25, .75, 1} are exact in bf16
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        whw[a][b] = bf16_bits_exact(ub_weight(2 * h - 1 + a, a, Ho) * ub_weight(2 * w - 1 + b, b, Wo));
+    const bool valid_hw = (h < Hi) && (w < Wi);
+    float prev[8], cur[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { prev[k] = 0.f; cur[k] = 0.f; }
+    // prologue: planes 0 .. S-2 of this item (the previous item's planes are all consumed: see the barrier below)
+    __syncthreads();
+    if (tid == 0) {
+      for (int p = 0; p < kUbStages - 1 && p < n_planes; ++p) {
+        const int s = (int)((gp + p) % kUbStages);
+        mbar_arrive_expect_tx(&full[s], (uint32_t)kUbPlaneBytes);
+        tma_load_5d(ring + (size_t)s * kUbPlaneBytes, &tmap, &full[s], slice * kUbC, 2 * w0 - 1, 2 * h0 - 1,
+                    2 * d0 - 1 + p, n);
+      }
+    }
+    for (int p = 0; p < n_planes; ++p, ++gp) {
+      __syncthreads();                                   // plane p-1 is consumed by everybody: its stage is free
+      if (tid == 0 && p + kUbStages - 1 < n_planes) {
+        const int s = (int)((gp + kUbStages - 1) % kUbStages);
+        mbar_arrive_expect_tx(&full[s], (uint32_t)kUbPlaneBytes);
+        tma_load_5d(ring + (size_t)s * kUbPlaneBytes, &tmap, &full[s], slice * kUbC, 2 * w0 - 1, 2 * h0 - 1,
+                    2 * d0 - 1 + p + kUbStages - 1, n);
+      }
+      const int s = (int)(gp % kUbStages);
+      mbar_wait(&full[s], (gp / kUbStages) & 1u);
+      const uint32_t pl = smem_u32(ring) + (uint32_t)s * kUbPlaneBytes +
+                          (uint32_t)(((2 * lh) * (2 * kUbTW + 2) + 2 * lw) * kUbC + oct * 8) * 2u;
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          fma8_bf16(acc, lds16(pl + (uint32_t)((a * (2 * kUbTW + 2) + b) * kUbC) * 2u), whw[a][b]);
+      // D taps: fine plane f = 2 d0 - 1 + p.  Even p: f = 2j - 1 (tap 0 of coarse j, tap 2 of coarse j - 1);
+      // odd p: f = 2j (tap 1 of j, tap 3 of j - 1, which it completes), j = d0 + p / 2.
+      const int f = 2 * d0 - 1 + p;
+      const int j = d0 + (p >> 1);
+      if ((p & 1) == 0) {
+        const float w_open = ub_weight(f, 0, Do), w_close = ub_weight(f, 2, Do);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { cur[k] = w_open * acc[k]; prev[k] = fmaf(w_close, acc[k], prev[k]); }
+      } else {
+        const float w_open = ub_weight(f, 1, Do), w_close = ub_weight(f, 3, Do);
+        f8 o;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { o.v[k] = fmaf(w_close, acc[k], prev[k]); prev[k] = fmaf(w_open, acc[k], cur[k]); }
+        if (j - 1 >= d0 && valid_hw) {                    // coarse plane j - 1 is complete
+          const size_t v = (((size_t)n * Di + (j - 1)) * Hi + h) * Wi + w;
+          const uint4 pk = pack8(o);
+          stg16(dx + v * C + slice * kUbC + oct * 8, pk);
+          if (stat_acc != nullptr) bstats_accumulate(st_s, st_q, pk, ldg16(stat_r + v * C + slice * kUbC + oct * 8));
+        }
+      }
+    }
+  }
+  if (stat_acc != nullptr) {
+    __syncthreads();
+    const int vloc = tid >> 3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[vloc][oct * 8 + k][0] = st_s[k];
+      red[vloc][oct * 8 + k][1] = st_q[k];
+    }
+    __syncthreads();
+    if (tid < kUbC) {
+      float a = 0.f, b = 0.f;
+      for (int r = 0; r < kUbTH * kUbTW; ++r) { a += red[r][tid][0]; b += red[r][tid][1]; }
+      stat_atomic_add(stat_acc + 4 * (slice * kUbC + tid), a);
+      stat_atomic_add(stat_acc + 4 * (slice * kUbC + tid) + 2, b);
+    }
+  }
+}
+
+int make_act_tmap_plain(CUtensorMap* map, const void* base, int N, int D, int H, int W, int C, int ld, int coff,
+                        int box_c, int bw, int bh, int bd);
+
 }  // namespace b2
 
 using namespace b2;
@@ -493,6 +635,35 @@ static int upcat_bwd_separable_impl(const void* dcat, int ldc, int coff, int N, 
   B2_REQUIRE(workspace_bytes >= b2_upcat_bwd_workspace_bytes(N, Do, Ho, Wi, C), "b2_upcat_bwd_separable: workspace too small");
   if (stat_acc)
     B2_REQUIRE(N == 1 && 2048 % C == 0 && C >= 8, "b2_upcat_bwd_separable_bstats: needs batch 1 and C dividing 2048 (C=%d)", C);
+  static const bool no_onepass = getenv("B2_NO_UP1PASS") != nullptr;
+  if (!no_onepass && Do == 2 * Di && Ho == 2 * Hi && Wo == 2 * Wi && C % kUbC == 0) {
+    // exact 2x: single-pass stencil kernel (TMA-staged fine planes), see upsample2x_bwd_kernel
+    CUtensorMap tm;
+    int rc = make_act_tmap_plain(&tm, dcat, N, Do, Ho, Wo, C, ldc, coff, kUbC, 2 * kUbTW + 2, 2 * kUbTH + 2, 1);
+    if (rc) return rc;
+    const int tiles_h = ceil_div(Hi, kUbTH), tiles_w = ceil_div(Wi, kUbTW), n_slices = C / kUbC;
+    const int slots = 2 * num_sms() / n_slices * n_slices;      // resident CTAs, a multiple of the slice count
+    // D segment length: trade the 2-plane halo per segment against filling the last wave
+    int best_ds = Di;
+    double best = -1.0;
+    for (int ds = 1; ds <= Di; ++ds) {
+      const long long items = (long long)N * ceil_div(Di, ds) * tiles_h * tiles_w * n_slices;
+      const double waves = (double)items / slots;
+      const double eff = (waves / (double)((items + slots - 1) / slots)) * (2.0 * ds / (2.0 * ds + 2.0));
+      if (eff > best + 1e-9) { best = eff; best_ds = ds; }
+    }
+    const int n_dseg = ceil_div(Di, best_ds);
+    const long long items = (long long)N * n_dseg * tiles_h * tiles_w * n_slices;
+    B2_REQUIRE(items < (1LL << 31), "b2_upcat_bwd: too many tiles");
+    const int grid = (int)(items < slots ? items : slots);
+    const size_t smem = (size_t)kUbStages * kUbPlaneBytes + 128;
+    B2_CHECK_CUDA(cudaFuncSetAttribute(upsample2x_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2_LAUNCH(upsample2x_bwd_kernel, grid, kUbThreads, smem, stream, tm, reinterpret_cast<__nv_bfloat16*>(dx), Di, Hi,
+              Wi, C, tiles_h, tiles_w, n_slices, best_ds, n_dseg, (int)items,
+              reinterpret_cast<const __nv_bfloat16*>(stat_r), stat_acc);
+    B2_CHECK_CUDA(cudaGetLastError());
+    return B2_OK;
+  }
   __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(workspace);
   B2_LAUNCH(upsample_bwd_w_kernel, (unsigned)(N * Do * Ho), 256, 0, stream,
             reinterpret_cast<const __nv_bfloat16*>(dcat), ldc, coff, Wo, t, Wi, C);

@@ -354,16 +354,18 @@ def upcat_bwd(dcat_window, Di, Hi, Wi, separable=True, stat_r=None, pool=None):
     dx = ActView.alloc(c.N, Di, Hi, Wi, c.C, c.buf.device)
     if separable:
         ws = Workspace.get(lib.b2_upcat_bwd_workspace_bytes(c.N, c.D, c.H, Wi, c.C), c.buf.device, "upbwd")
+        # exact 2x levels run the single-pass stencil kernel (one launch), other ratios the two separable passes
+        n_launch = 1 if (c.D == 2 * Di and c.H == 2 * Hi and c.W == 2 * Wi and c.C % 64 == 0) else 2
         if stat_r is not None:
             acc = _acc(pool, c.C, c.buf.device)
             _lib.check(lib.b2_upcat_bwd_separable_bstats(_p(c.buf), c.ld, c.coff, c.N, c.D, c.H, c.W, _p(dx.buf), Di,
                                                          Hi, Wi, c.C, _p(ws), ws.numel(), _p(stat_r.buf), _p(acc),
                                                          _s()), "b2_upcat_bwd_separable_bstats")
-            _count(2)
+            _count(n_launch)
             return dx, acc
         _lib.check(lib.b2_upcat_bwd_separable(_p(c.buf), c.ld, c.coff, c.N, c.D, c.H, c.W, _p(dx.buf), Di, Hi, Wi,
                                               c.C, _p(ws), ws.numel(), _s()), "b2_upcat_bwd_separable")
-        _count(2)
+        _count(n_launch)
     else:
         _lib.check(lib.b2_upcat_bwd(_p(c.buf), c.ld, c.coff, c.N, c.D, c.H, c.W, _p(dx.buf), Di, Hi, Wi, c.C, _s()),
                    "b2_upcat_bwd")

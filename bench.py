@@ -431,7 +431,7 @@ def run_ours(args):
     }
 
     # ---- end to end through the reference-facing API: UnetTrainingSulciLabelling.learning() ----------------------
-    e2e = run_e2e_learning(args, world, rank, local, dev)
+    e2e = None if args.no_e2e else run_e2e_learning(args, world, rank, local, dev)
 
     # secondary metric of BASELINE.json: inference ms per hemisphere = eval forward + Softmax scores gathered at the
     # skeleton voxels + the cutting / fold-vote pass for thresholds [50, 100, 150] (pattern_class.py:177-245), device
@@ -634,6 +634,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-gpu", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the learning() leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

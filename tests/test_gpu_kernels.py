@@ -533,6 +533,39 @@ def test_upsample_concat_fwd_bwd(din, dout):
         assert rel_l2(from_view(dx), x.grad) < 4e-3, separable
 
 
+@pytest.mark.parametrize("N,C,din", [(1, 64, (5, 6, 9)), (1, 128, (24, 28, 24)), (2, 256, (3, 5, 4)), (1, 512, (6, 7, 6))])
+def test_upsample2x_adjoint_single_pass(N, C, din):
+    """exact-2x levels: the single-pass TMA-staged stencil kernel (upsample2x_bwd_kernel) == PyTorch's adjoint, ==
+    the two-pass separable kernels (B2_NO_UP1PASS), with and without the fused GroupNorm-backward statistics;
+    partial tiles (5x6x9), several D segments and work items per CTA (24x28x24), batch 2."""
+    ops = _ops()
+    Cs = 64
+    dout = tuple(2 * d for d in din)
+    g = torch.Generator(device="cuda").manual_seed(21)
+    x = bf16_round(torch.randn(N, C, *din, device="cuda", generator=g)).requires_grad_(True)
+    ref = F.interpolate(x, size=dout, mode="trilinear", align_corners=False)
+    dcat = bf16_round(torch.randn(N, Cs + C, *dout, device="cuda", generator=g))
+    ref.backward(dcat[:, Cs:])
+    win = ops.ActView(to_ndhwc(dcat), N, *dout, C, ld=Cs + C, coff=Cs)
+    dx = ops.upcat_bwd(win, *din)
+    torch.cuda.synchronize()
+    e = rel_l2(from_view(dx), x.grad)
+    assert e < 4e-3, e
+    if N == 1:
+        r = bf16_round(torch.randn(1, C, *din, device="cuda", generator=g).relu())
+        dx2, acc = ops.upcat_bwd(win, *din, stat_r=ops.ActView(to_ndhwc(r), 1, *din, C))
+        torch.cuda.synchronize()
+        assert torch.equal(dx.buf, dx2.buf)
+        a4 = acc.view(C, 4).double()
+        o = dx2.buf.double().reshape(-1, C)
+        rr = to_ndhwc(r).double().reshape(-1, C)
+        assert torch.allclose(a4[:, 0] + a4[:, 1] / 2.0 ** 32, o.sum(0), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(a4[:, 2] + a4[:, 3] / 2.0 ** 32, (o * rr).sum(0), rtol=1e-5, atol=1e-3)
+        dx3, _ = ops.upcat_bwd(win, *din, stat_r=ops.ActView(to_ndhwc(r), 1, *din, C))   # bit-identical run to run
+        torch.cuda.synchronize()
+        assert torch.equal(dx2.buf, dx3.buf)
+
+
 def _head_inputs(seed, N=1, D=6, H=7, W=8, Cin=64, Cout=56, frac=0.2):
     g = torch.Generator(device="cuda").manual_seed(seed)
     x = bf16_round(torch.randn(N, Cin, D, H, W, device="cuda", generator=g))

@@ -54,6 +54,8 @@ def main():
     for name, cin, cout, lvl in LAYERS:
         if only and only not in name:
             continue
+        if only == "bw":
+            break
         D, H, W = DIMS[lvl]
         x = ops.ActView(torch.randn(1, D, H, W, cin, device="cuda").to(torch.bfloat16), 1, D, H, W, cin)
         dy = ops.ActView(torch.randn(1, D, H, W, cout, device="cuda").to(torch.bfloat16), 1, D, H, W, cout)
@@ -76,7 +78,7 @@ def main():
         if t > 0:
             print("TOTAL %s: %.1f GF in %.3f ms = %.1f TF/s (%.1f%% of measured burst %.0f)" %
                   (k, f / 1e9, t * 1e3, f / t / 1e12, 100 * f / t / 1e12 / PEAKS["bf16_tflops"], PEAKS["bf16_tflops"]))
-    if only:
+    if only and only != "bw":
         return
     # bandwidth kernels at full resolution
     D, H, W = DIMS[0]
@@ -108,6 +110,16 @@ def main():
     print("upcat_fwd 128ch: %.3f ms  %.0f GB/s" % (t * 1e3, (V * 128 * 2 * 1.125) / t / 1e9))
     t = timeit(lambda: ops.upcat_bwd(cat.window(64, 128), 48, 56, 48))
     print("upcat_bwd 128ch: %.3f ms  %.0f GB/s" % (t * 1e3, (V * 128 * 2 * 1.125) / t / 1e9))
+    rr = ops.ActView(torch.randn(1, 48, 56, 48, 128, device="cuda").abs().to(torch.bfloat16), 1, 48, 56, 48, 128)
+    pool = ops.StatPool("cuda")
+    t = timeit(lambda: (pool.reset(), ops.upcat_bwd(cat.window(64, 128), 48, 56, 48, stat_r=rr, pool=pool)))
+    print("upcat_bwd 128ch + stats: %.3f ms  %.0f GB/s" % (t * 1e3, (V * 128 * 2 * 1.25) / t / 1e9))
+    for (cc, dims) in ((256, (24, 28, 24)), (512, (12, 14, 12))):
+        fine = ops.ActView.alloc(1, 2 * dims[0], 2 * dims[1], 2 * dims[2], cc + cc // 2, "cuda")
+        fine.buf.normal_()
+        t = timeit(lambda: ops.upcat_bwd(fine.window(cc // 2, cc), *dims))
+        print("upcat_bwd %dch coarse %s: %.3f ms  %.0f GB/s" % (cc, dims, t * 1e3,
+              (8 * dims[0] * dims[1] * dims[2] * cc * 2 * 1.125) / t / 1e9))
     dp = ops.ActView.alloc(1, 48, 56, 48, 64, "cuda")
     t = timeit(lambda: ops.maxpool3d_bwd_add(cat.window(0, 64), cat.window(0, 64), dp))
     print("pool_bwd_add 64ch: %.3f ms  %.0f GB/s" % (t * 1e3, (V * 64 * 2 * 3.125) / t / 1e9))
