@@ -58,6 +58,14 @@ SIGNATURES = {
     "b2_match_voxels_workspace_bytes": (_ll, [_i]),
     "b2_match_voxels": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _ll, _vp]),
     "b2_esi_counts": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),
+    "b2_exact_split3": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp]),
+    "b2_exact_split_first": (_i, [_vp, _ll, _vp, _vp]),
+    "b2_exact_gn_workspace_bytes": (_ll, [_i]),
+    "b2_exact_gn_stats": (_i, [_vp, _ll, _i, _i, _f, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "b2_exact_gn_apply": (_i, [_vp, _ll, _i, _vp, _vp, _i, _i, _vp]),
+    "b2_exact_maxpool": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "b2_exact_upsample": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b2_exact_head_gather": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "b2_step_metrics": (_i, [_vp, _vp, _ll, _i, _vp, _vp, C.c_double, _vp, _vp]),
 }
 

@@ -496,6 +496,104 @@ class UNet3D(nn.Module):
             return ops.head_gather(feat, index, hw, hb, softmax=True, x_scale_shift=xss)
 
 
+def _exact_methods():
+    """exact-label inference: split-precision forward (see csrc/exact.cu)"""
+
+    def _exact_packs(self):
+        L = self._layers()
+        key = tuple((l.conv.weight._version, l.conv.weight.data_ptr()) for l in L)
+        cache = self.__dict__.get("_exact_pack_cache")
+        if cache is not None and cache[0] == key:
+            return cache[1]
+        packs = []
+        with torch.no_grad():
+            for l in L:
+                w = l.conv.weight.detach().float()
+                hi = w.to(torch.bfloat16).float()
+                lo = (w - hi).to(torch.bfloat16).float()
+                if l.cin == 1:
+                    w3 = torch.zeros((l.cout, 32, 3, 3, 3), dtype=torch.float32, device=w.device)
+                    w3[:, 0] = hi[:, 0]
+                    w3[:, 1] = lo[:, 0]
+                else:
+                    w3 = torch.cat([hi, hi, lo], dim=1).contiguous()
+                packs.append(ops.pack_conv_weights(w3, want_dgrad=False)[0])
+        self.__dict__["_exact_pack_cache"] = (key, packs)
+        return packs
+
+    def _exact_trunk(self, x):
+        """x fp32 [1,1,D,H,W] -> fp32 features [V, f] (NDHWC) of the last decoder block"""
+        if x.shape[0] != 1:
+            raise RuntimeError("unetsulc_b200.UNet3D: exact inference handles one volume per call")
+        L = self._layers()
+        packs = self._exact_packs()
+        G = self.num_groups
+        f = self.init_channel_number
+        _, _, D0, H0, W0 = x.shape
+        dims = [(D0, H0, W0)]
+        for _ in range(3):
+            d, h, w = dims[-1]
+            dims.append((d // 2, h // 2, w // 2))
+        if min(dims[3]) < 1:
+            raise RuntimeError("unetsulc_b200.UNet3D: volume %s too small for 3 poolings" % ((D0, H0, W0),))
+        dev = x.device
+        skip_c = [f, 2 * f, 4 * f]
+        up_c = [2 * f, 4 * f, 8 * f]
+        vol = [d * h * w for d, h, w in dims]
+        cats = [torch.empty((vol[l], skip_c[l] + up_c[l]), dtype=torch.float32, device=dev) for l in range(3)]
+
+        def conv_gn(i, xs, cin3, out, ld, off):
+            layer = L[i]
+            r = ops.exact_conv(xs, packs[i], cin3, layer.cout, relu=True)
+            ops.exact_gn(r, G, layer.norm.eps, layer.norm.weight.detach().float(), layer.norm.bias.detach().float(),
+                         out, ld, off)
+
+        def block(i, src, ld, off, cin, lvl, out, out_ld, out_off):
+            """two (conv, relu, gn) layers i, i+1 at level lvl; src = fp32 [V, ld] window or None for the network input"""
+            d, h, w = dims[lvl]
+            if src is None:
+                xs, cin3 = ops.exact_split_first(x, d, h, w), 32
+            else:
+                xs, cin3 = ops.exact_split3(src, ld, off, cin, d, h, w), 3 * cin
+            c1 = L[i].cout
+            y1 = torch.empty((vol[lvl], c1), dtype=torch.float32, device=dev)
+            conv_gn(i, xs, cin3, y1, c1, 0)
+            xs2 = ops.exact_split3(y1, c1, 0, c1, d, h, w)
+            conv_gn(i + 1, xs2, 3 * c1, out, out_ld, out_off)
+
+        cur, cur_c = None, 1
+        for lvl in range(4):
+            if lvl < 3:
+                block(2 * lvl, cur, cur_c, 0, cur_c, lvl, cats[lvl], skip_c[lvl] + up_c[lvl], 0)
+                cur = ops.exact_maxpool(cats[lvl], skip_c[lvl] + up_c[lvl], 0, skip_c[lvl], *dims[lvl])
+                cur_c = skip_c[lvl]
+            else:
+                out = torch.empty((vol[3], 8 * f), dtype=torch.float32, device=dev)
+                block(6, cur, cur_c, 0, cur_c, 3, out, 8 * f, 0)
+                cur, cur_c = out, 8 * f
+        li = 8
+        for lvl in (2, 1, 0):
+            ld = skip_c[lvl] + up_c[lvl]
+            ops.exact_upsample(cur, cur_c, dims[lvl + 1], cats[lvl], ld, skip_c[lvl], dims[lvl])
+            cout = L[li + 1].cout
+            out = torch.empty((vol[lvl], cout), dtype=torch.float32, device=dev)
+            block(li, cats[lvl], ld, 0, ld, lvl, out, cout, 0)
+            cur, cur_c = out, cout
+            li += 2
+        return cur
+
+    def _exact_scores_at(self, x, index):
+        with torch.no_grad():
+            hw, hb = self._head_effective()
+            feat = self._exact_trunk(x)
+            return ops.exact_head_gather(feat, index, hw.detach(), hb.detach(), softmax=True)
+
+    return _exact_packs, _exact_trunk, _exact_scores_at
+
+
+UNet3D._exact_packs, UNet3D._exact_trunk, UNet3D._exact_scores_at = _exact_methods()
+
+
 def _needs(ctx_needs, offset):
     return list(ctx_needs[offset:offset + 42])
 

@@ -673,3 +673,75 @@ def esi_counts(y_true, y_pred, n_classes, counts=None):
                                  _p(counts), _s()), "b2_esi_counts")
     _count(1)
     return counts
+
+
+# ---------------------------------------------------------------------------------------------------- exact inference
+F32 = torch.float32
+
+
+def exact_split3(x, ld, off, C, D, H, W):
+    """fp32 [V, ld] channel window [off, off + C) -> ActView bf16 [1, D, H, W, 3C] = [hi | lo | hi]"""
+    lib = _lib.load()
+    V = D * H * W
+    out = ActView.alloc(1, D, H, W, 3 * C, x.device)
+    _lib.check(lib.b2_exact_split3(_p(x), V, C, ld, off, _p(out.buf), _s()), "b2_exact_split3")
+    _count(1)
+    return out
+
+
+def exact_split_first(x, D, H, W):
+    """network input fp32 [1, 1, D, H, W] -> ActView bf16 [1, D, H, W, 32] = [x, x, 0 ...]"""
+    lib = _lib.load()
+    out = ActView.alloc(1, D, H, W, 32, x.device)
+    _lib.check(lib.b2_exact_split_first(_p(x), D * H * W, _p(out.buf), _s()), "b2_exact_split_first")
+    _count(1)
+    return out
+
+
+def exact_conv(xsplit, wpack, cin3, cout, relu=True):
+    """split-operand 3x3x3 conv on the tcgen05 implicit-GEMM kernel, fp32 output [V, cout] (+ ReLU)"""
+    dev = xsplit.buf.device
+    r = torch.empty((xsplit.V, cout), dtype=F32, device=dev)
+    y = ActView(r, 1, xsplit.D, xsplit.H, xsplit.W, cout)
+    conv3d_igemm(xsplit, wpack, y, cin3, cout, relu=relu, y_fp32=True)
+    return r
+
+
+def exact_gn(r, groups, eps, gamma, beta, out, ld, off):
+    """GroupNorm(groups, C) of the fp32 [V, C] tensor r (fp64 statistics) written to out[:, off:off+C] (fp32 [V, ld])"""
+    lib = _lib.load()
+    V, Cc = r.shape
+    ss = torch.empty((Cc, 2), dtype=F32, device=r.device)
+    ws = Workspace.get(lib.b2_exact_gn_workspace_bytes(Cc), r.device, "exgn")
+    _lib.check(lib.b2_exact_gn_stats(_p(r), V, Cc, groups, float(eps), _p(gamma), _p(beta), _p(ss), _p(ws), ws.numel(),
+                                     _s()), "b2_exact_gn_stats")
+    _lib.check(lib.b2_exact_gn_apply(_p(r), V, Cc, _p(ss), _p(out), ld, off, _s()), "b2_exact_gn_apply")
+    _count(3)
+
+
+def exact_maxpool(x, ld, off, C, D, H, W):
+    lib = _lib.load()
+    y = torch.empty(((D // 2) * (H // 2) * (W // 2), C), dtype=F32, device=x.device)
+    _lib.check(lib.b2_exact_maxpool(_p(x), 1, D, H, W, C, ld, off, _p(y), _s()), "b2_exact_maxpool")
+    _count(1)
+    return y
+
+
+def exact_upsample(x, C, din, out, ld, off, dout):
+    lib = _lib.load()
+    _lib.check(lib.b2_exact_upsample(_p(x), 1, din[0], din[1], din[2], C, _p(out), ld, off, dout[0], dout[1], dout[2],
+                                     _s()), "b2_exact_upsample")
+    _count(1)
+
+
+def exact_head_gather(feat, index, W, b, softmax=True):
+    lib = _lib.load()
+    cout, cin = W.shape[0], W.shape[1]
+    n = index.numel()
+    scores = torch.empty((n, cout), dtype=F32, device=feat.device)
+    preds = torch.empty(n, dtype=torch.int32, device=feat.device)
+    Wc = W.reshape(cout, cin).contiguous().float()
+    _lib.check(lib.b2_exact_head_gather(_p(feat), _p(index.contiguous()), n, _p(Wc), _p(b.contiguous().float()), cin,
+                                        cout, int(softmax), _p(scores), _p(preds), _s()), "b2_exact_head_gather")
+    _count(1)
+    return scores, preds

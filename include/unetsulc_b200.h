@@ -187,6 +187,28 @@ int b2_esi_counts(const int* y_true, const int* y_pred, long long n, int C, unsi
 int b2_step_metrics(const long long* labels, const int* preds, long long n, int C, unsigned long long* counts,
                     const float* loss, double loss_weight, double* loss_acc, cudaStream_t stream);
 
+/* ---- exact-label inference mode (labeling(), pattern_class.py:262-277, with fp32-accurate scores) ------------------
+ * fp32 activations throughout; every 3x3x3 conv runs on b2_conv3d_igemm (y_is_fp32 = 1) over split operands:
+ * b2_exact_split3 turns an fp32 channel window [V][C] into bf16 [V][3C] = [hi | lo | hi] (hi = bf16(x), lo =
+ * bf16(x - hi)), paired with weights packed as [w_hi | w_hi | w_lo]: x*w to 2^-16 relative with fp32 accumulation.
+ * b2_exact_split_first does the same for the binary network input: bf16 [V][32] = [x, x, 0 ...] against
+ * [w_hi, w_lo, 0 ...].  The remaining operators are fp32: GroupNorm with fp64 statistics (deterministic two-stage
+ * reduction; scale_shift fp32 [C][2]), MaxPool3d(2), trilinear upsample (align_corners=False) into a concat window,
+ * and the 1x1x1 head + Softmax + arg-max at gathered voxels.  All tensors NDHWC, one sample.                        */
+int b2_exact_split3(const float* x, long long V, int C, int ldx, int xoff, void* out, cudaStream_t stream);
+int b2_exact_split_first(const float* x, long long V, void* out, cudaStream_t stream);
+long long b2_exact_gn_workspace_bytes(int C);
+int b2_exact_gn_stats(const float* r, long long V, int C, int G, float eps, const float* gamma, const float* beta,
+                      float* scale_shift, void* workspace, long long workspace_bytes, cudaStream_t stream);
+int b2_exact_gn_apply(const float* r, long long V, int C, const float* scale_shift, float* y, int ldy, int yoff,
+                      cudaStream_t stream);
+int b2_exact_maxpool(const float* x, int N, int D, int H, int W, int C, int ldx, int xoff, float* y,
+                     cudaStream_t stream);
+int b2_exact_upsample(const float* x, int N, int Di, int Hi, int Wi, int C, float* y, int ldy, int yoff, int Do, int Ho,
+                      int Wo, cudaStream_t stream);
+int b2_exact_head_gather(const float* x, const long long* index, long long n, const float* W, const float* b, int Cin,
+                         int Cout, int softmax, float* scores, int* preds, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
