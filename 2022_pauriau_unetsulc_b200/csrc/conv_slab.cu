@@ -40,13 +40,17 @@ struct SlabParams {
 };
 
 static constexpr int kSlabThreads = 32 * 12;
-static constexpr int kTW = 32, kTH = 4, kTD = 4;
-static constexpr int kPlaneRows = kTW * (kTH + 2);   // 192
+static constexpr int kTD = 4;
 
-template <int KC>
+// kTW x kTH x kTD output tile with kTW * kTH = 128 voxels per plane: 32 x 4 (round 1) or 16 x 8 — the second shape cuts
+// the tile-quantisation waste of volumes whose W is not a multiple of 32 (bounding boxes of real cohorts: W = 72 pads to
+// 80 instead of 96).  Both keep every h-tap offset (kTW rows) a multiple of the 8-row swizzle atom.
+template <int KC, int kTW>
 __global__ void __launch_bounds__(kSlabThreads, 1)
 conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                    const SlabParams p) {
+  constexpr int kTH = 128 / kTW;
+  constexpr int kPlaneRows = kTW * (kTH + 2);
   pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -195,7 +199,9 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   } else if (warp >= 8) {
     // ---------------------------------------------------------------- epilogue
-    const int q = warp & 3;           // lane quarter == h-line within the tile
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;    // accumulator row == voxel within the output plane: (h-line, w)
+    const int lw = row % kTW, lh = row / kTW;
     float st_s[2] = {0.f, 0.f}, st_q[2] = {0.f, 0.f};
     // every MMA accumulates: clear both accumulator sets once, then hand them to the MMA issuer
     for (uint32_t c = 0; c < 512; c += 32) tmem_st32_zero(tmem_base + ((uint32_t)(q * 32) << 16) + c);
@@ -211,7 +217,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int h0 = (t % p.tiles_h) * kTH;
       const int d0 = (t / p.tiles_h) * kTD;
       const uint32_t acc = it & 1u;
-      const int w = w0 + lane, h = h0 + q;
+      const int w = w0 + lw, h = h0 + lh;
       mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
       tc_fence_after();
       for (int o = 0; o < kTD; ++o) {
@@ -302,14 +308,33 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   }
 }
 
-// host: is the slab kernel applicable / worthwhile for this layer?
+// host: tile shape with the least padding, and whether the slab kernel is worthwhile for this layer.
+// Padded voxels cost MMA time; the alternative for these narrow-N layers is the plain implicit GEMM at ~35-45 % of the
+// tensor peak against ~85 % here, so the slab kernel wins up to ~1.5x padding.  (Round 1 bailed out above 1.12x with a
+// single 32 x 4 x 4 tile: bounding boxes such as 80 x 104 x 72 fell back to the slow path.)
+static long long slab_padded(int D, int H, int W, int tw) {
+  const int th = 128 / tw;
+  return (long long)ceil_div(W, tw) * tw * ceil_div(H, th) * th * ceil_div(D, kTD) * kTD;
+}
+static int slab_tile_w(int D, int H, int W) { return slab_padded(D, H, W, 16) < slab_padded(D, H, W, 32) ? 16 : 32; }
+
 bool slab_applicable(int N, int D, int H, int W, int Cin, int Cout, int y_is_fp32) {
   if (y_is_fp32) return false;
   if (!(Cout == 32 || Cout == 64)) return false;
   if (!(Cin % 64 == 0 || Cin == 32)) return false;
-  const long long padded = (long long)ceil_div(W, kTW) * kTW * ceil_div(H, kTH) * kTH * ceil_div(D, kTD) * kTD;
-  if (padded * 100 > (long long)W * H * D * 112) return false;   // <= 12 % tile-quantisation waste
+  const long long padded = slab_padded(D, H, W, slab_tile_w(D, H, W));
+  if (padded * 100 > (long long)W * H * D * 150) return false;
   return true;
+}
+
+template <int KC, int TW>
+static int launch_slab_t(const CUtensorMap& ta, const CUtensorMap& tb, const SlabParams& p, size_t smem_bytes,
+                         cudaStream_t stream) {
+  long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab_kernel<KC, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_LAUNCH((conv3d_slab_kernel<KC, TW>), (unsigned)grid, kSlabThreads, smem_bytes, stream, ta, tb, p);
+  B2_CHECK_CUDA(cudaGetLastError());
+  return B2_OK;
 }
 
 int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, int ldy, int y_coff, int N, int D,
@@ -318,9 +343,10 @@ int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, 
   SlabParams p;
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   const int KC = (Cin % 64 == 0) ? 64 : 32;
+  const int tw = slab_tile_w(D, H, W), th = 128 / tw;
   p.n_chunks = Cin / KC;
-  p.tiles_w = ceil_div(W, kTW);
-  p.tiles_h = ceil_div(H, kTH);
+  p.tiles_w = ceil_div(W, tw);
+  p.tiles_h = ceil_div(H, th);
   p.tiles_d = ceil_div(D, kTD);
   p.relu = relu;
   p.ldy = ldy; p.y_coff = y_coff;
@@ -329,7 +355,7 @@ int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, 
   p.stat_acc = stat_acc;
   p.stat_r = reinterpret_cast<const __nv_bfloat16*>(stat_r);
   if (stat_acc) B2_REQUIRE(N == 1, "b2_conv3d_igemm_stats: fused statistics need batch 1");
-  const int plane_bytes = kPlaneRows * KC * 2;
+  const int plane_bytes = tw * (th + 2) * KC * 2;
   const int b_bytes = 9 * Cout * KC * 2;
   const int budget = 227 * 1024 - 1024 - 512;
   p.stages = (budget - 2 * b_bytes) / plane_bytes;
@@ -337,7 +363,7 @@ int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, 
   if (p.stages > 9) p.stages = 9;
   B2_REQUIRE(p.stages >= 3, "conv3d_slab: tile does not fit shared memory");
   CUtensorMap ta, tb;
-  int rc = make_act_tmap(&ta, x, N, D, H, W, Cin, ldx, x_coff, KC, kTW, kTH + 2, 1);
+  int rc = make_act_tmap(&ta, x, N, D, H, W, Cin, ldx, x_coff, KC, tw, th + 2, 1);
   if (rc) return rc;
   {
     const uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)27 * Cout};
@@ -347,16 +373,10 @@ int launch_slab(const void* x, int ldx, int x_coff, const void* wpack, void* y, 
     if (rc) return rc;
   }
   const size_t smem_bytes = 2 * (size_t)b_bytes + (size_t)p.stages * plane_bytes + 1024 + 512;
-  long long grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  if (KC == 64) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B2_LAUNCH(conv3d_slab_kernel<64>, (unsigned)grid, kSlabThreads, smem_bytes, stream, ta, tb, p);
-  } else {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B2_LAUNCH(conv3d_slab_kernel<32>, (unsigned)grid, kSlabThreads, smem_bytes, stream, ta, tb, p);
-  }
-  B2_CHECK_CUDA(cudaGetLastError());
-  return B2_OK;
+  if (KC == 64) return tw == 32 ? launch_slab_t<64, 32>(ta, tb, p, smem_bytes, stream)
+                                : launch_slab_t<64, 16>(ta, tb, p, smem_bytes, stream);
+  return tw == 32 ? launch_slab_t<32, 32>(ta, tb, p, smem_bytes, stream)
+                  : launch_slab_t<32, 16>(ta, tb, p, smem_bytes, stream);
 }
 
 }  // namespace b2

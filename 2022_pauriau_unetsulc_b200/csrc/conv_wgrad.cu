@@ -213,23 +213,36 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 
 // dW[co][ci][tap] = sum_s ws[s][tap][ci][co]: block = (32-wide co tile, 8-wide ci tile), all 27 taps; reads run along
 // co (128-byte runs), writes run along (ci, tap) (864-byte runs) through a padded shared-memory transpose.
+// 27 elements per thread: the loads of 9 elements (x splits) are issued before any is consumed (round 1 walked them one
+// dependent load at a time: 28 us for 5.3 M elements, 1.5 TB/s).
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int Cin, int Cout) {
   pdl_prologue();
   __shared__ float t[32 * 217];
   const int co0 = blockIdx.x * 32, ci0 = blockIdx.y * 8;
   const long long total = 27LL * Cin * Cout;
-  for (int e = threadIdx.x; e < 27 * 8 * 32; e += 256) {
-    const int co = e & 31, ci = (e >> 5) & 7, tap = e >> 8;
-    const long long src = ((long long)tap * Cin + ci0 + ci) * Cout + co0 + co;
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += ws[(long long)s * total + src];
-    t[co * 217 + ci * 27 + tap] = acc;
+  const int co = threadIdx.x & 31, ci = (threadIdx.x >> 5) & 7;
+  const float* src = ws + ((long long)(ci0 + ci)) * Cout + co0 + co;
+  const long long tap_stride = (long long)Cin * Cout;
+#pragma unroll
+  for (int t0 = 0; t0 < 27; t0 += 9) {
+    float acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      float v[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) v[k] = __ldcg(src + (long long)s * total + (t0 + k) * tap_stride);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[k] += v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) t[co * 217 + ci * 27 + t0 + k] = acc[k];
   }
   __syncthreads();
   for (int e = threadIdx.x; e < 32 * 216; e += 256) {
-    const int co = e / 216, r = e % 216;   // r = ci*27 + tap
-    dw[((long long)(co0 + co) * Cin + ci0) * 27 + r] = t[co * 217 + r];
+    const int c = e / 216, r = e % 216;   // r = ci*27 + tap
+    dw[((long long)(co0 + c) * Cin + ci0) * 27 + r] = t[c * 217 + r];
   }
 }
 
@@ -423,7 +436,7 @@ extern "C" int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* d
     B2_LAUNCH(wgrad_reduce_par_kernel<0>, (unsigned)((total + 31) / 32), 256, 0, stream, p.ws, dw, p.splits, Cin, Cout);
   } else if (swap) {
     B2_LAUNCH(wgrad_reduce_swapped_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, p.ws, dw, p.splits, Cin, Cout);
-  } else if ((Cout / 32) * (Cin / 8) >= 2 * num_sms()) {
+  } else if ((Cout / 32) * (Cin / 8) >= num_sms()) {
     B2_LAUNCH(wgrad_reduce_kernel, dim3(Cout / 32, Cin / 8), 256, 0, stream, p.ws, dw, p.splits, Cin, Cout);
   } else {
     B2_LAUNCH(wgrad_reduce_simple_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, p.ws, dw, p.splits, Cin, Cout);

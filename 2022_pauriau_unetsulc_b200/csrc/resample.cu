@@ -39,15 +39,14 @@ __device__ __forceinline__ void block_bstats_commit(const float (&s)[8], const f
   }
 }
 __device__ __forceinline__ void bstats_accumulate(float (&s)[8], float (&q)[8], const uint4& stored, const uint4& rr) {
-  const f8 g = unpack8(stored), x = unpack8(rr);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { s[k] += g.v[k]; q[k] = fmaf(g.v[k], x.v[k], q[k]); }
+  fma8_bf16(s, stored, (unsigned short)0x3f80);   // s += g * 1
+  fma8_bf16_vv(q, stored, rr);                    // q += g * r   (FHFMA.BF16: no unpacking)
 }
 
 // out[v, c] = dskip[v, c] + (v is the arg-max of its 2x2x2 cell ? dpool[cell, c] : 0)
 // arg-max is recomputed from the stored forward tensor y; first maximum in (d, h, w) scan order wins, as in
 // PyTorch's max_pool3d_with_indices.
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 2)
 pool_bwd_add_kernel(const __nv_bfloat16* __restrict__ y, int ldy, int y_coff, const __nv_bfloat16* __restrict__ dskip,
                     int ldd, int d_coff, const __nv_bfloat16* __restrict__ dpool, __nv_bfloat16* __restrict__ out,
                     int N, int D, int H, int W, int C, const __nv_bfloat16* __restrict__ stat_r,
@@ -69,44 +68,50 @@ pool_bwd_add_kernel(const __nv_bfloat16* __restrict__ y, int ldy, int y_coff, co
     const int cd = (int)(t % Dc);
     const int n = (int)(t / Dc);
     const bool pooled = (cd < Dp && ch < Hp && cw < Wp);
-    int arg[8];
-    f8 gp;
+    // packed bf16x2 arithmetic throughout (HMNMX2 / HSET2 / HFMA2): the channel-wise maximum of the 8 voxels, then the
+    // FIRST voxel in (d, h, w) scan order that equals it takes the pooled gradient (PyTorch's max_pool3d_with_indices:
+    // a later voxel replaces the running maximum only if strictly greater), added to the skip gradient with one
+    // correctly rounded bf16 add.  No unpacking to fp32: ~2x fewer instructions than the fp32 form.
+    uint32_t mx[4] = {0u, 0u, 0u, 0u}, gp[4] = {0u, 0u, 0u, 0u}, found[4] = {0u, 0u, 0u, 0u};
+    uint4 yv[8];
     if (pooled) {
-      float mx[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { mx[k] = -INFINITY; arg[k] = 0; }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int d = 2 * cd + (j >> 2), h = 2 * ch + ((j >> 1) & 1), w = 2 * cw + (j & 1);
         const long long v = (((long long)n * D + d) * H + h) * W + w;
-        const f8 x = unpack8(ldg16(y + v * ldy + y_coff + oct * 8));
+        yv[j] = ldg16(y + v * ldy + y_coff + oct * 8);
+      }
+      mx[0] = yv[0].x; mx[1] = yv[0].y; mx[2] = yv[0].z; mx[3] = yv[0].w;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (x.v[k] > mx[k]) { mx[k] = x.v[k]; arg[k] = j; }
+      for (int j = 1; j < 8; ++j) {
+        mx[0] = bf2_max(mx[0], yv[j].x); mx[1] = bf2_max(mx[1], yv[j].y);
+        mx[2] = bf2_max(mx[2], yv[j].z); mx[3] = bf2_max(mx[3], yv[j].w);
       }
       const long long pv = (((long long)n * Dp + cd) * Hp + ch) * Wp + cw;
-      gp = unpack8(ldg16(dpool + pv * C + oct * 8));
+      const uint4 g4 = ldg16(dpool + pv * C + oct * 8);
+      gp[0] = g4.x; gp[1] = g4.y; gp[2] = g4.z; gp[3] = g4.w;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int d = 2 * cd + (j >> 2), h = 2 * ch + ((j >> 1) & 1), w = 2 * cw + (j & 1);
       if (d < D && h < H && w < W) {
         const long long v = (((long long)n * D + d) * H + h) * W + w;
-        f8 g;
-        if (dskip) {
-          g = unpack8(ldg16(dskip + v * ldd + d_coff + oct * 8));
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) g.v[k] = 0.f;
-        }
+        uint4 g = make_uint4(0u, 0u, 0u, 0u);
+        if (dskip) g = ldg16(dskip + v * ldd + d_coff + oct * 8);
         if (pooled) {
+          const uint32_t yw[4] = {yv[j].x, yv[j].y, yv[j].z, yv[j].w};
+          uint32_t add[4];
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (arg[k] == j) g.v[k] += gp.v[k];
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t eq = bf2_eq_mask(yw[k], mx[k]) & ~found[k];
+            found[k] |= eq;
+            add[k] = gp[k] & eq;
+          }
+          g.x = bf2_add(g.x, add[0]); g.y = bf2_add(g.y, add[1]);
+          g.z = bf2_add(g.z, add[2]); g.w = bf2_add(g.w, add[3]);
         }
-        const uint4 pk = pack8(g);
-        stg16(out + v * C + oct * 8, pk);
-        if (stat_acc != nullptr) bstats_accumulate(st_s, st_q, pk, ldg16(stat_r + v * C + oct * 8));
+        stg16(out + v * C + oct * 8, g);
+        if (stat_acc != nullptr) bstats_accumulate(st_s, st_q, g, ldg16(stat_r + v * C + oct * 8));
       }
     }
   }

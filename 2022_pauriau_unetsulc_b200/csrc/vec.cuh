@@ -51,6 +51,32 @@ __device__ __forceinline__ void fma8_bf16(float (&acc)[8], const uint4& u, unsig
       : "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w), "h"(w));
 }
 
+// acc[k] += u[k] * v[k] for two 16-byte vectors of 8 bf16 values (exact products, fp32 accumulation)
+__device__ __forceinline__ void fma8_bf16_vv(float (&acc)[8], const uint4& u, const uint4& v) {
+  asm("{\n\t.reg .b16 l0, h0, l1, h1, l2, h2, l3, h3, m0, n0, m1, n1, m2, n2, m3, n3;\n\t"
+      "mov.b32 {l0, h0}, %8;\n\tmov.b32 {l1, h1}, %9;\n\tmov.b32 {l2, h2}, %10;\n\tmov.b32 {l3, h3}, %11;\n\t"
+      "mov.b32 {m0, n0}, %12;\n\tmov.b32 {m1, n1}, %13;\n\tmov.b32 {m2, n2}, %14;\n\tmov.b32 {m3, n3}, %15;\n\t"
+      "fma.rn.f32.bf16 %0, l0, m0, %0;\n\tfma.rn.f32.bf16 %1, h0, n0, %1;\n\t"
+      "fma.rn.f32.bf16 %2, l1, m1, %2;\n\tfma.rn.f32.bf16 %3, h1, n1, %3;\n\t"
+      "fma.rn.f32.bf16 %4, l2, m2, %4;\n\tfma.rn.f32.bf16 %5, h2, n2, %5;\n\t"
+      "fma.rn.f32.bf16 %6, l3, m3, %6;\n\tfma.rn.f32.bf16 %7, h3, n3, %7;\n\t}"
+      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]), "+f"(acc[6]), "+f"(acc[7])
+      : "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
+// packed bf16x2 helpers on raw 32-bit words (HMNMX2 / HSET2 / HFMA2 .BF16_V2: one instruction per pair)
+__device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t bf2_eq_mask(uint32_t a, uint32_t b) {   // 0xffff per equal half
+  return __heq2_mask(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+}
+__device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) {       // correctly rounded bf16 sums
+  __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
 // 16-byte shared-memory load through an explicit shared-window address (pointers derived from an aligned dynamic
 // shared-memory base by integer arithmetic lose their address space and would compile to generic LD)
 __device__ __forceinline__ uint4 lds16(uint32_t saddr) {

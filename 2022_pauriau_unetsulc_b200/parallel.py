@@ -10,8 +10,11 @@ the reference run with gradient accumulation over W subjects divided by W.  Grou
 normalisation is unchanged by the partitioning.
 
 Buckets (fp32, 65.3 MB in total), in the order backward produces them:
-  0: final_conv + decoders.2 + decoders.1      (2.2 M)      2: encoders.3            (5.3 M)
-  1: decoders.0                                (7.1 M)      3: encoders.2/1/0        (1.7 M)
+  0: final_conv + decoders.2 + decoders.1      (2.2 M)      3: encoders.2 + encoders.1   (1.66 M)
+  1: decoders.0                                (7.1 M)      4: encoders.0                (56 k)
+  2: encoders.3                                (5.3 M)
+The last bucket closes when backward ends, so its all-reduce is fully exposed in front of the optimiser step: it holds
+only encoders.0 (225 KB, latency-bound).  Round 1 had encoders.2/1/0 (6.8 MB) there.
 Gradients are written by the wgrad / GroupNorm-backward kernels directly into views of the flat bucket (no copy);
 when the last layer of a bucket reports ready, an event is recorded on the compute stream and the all-reduce is
 enqueued on a dedicated communication stream.  ``finish()`` makes the compute stream wait for all of them.
@@ -20,9 +23,10 @@ import torch
 import torch.distributed as dist
 
 # layer index (0..13 trunk conv layers in forward order, 14 = head) -> bucket id
-_BUCKET_OF_LAYER = {14: 0, 13: 0, 12: 0, 11: 0, 10: 0, 9: 1, 8: 1, 7: 2, 6: 2, 5: 3, 4: 3, 3: 3, 2: 3, 1: 3, 0: 3}
+_BUCKET_OF_LAYER = {14: 0, 13: 0, 12: 0, 11: 0, 10: 0, 9: 1, 8: 1, 7: 2, 6: 2, 5: 3, 4: 3, 3: 3, 2: 3, 1: 4, 0: 4}
+N_BUCKETS = 5
 # the layer whose completion closes each bucket (backward runs 14, 13, ..., 0)
-_LAST_LAYER_OF_BUCKET = {0: 10, 1: 8, 2: 6, 3: 0}
+_LAST_LAYER_OF_BUCKET = {0: 10, 1: 8, 2: 6, 3: 2, 4: 0}
 
 
 def layer_of_param(i):
@@ -43,7 +47,7 @@ class BucketedGradReducer(object):
             # weights or the averaged gradients are taken at different points and the replicas never agree
             broadcast_parameters(model, process_group)
         self.params = params
-        sizes = [0, 0, 0, 0]
+        sizes = [0] * N_BUCKETS
         self.slot = []
         for i, p in enumerate(params):
             b = _BUCKET_OF_LAYER[layer_of_param(i)]
@@ -72,7 +76,7 @@ class BucketedGradReducer(object):
         needs = [bool(p.requires_grad) for p in self.params]
         active_layers = sorted({layer_of_param(i) for i, n in enumerate(needs) if n})
         self._close_at = {}
-        for b in range(4):
+        for b in range(N_BUCKETS):
             layers = [l for l in active_layers if _BUCKET_OF_LAYER[l] == b]
             if layers:
                 self._close_at[min(layers)] = b    # backward visits layers in decreasing order

@@ -392,6 +392,10 @@ class UnetPatternSulciLabelling(object):
     # stream, so it still overlaps the rest of the backward pass; the last segment (fused SGD) is replayed after the
     # compute stream has waited for every all-reduce.
     use_cuda_graph = True
+    # data parallel: capture the NCCL all-reduces INSIDE the step's graph (fork / join of the communication stream is
+    # recorded by the capture) instead of cutting the step into segments around eager collectives: one replay per
+    # step.  B2_DP_CAPTURE_NCCL=0 selects the segmented form.
+    dp_capture_nccl = os.environ.get("B2_DP_CAPTURE_NCCL", "1") != "0"
     _graph_cache_limit = 8
     _graph_capture_after = 2      # eager sightings of a (shape, optimiser, mask) key before it is captured
 
@@ -460,7 +464,7 @@ class UnetPatternSulciLabelling(object):
         torch.cuda.synchronize()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            if reducer is not None:
+            if reducer is not None and not (self.dp_capture_nccl and reducer.world > 1):
                 reducer.segment_cb = cut
             # the loss is final once the head has run: a cut here lets train_step() read it back (and return, and
             # start the next step's H2D copies) while the backward pass of this step is still running

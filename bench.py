@@ -488,10 +488,34 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "torch_gpu": torch_gpu, "wall_s_timed_region": wall, "inference": inference,
         }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        print(json.dumps(line), flush=True)
+    _shutdown(world, [trainer])
     return 0
+
+
+def _shutdown(world, holders):
+    """Tears the process group down without ever hanging the launcher: captured CUDA graphs that contain NCCL kernels
+    are released first (destroying a communicator that live graphs still reference can block), and the destroy itself
+    runs under a watchdog."""
+    import gc
+    import torch
+    import torch.distributed as dist
+    if world <= 1:
+        return
+    for h in holders:
+        h.__dict__.pop("_graphs", None)
+        h.__dict__.pop("_graph_seen", None)
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(20)
+    if t.is_alive():
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_e2e_learning(args, world, rank, local, dev):
@@ -615,9 +639,8 @@ def run_inference(args):
                                    "hemispheres (two models), %d subjects per hemisphere, pairs round-robin over "
                                    "%d rank(s); wall clock incl. host point-list handling" % (S, world)},
             "clocks": clocks, "ceiling_ms": FWD_GFLOP / float(peaks.get("bf16_tflops", 1678.4)),
-            "threshold_scores_L_first": {str(k): v[0][:2] for k, v in sc.items()}}))
-    if world > 1:
-        dist.destroy_process_group()
+            "threshold_scores_L_first": {str(k): v[0][:2] for k, v in sc.items()}}), flush=True)
+    _shutdown(world, list(trainers.values()))
     return 0
 
 

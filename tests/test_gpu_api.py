@@ -197,7 +197,7 @@ def test_cuda_graph_step_matches_eager_step(tmp_path, segmented):
         losses = [t.train_step(*data[i % 3], opt, red) for i in range(6)]
         if segmented and use_graph:
             segs = next(iter(t._graphs.values()))[0]
-            assert [[a[0] for a in acts] for _, acts in segs] == [["loss"]] + [["reduce"]] * 3 + [
+            assert [[a[0] for a in acts] for _, acts in segs] == [["loss"]] + [["reduce"]] * 4 + [
                 ["reduce", "finish"], []]
         # an eager evaluation after graph replays must see the updated weights
         t.model.eval()

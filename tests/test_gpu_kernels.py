@@ -89,6 +89,10 @@ SLAB_SHAPES = [
     (1, 64, 32, 8, 12, 64),      # N = 32 (dgrad of encoders.0.conv2)
     (2, 64, 64, 8, 12, 60),      # ragged W edge (60 -> 64), batch 2
     (1, 64, 64, 4, 4, 32),       # a single tile: every plane touches the volume border
+    (1, 64, 64, 10, 13, 72),     # 16 x 8 x 4 tile shape (W = 72 pads to 80, not 96); ragged H and D edges
+    (1, 32, 64, 8, 16, 48),      # 16-wide tiles with 64-byte rows (KC = 32)
+    (1, 192, 64, 6, 9, 40),      # 16-wide tiles, 3 channel chunks, ragged everywhere
+    (1, 64, 32, 9, 11, 24),      # 16-wide tiles, N = 32
 ]
 
 

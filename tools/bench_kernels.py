@@ -97,6 +97,19 @@ def main():
         print("gn_apply+pool C=%3d: %.3f ms  %.0f GB/s" % (C, t * 1e3, (2 + 0.125) * V * C * 2 / t / 1e9))
         t = timeit(lambda: ops.relu_gn_bwd(y, r, 32, gamma, mr))
         print("gn_bwd    C=%3d: %.3f ms  %.0f GB/s (2 passes: 5 tensor sweeps)" % (C, t * 1e3, 5 * V * C * 2 / t / 1e9))
+    # the same bandwidth kernels at the coarser levels (launch / tail / latency effects)
+    for (C, dims) in ((64, DIMS[1]), (128, DIMS[1]), (128, DIMS[2]), (256, DIMS[2]), (512, DIMS[3])):
+        d_, h_, w_ = dims
+        Vl = d_ * h_ * w_
+        r = ops.ActView(torch.randn(1, d_, h_, w_, C, device="cuda").abs().to(torch.bfloat16), 1, d_, h_, w_, C)
+        gamma = torch.ones(C, device="cuda"); beta = torch.zeros(C, device="cuda")
+        mr, ss = ops.relu_gn_stats(r, 32, 1e-5, gamma, beta)
+        y = ops.ActView.alloc(1, d_, h_, w_, C, "cuda")
+        t = timeit(lambda: ops.relu_gn_apply(r, ss, y))
+        acc = torch.zeros(4 * C, dtype=torch.int64, device="cuda")
+        t2 = timeit(lambda: ops.relu_gn_bwd_from_stats(acc, y, r, 32, gamma, mr))
+        print("level %s C=%3d: gn_apply %.1f us %.0f GB/s | gn_bwd finalize+apply %.1f us %.0f GB/s"
+              % (dims, C, t * 1e6, 2 * Vl * C * 2 / t / 1e9, t2 * 1e6, 3 * Vl * C * 2 / t2 / 1e9))
     x = torch.zeros(1, 1, D, H, W, device="cuda"); x[torch.rand_like(x) < 0.03] = 1
     w = torch.randn(32, 1, 3, 3, 3, device="cuda")
     y = ops.ActView.alloc(1, D, H, W, 32, "cuda")
