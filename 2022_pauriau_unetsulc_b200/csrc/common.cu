@@ -90,6 +90,11 @@ bool pdl_enabled() {
   return on;
 }
 
+bool pdl_finalize_enabled() {
+  static const bool on = getenv("B2_PDL_FINALIZE") != nullptr;   // opt-in: measured +-0.7 % (noise), round 2
+  return on;
+}
+
 }  // namespace b2
 
 extern "C" const char* b2_last_error(void) { return b2::last_error(); }

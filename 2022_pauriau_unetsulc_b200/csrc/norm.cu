@@ -557,7 +557,7 @@ extern "C" int b2_relu_gn_finalize_acc(const long long* stat_acc, long long V, i
   int rc = check_gn_shape("b2_relu_gn_finalize_acc", 1, V, C, G);
   if (rc) return rc;
   B2_REQUIRE(C <= kMaxAccC, "b2_relu_gn_finalize_acc: C=%d > %d", C, kMaxAccC);
-  B2_LAUNCH(gn_finalize_acc_kernel, 1, (C + 31) / 32 * 32, 0, stream, stat_acc, C, G, 1.0 / ((double)V * (C / G)), eps,
+  B2_LAUNCH_DEP(gn_finalize_acc_kernel, 1, (C + 31) / 32 * 32, 0, stream, stat_acc, C, G, 1.0 / ((double)V * (C / G)), eps,
             gamma, beta, mean_rstd, scale_shift);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
@@ -571,12 +571,12 @@ extern "C" int b2_relu_gn_apply(const void* r, int N, int D, int H, int W, int C
   const long long V = (long long)D * H * W;
   if (pooled) {
     const long long total = (long long)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-    B2_LAUNCH(gn_apply_pool_kernel, ew_blocks(total), 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(r), N, D,
+    B2_LAUNCH_DEP(gn_apply_pool_kernel, ew_blocks(total), 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(r), N, D,
               H, W, C, scale_shift, reinterpret_cast<__nv_bfloat16*>(y), ldy, y_coff,
               reinterpret_cast<__nv_bfloat16*>(pooled));
   } else {
     B2_REQUIRE(256 % (C / 8) == 0, "b2_relu_gn_apply: C=%d unsupported", C);
-    B2_LAUNCH(gn_apply_kernel, dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream,
+    B2_LAUNCH_DEP(gn_apply_kernel, dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream,
               reinterpret_cast<const __nv_bfloat16*>(r), V, C, scale_shift, reinterpret_cast<__nv_bfloat16*>(y), ldy,
               y_coff);
   }
@@ -631,15 +631,15 @@ extern "C" int b2_relu_gn_bwd_acc(const long long* stat_acc, const void* dy, int
   B2_REQUIRE(lddy % 8 == 0 && dy_coff % 8 == 0, "b2_relu_gn_bwd_acc: lddy/dy_coff must be multiples of 8");
   B2_REQUIRE(workspace_bytes >= (long long)C * 4 * (long long)sizeof(float), "b2_relu_gn_bwd_acc: workspace too small");
   float* coef = reinterpret_cast<float*>(workspace);
-  B2_LAUNCH(gn_bwd_finalize_acc_kernel, 1, (C + 31) / 32 * 32, 0, stream, stat_acc, C, G,
+  B2_LAUNCH_DEP(gn_bwd_finalize_acc_kernel, 1, (C + 31) / 32 * 32, 0, stream, stat_acc, C, G,
             1.0 / ((double)V * (C / G)), gamma, mean_rstd, coef, dgamma, dbeta);
   B2_CHECK_CUDA(cudaGetLastError());
   if (dy_row_labels != nullptr)
-    B2_LAUNCH(gn_bwd_apply_kernel<true>, dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream,
+    B2_LAUNCH_DEP(gn_bwd_apply_kernel<true>, dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream,
               reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V,
               C, mean_rstd, static_cast<const float*>(coef), reinterpret_cast<__nv_bfloat16*>(dr), dy_row_labels);
   else
-    B2_LAUNCH(gn_bwd_apply_kernel<false>, dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream,
+    B2_LAUNCH_DEP(gn_bwd_apply_kernel<false>, dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream,
               reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V,
               C, mean_rstd, static_cast<const float*>(coef), reinterpret_cast<__nv_bfloat16*>(dr), dy_row_labels);
   B2_CHECK_CUDA(cudaGetLastError());

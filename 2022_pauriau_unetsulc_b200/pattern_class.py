@@ -396,7 +396,8 @@ class UnetPatternSulciLabelling(object):
     # recorded by the capture) instead of cutting the step into segments around eager collectives: one replay per
     # step.  B2_DP_CAPTURE_NCCL=0 selects the segmented form.
     dp_capture_nccl = os.environ.get("B2_DP_CAPTURE_NCCL", "1") != "0"
-    _graph_cache_limit = 8
+    _graph_cache_limit = 24       # captured shapes kept (each holds its own ~2.5 GB activation pool at 96x112x96);
+    _graph_min_free_frac = 0.30   # ... but never capture another one with less than this fraction of HBM free
     _graph_capture_after = 2      # eager sightings of a (shape, optimiser, mask) key before it is captured
 
     def _graph_key(self, shape, optimizer):
@@ -506,8 +507,11 @@ class UnetPatternSulciLabelling(object):
                     seen.clear()
                 seen[key] = n_seen + 1
                 return self._eager_step(x, y, optimizer, reducer, metrics)
-            if len(cache) >= self._graph_cache_limit:
-                cache.pop(next(iter(cache)))
+            free, total = torch.cuda.mem_get_info(self.device)
+            while cache and (len(cache) >= self._graph_cache_limit or free < self._graph_min_free_frac * total):
+                cache.pop(next(iter(cache)))          # oldest first; its private pool goes back to the allocator
+                torch.cuda.empty_cache()
+                free, total = torch.cuda.mem_get_info(self.device)
             sx, sy = torch.empty_like(x), torch.empty_like(y)
             sx.copy_(x)
             sy.copy_(y)

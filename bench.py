@@ -644,6 +644,68 @@ def run_inference(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------- variable bounding boxes (sweep)
+def run_sweep(args):
+    """VERDICT r1 item 9 / SURVEY §8(d): a cohort of 16 subjects whose bounding boxes are drawn around 80x104x72 +- 8
+    (what real cohorts look like, dataset.py:68-75) through learning(), batch 1:
+      (a) as the reference runs it — no fixed img_size, rotation augmentation on: every sample has its own box, the
+          step runs eagerly (shapes never repeat, nothing to replay);
+      (b) the same cohort with dict_model['img_size'] = the largest box + margin: one shape, CUDA-graph replay.
+    Prints one JSON line with the train-phase volumes/s of the last epoch of both."""
+    import random
+    import numpy as np
+    import torch
+    from unetsulc_b200.training import UnetTrainingSulciLabelling
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    rng = np.random.RandomState(11)
+    names = ["S%02d_left" % i for i in range(N_CLASSES)]
+    bck2, nm, boxes = {}, {}, []
+    for s in range(16):
+        box = tuple(int(v) for v in (np.array([80, 104, 72]) + rng.randint(-8, 9, size=3)))
+        boxes.append(box)
+        n_pts = int(0.03 * box[0] * box[1] * box[2])
+        lin = rng.choice(box[0] * box[1] * box[2], size=n_pts, replace=False)
+        pts = np.stack(np.unravel_index(lin, box), 1)
+        pts = np.concatenate([pts, [[0, 0, 0], [box[0] - 1, box[1] - 1, box[2] - 1]]])   # pin the bounding box
+        g = "sweep_subject%02d.arg" % s
+        bck2[g] = pts.tolist()
+        nm[g] = [names[l] for l in rng.randint(0, N_CLASSES, size=len(pts))]
+    files = sorted(bck2)
+    out = {}
+    # (b): the fixed size comes from the reference's own pre-scan for batch > 1 (training.py:119-134): largest box over
+    # the augmented draws of all epochs, then the generators are re-seeded so that the same draws are made again
+    from unetsulc_b200.dataset import SulciDataset
+    random.seed(42); np.random.seed(42)
+    scan = SulciDataset(files[:15], {n_: i for i, n_ in enumerate(names)}, train=True, dict_bck2=bck2, dict_names=nm)
+    big = [0, 0, 0]
+    for _ in range(4):
+        for k in range(15):
+            big = [max(a_, b_) for a_, b_ in zip(big, scan.item_size(k))]
+    big = [max(a_, b_ ) for a_, b_ in zip(big, [max(b[k] for b in boxes) for k in range(3)])]
+    for mode, dm in (("variable_boxes_eager", {"name": "sweep_a"}),
+                     ("padded_to_%dx%dx%d_graph" % tuple(big), {"name": "sweep_b", "img_size": big})):
+        random.seed(42); np.random.seed(42); torch.manual_seed(42)
+        with _quiet():
+            tr = UnetTrainingSulciLabelling(files, "L", cuda=0, working_path="/tmp/unetsulc_bench", dict_model=dm,
+                                            dict_names=nm, dict_bck2=bck2, sulci_side_list=names)
+            tr.learning(1e-2, 0.9, 4, files[:15], files[15:], batch_size=1, patience={}, save_results=False)
+        t = tr.timings["train"]
+        out[mode] = {"volumes_per_s": [round(x["steps"] / x["seconds"], 2) for x in t],
+                     "ms_per_step_last_epoch": t[-1]["seconds"] / t[-1]["steps"] * 1e3}
+        del tr
+        torch.cuda.empty_cache()
+    vox = float(np.mean([b[0] * b[1] * b[2] for b in boxes]))
+    print(json.dumps({"metric": "training volumes/sec (variable bounding boxes)", "unit": "volumes/s", "n_gpus": 1,
+                      "boxes": boxes, "mean_voxels": vox, "voxels_vs_96x112x96": vox / (96 * 112 * 96),
+                      "epochs": 4, "subjects": 15, "results": out,
+                      "note": "train-phase wall clock per epoch incl. host-side sample building; epoch 0 includes "
+                              "first-use workspace allocation (a) / eager steps before the capture (b)"}))
+    return 0
+
+
 def main():
     if os.environ.get("B2_DEBUG_DP") == "1":   # debugging aid: dump every thread's Python stack if the run stalls
         import faulthandler
@@ -654,6 +716,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--inference", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="variable bounding boxes through learning() (1 GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-gpu", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true")
@@ -663,6 +726,8 @@ def main():
         return run_reference_arm(args)
     if args.inference:
         return run_inference(args)
+    if args.sweep:
+        return run_sweep(args)
     return run_ours(args)
 
 
