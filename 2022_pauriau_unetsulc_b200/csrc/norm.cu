@@ -225,12 +225,30 @@ gn_bwd_finalize_acc_kernel(const long long* __restrict__ acc, int C, int G, doub
   }
   __syncthreads();
   if (c < C) {
+    // dr = relu'(r) * (a*dy + b*xhat + c0), xhat = (r - mu)*rstd  ==  relu'(r) * (a*dy + kb*r + kc): the apply kernel
+    // reads {a, kb, kc} as ONE 16-byte load per channel (it used to read mean/rstd as well and fold them itself)
+    const float b = -rstd * s_g[c / cpg][0], c0 = -rstd * s_g[c / cpg][1];
+    const float mu = mean_rstd[2 * c];
     float* o = coef + (size_t)c * 4;
     o[0] = rstd * gm;
-    o[1] = -rstd * s_g[c / cpg][0];
-    o[2] = -rstd * s_g[c / cpg][1];
+    o[1] = b * rstd;
+    o[2] = c0 - b * rstd * mu;
     o[3] = 0.f;
   }
+}
+
+// Blocks for the apply kernels (one channel octet of one voxel per thread and loop trip).  Every thread pays a fixed
+// prologue (4-8 coefficient loads): a thread should own >= 4..8 voxels, but a small tensor must still cover one full
+// resident wave (4 blocks/SM).  ncu, round 2: with one voxel per thread the 24x28x24 levels ran at 0.6-0.9 TB/s with the
+// load-store unit throttled by the coefficient loads (lg_throttle 15 stall cycles per issue).
+static inline int apply_blocks(long long items) {
+  const long long wave = (long long)num_sms() * 4;
+  const long long nb8 = (items + 2047) / 2048, nb2 = (items + 511) / 512;
+  long long nb = nb8 >= wave ? nb8 : (nb2 < wave ? nb2 : wave);
+  const long long cap = (long long)num_sms() * 16;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  return (int)nb;
 }
 
 // ------------------------------------------------------------------------------------------------- forward apply
@@ -255,6 +273,19 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ r, long long V, int C, const f
   }
   const __nv_bfloat16* rp = r + ((size_t)n * V) * C + oct * 8;
   __nv_bfloat16* yp = y + ((size_t)n * V) * ldy + y_coff + oct * 8;
+  for (; v + 3 * vstride < V; v += 4 * vstride) {   // 4 independent 16-byte loads in flight per thread
+    uint4 u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = ldg16(rp + (v + j * vstride) * C);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const f8 x = unpack8(u[j]);
+      f8 o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = fmaf(x.v[k], sc[k], sh[k]);
+      stg16(yp + (v + j * vstride) * ldy, pack8(o));
+    }
+  }
   for (; v + vstride < V; v += 2 * vstride) {
     const uint4 u0 = ldg16(rp + v * C), u1 = ldg16(rp + (v + vstride) * C);
     const f8 x0 = unpack8(u0), x1 = unpack8(u1);
@@ -408,11 +439,13 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
     const double m = (double)V * cpg;
     for (int k = 0; k < cpg; ++k) {
       const int c = g * cpg + k;
-      const double rstd = (double)mean_rstd[((size_t)n * C + c) * 2 + 1];
-      float* o = coef + ((size_t)n * C + c) * 4;
+      const float mu_f = mean_rstd[((size_t)n * C + c) * 2], rstd_f = mean_rstd[((size_t)n * C + c) * 2 + 1];
+      const double rstd = (double)rstd_f;
+      const float b = (float)(-rstd * S2 / m), c0 = (float)(-rstd * S1 / m);
+      float* o = coef + ((size_t)n * C + c) * 4;   // {a, kb, kc}: see gn_bwd_finalize_acc_kernel
       o[0] = (float)(rstd * (double)gamma[c]);
-      o[1] = (float)(-rstd * S2 / m);
-      o[2] = (float)(-rstd * S1 / m);
+      o[1] = b * rstd_f;
+      o[2] = c0 - b * rstd_f * mu_f;
       o[3] = 0.f;
     }
   }
@@ -450,16 +483,36 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int dy_coff,
   float ca[8], kb[8], kc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int c = oct * 8 + k;
-    const float2 mr = __ldg(reinterpret_cast<const float2*>(mean_rstd + ((size_t)n * C + c) * 2));
-    const float4 cf = __ldg(reinterpret_cast<const float4*>(coef + ((size_t)n * C + c) * 4));
+    const float4 cf = __ldg(reinterpret_cast<const float4*>(coef + ((size_t)n * C + oct * 8 + k) * 4));
     ca[k] = cf.x;
-    kb[k] = cf.y * mr.y;
-    kc[k] = cf.z - cf.y * mr.y * mr.x;
+    kb[k] = cf.y;
+    kc[k] = cf.z;
   }
   const __nv_bfloat16* rp = r + ((size_t)n * V) * C + oct * 8;
   const __nv_bfloat16* gp = dy + ((size_t)n * V) * lddy + dy_coff + oct * 8;
   __nv_bfloat16* op = dr + ((size_t)n * V) * C + oct * 8;
+  for (; v + 3 * vstride < V; v += 4 * vstride) {   // 8 independent 16-byte loads in flight per thread
+    bool lb[4];
+    uint4 ux[4], ug[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lb[j] = !kRowLabels || __ldg(row_labels + (size_t)n * V + v + j * vstride) >= 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ux[j] = ldg16(rp + (v + j * vstride) * C);
+      ug[j] = lb[j] ? ldg16(gp + (v + j * vstride) * lddy) : zero4;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const f8 x = unpack8(ux[j]), g = unpack8(ug[j]);
+      f8 o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = fmaf(ca[k], g.v[k], fmaf(kb[k], x.v[k], kc[k]));
+        o.v[k] = x.v[k] > 0.f ? d : 0.f;
+      }
+      stg16(op + (v + j * vstride) * C, pack8(o));
+    }
+  }
   for (; v + vstride < V; v += 2 * vstride) {
     const bool l0 = !kRowLabels || __ldg(row_labels + (size_t)n * V + v) >= 0;
     const bool l1 = !kRowLabels || __ldg(row_labels + (size_t)n * V + v + vstride) >= 0;
@@ -576,7 +629,7 @@ extern "C" int b2_relu_gn_apply(const void* r, int N, int D, int H, int W, int C
               reinterpret_cast<__nv_bfloat16*>(pooled));
   } else {
     B2_REQUIRE(256 % (C / 8) == 0, "b2_relu_gn_apply: C=%d unsupported", C);
-    B2_LAUNCH_DEP(gn_apply_kernel, dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream,
+    B2_LAUNCH_DEP(gn_apply_kernel, dim3(apply_blocks(V * (C / 8)), N), 256, 0, stream,
               reinterpret_cast<const __nv_bfloat16*>(r), V, C, scale_shift, reinterpret_cast<__nv_bfloat16*>(y), ldy,
               y_coff);
   }
@@ -604,7 +657,7 @@ extern "C" int b2_relu_gn_bwd(const void* dy, int lddy, int dy_coff, const void*
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
       mean_rstd, partial, counters, N, G, gamma, coef, dgb_n, dgamma, dbeta);
   B2_CHECK_CUDA(cudaGetLastError());
-  B2_LAUNCH(gn_bwd_apply_kernel<false>, dim3(ew_blocks(V * (C / 8)), N), 256, 0, stream, 
+  B2_LAUNCH(gn_bwd_apply_kernel<false>, dim3(apply_blocks(V * (C / 8)), N), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V, C,
       mean_rstd, coef, reinterpret_cast<__nv_bfloat16*>(dr), static_cast<const long long*>(nullptr));
   B2_CHECK_CUDA(cudaGetLastError());
@@ -635,11 +688,11 @@ extern "C" int b2_relu_gn_bwd_acc(const long long* stat_acc, const void* dy, int
             1.0 / ((double)V * (C / G)), gamma, mean_rstd, coef, dgamma, dbeta);
   B2_CHECK_CUDA(cudaGetLastError());
   if (dy_row_labels != nullptr)
-    B2_LAUNCH_DEP(gn_bwd_apply_kernel<true>, dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream,
+    B2_LAUNCH_DEP(gn_bwd_apply_kernel<true>, dim3(apply_blocks(V * (C / 8)), 1), 256, 0, stream,
               reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V,
               C, mean_rstd, static_cast<const float*>(coef), reinterpret_cast<__nv_bfloat16*>(dr), dy_row_labels);
   else
-    B2_LAUNCH_DEP(gn_bwd_apply_kernel<false>, dim3(ew_blocks(V * (C / 8)), 1), 256, 0, stream,
+    B2_LAUNCH_DEP(gn_bwd_apply_kernel<false>, dim3(apply_blocks(V * (C / 8)), 1), 256, 0, stream,
               reinterpret_cast<const __nv_bfloat16*>(dy), lddy, dy_coff, reinterpret_cast<const __nv_bfloat16*>(r), V,
               C, mean_rstd, static_cast<const float*>(coef), reinterpret_cast<__nv_bfloat16*>(dr), dy_row_labels);
   B2_CHECK_CUDA(cudaGetLastError());

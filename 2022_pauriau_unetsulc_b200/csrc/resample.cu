@@ -46,7 +46,7 @@ __device__ __forceinline__ void bstats_accumulate(float (&s)[8], float (&q)[8], 
 // out[v, c] = dskip[v, c] + (v is the arg-max of its 2x2x2 cell ? dpool[cell, c] : 0)
 // arg-max is recomputed from the stored forward tensor y; first maximum in (d, h, w) scan order wins, as in
 // PyTorch's max_pool3d_with_indices.
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 4)
 pool_bwd_add_kernel(const __nv_bfloat16* __restrict__ y, int ldy, int y_coff, const __nv_bfloat16* __restrict__ dskip,
                     int ldd, int d_coff, const __nv_bfloat16* __restrict__ dpool, __nv_bfloat16* __restrict__ out,
                     int N, int D, int H, int W, int C, const __nv_bfloat16* __restrict__ stat_r,
@@ -73,19 +73,18 @@ pool_bwd_add_kernel(const __nv_bfloat16* __restrict__ y, int ldy, int y_coff, co
     // a later voxel replaces the running maximum only if strictly greater), added to the skip gradient with one
     // correctly rounded bf16 add.  No unpacking to fp32: ~2x fewer instructions than the fp32 form.
     uint32_t mx[4] = {0u, 0u, 0u, 0u}, gp[4] = {0u, 0u, 0u, 0u}, found[4] = {0u, 0u, 0u, 0u};
-    uint4 yv[8];
-    if (pooled) {
+    if (pooled) {   // pass 1: channel-wise maximum of the cell (the 8 rows are read again in pass 2: L1 hits, and 32
+                    // registers less than keeping them: 4 instead of 2 resident blocks per SM)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int d = 2 * cd + (j >> 2), h = 2 * ch + ((j >> 1) & 1), w = 2 * cw + (j & 1);
         const long long v = (((long long)n * D + d) * H + h) * W + w;
-        yv[j] = ldg16(y + v * ldy + y_coff + oct * 8);
-      }
-      mx[0] = yv[0].x; mx[1] = yv[0].y; mx[2] = yv[0].z; mx[3] = yv[0].w;
-#pragma unroll
-      for (int j = 1; j < 8; ++j) {
-        mx[0] = bf2_max(mx[0], yv[j].x); mx[1] = bf2_max(mx[1], yv[j].y);
-        mx[2] = bf2_max(mx[2], yv[j].z); mx[3] = bf2_max(mx[3], yv[j].w);
+        const uint4 yv = ldg16(y + v * ldy + y_coff + oct * 8);
+        if (j == 0) { mx[0] = yv.x; mx[1] = yv.y; mx[2] = yv.z; mx[3] = yv.w; }
+        else {
+          mx[0] = bf2_max(mx[0], yv.x); mx[1] = bf2_max(mx[1], yv.y);
+          mx[2] = bf2_max(mx[2], yv.z); mx[3] = bf2_max(mx[3], yv.w);
+        }
       }
       const long long pv = (((long long)n * Dp + cd) * Hp + ch) * Wp + cw;
       const uint4 g4 = ldg16(dpool + pv * C + oct * 8);
@@ -99,7 +98,8 @@ pool_bwd_add_kernel(const __nv_bfloat16* __restrict__ y, int ldy, int y_coff, co
         uint4 g = make_uint4(0u, 0u, 0u, 0u);
         if (dskip) g = ldg16(dskip + v * ldd + d_coff + oct * 8);
         if (pooled) {
-          const uint32_t yw[4] = {yv[j].x, yv[j].y, yv[j].z, yv[j].w};
+          const uint4 yj = ldg16(y + v * ldy + y_coff + oct * 8);
+          const uint32_t yw[4] = {yj.x, yj.y, yj.z, yj.w};
           uint32_t add[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
