@@ -22,6 +22,8 @@ SIGNATURES = {
     "b2_relu_gn_bwd_acc": (_i, [_vp, _vp, _i, _i, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp]),
     "b2_conv3d_wgrad_workspace_bytes": (_ll, [_i, _i, _i, _i, _i, _i]),
     "b2_conv3d_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp]),
+    "b2_conv3d_wgrad_partial": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "b2_wgrad_reduce_multi": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "b2_conv3d_first_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b2_conv3d_first_fwd_stats": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "b2_conv3d_first_wgrad_workspace_bytes": (_ll, [_i]),

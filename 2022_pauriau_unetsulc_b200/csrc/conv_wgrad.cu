@@ -332,6 +332,90 @@ wgrad_reduce_par_kernel(const float* __restrict__ ws, float* __restrict__ dw, in
   }
 }
 
+// ---- deferred reduction of SEVERAL layers in one launch --------------------------------------------------------------
+// The 13 per-layer reduce launches cost 231 us of a 6.7 ms step (A/B on B200, round 2) although they move little data:
+// each is a short, latency-bound kernel between two tensor-core kernels.  b2_conv3d_wgrad_partial leaves the split
+// partials of a layer in that layer's own workspace; one launch of this kernel then reduces every pending layer at once
+// (at the end of backward, or when a data-parallel gradient bucket closes): one launch latency, the whole GPU busy.
+// Per layer: mode 0 = transposing tile (32 co x 8 ci x 27 taps per block; few splits, big tensors), mode 1 = split-parallel
+// (32 elements per block, the 8 warps share the splits; many splits, small tensors; also the swapped layout).
+static constexpr int kMaxReduceLayers = 16;
+struct WgReduceArgs {
+  const float* ws[kMaxReduceLayers];
+  float* dw[kMaxReduceLayers];
+  int splits[kMaxReduceLayers], cin[kMaxReduceLayers], cout[kMaxReduceLayers], mode[kMaxReduceLayers];
+  int swapped[kMaxReduceLayers];
+  int first_block[kMaxReduceLayers + 1];
+  int count;
+};
+
+__global__ void __launch_bounds__(256)
+wgrad_reduce_multi_kernel(const WgReduceArgs a) {
+  pdl_prologue();
+  __shared__ float t[32 * 217];
+  int l = 0;
+  while (l + 1 < a.count && (int)blockIdx.x >= a.first_block[l + 1]) ++l;
+  const int b = blockIdx.x - a.first_block[l];
+  const float* __restrict__ ws = a.ws[l];
+  float* __restrict__ dw = a.dw[l];
+  const int splits = a.splits[l], Cin = a.cin[l], Cout = a.cout[l];
+  const long long total = 27LL * Cin * Cout;
+  if (a.mode[l] == 0) {
+    const int co_tiles = Cout / 32;
+    const int co0 = (b % co_tiles) * 32, ci0 = (b / co_tiles) * 8;
+    const int co = threadIdx.x & 31, ci = (threadIdx.x >> 5) & 7;
+    const float* src = ws + ((long long)(ci0 + ci)) * Cout + co0 + co;
+    const long long tap_stride = (long long)Cin * Cout;
+#pragma unroll
+    for (int t0 = 0; t0 < 27; t0 += 9) {
+      float acc[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+      for (int s = 0; s < splits; ++s) {
+        float v[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] = __ldcg(src + (long long)s * total + (t0 + k) * tap_stride);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[k] += v[k];
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) t[co * 217 + ci * 27 + t0 + k] = acc[k];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * 216; e += 256) {
+      const int c = e / 216, r = e % 216;   // r = ci*27 + tap
+      dw[((long long)(co0 + c) * Cin + ci0) * 27 + r] = t[c * 217 + r];
+    }
+  } else {
+    float (*part)[32] = reinterpret_cast<float (*)[32]>(t);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long i = (long long)b * 32 + lane;
+    float acc = 0.f;
+    if (i < total) {
+      int s = warp;
+      for (; s + 24 < splits; s += 32)
+        acc += (__ldcg(ws + (long long)s * total + i) + __ldcg(ws + (long long)(s + 8) * total + i)) +
+               (__ldcg(ws + (long long)(s + 16) * total + i) + __ldcg(ws + (long long)(s + 24) * total + i));
+      for (; s < splits; s += 8) acc += __ldcg(ws + (long long)s * total + i);
+    }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && i < total) {
+      const float r = ((part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane])) +
+                      ((part[4][lane] + part[5][lane]) + (part[6][lane] + part[7][lane]));
+      if (a.swapped[l]) {
+        const int ci = (int)(i % Cin);
+        const long long q = i / Cin;
+        dw[((long long)(int)(q % Cout) * Cin + ci) * 27 + (26 - (int)(q / Cout))] = r;
+      } else {
+        const int co = (int)(i % Cout);
+        const long long q = i / Cout;
+        dw[((long long)co * Cin + (int)(q % Cin)) * 27 + (int)(q / Cin)] = r;
+      }
+    }
+  }
+}
+
 // Which operand is shifted per tap?  The shifted operand is re-loaded for every tap, the other one once per
 // 128-voxel K-step, so shifting the NARROW one and keeping the wide one as the N dimension halves the TMA traffic
 // per tensor-cycle when Cout = 64 and Cin >= 128 (decoders.2.conv1: 133 -> 73 B/clk/SM).
@@ -397,17 +481,16 @@ extern "C" long long b2_conv3d_wgrad_workspace_bytes(int N, int D, int H, int W,
   return (long long)p.splits * 27 * Cin * Cout * (long long)sizeof(float);
 }
 
-extern "C" int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* dy, int ldy, int y_coff, float* dw,
-                               void* workspace, long long workspace_bytes, int N, int D, int H, int W, int Cin,
-                               int Cout, cudaStream_t stream) {
-  B2_REQUIRE(x && dy && dw && workspace, "b2_conv3d_wgrad: null pointer");
+static int wgrad_partial_impl(const void* x, int ldx, int x_coff, const void* dy, int ldy, int y_coff, void* workspace,
+                              long long workspace_bytes, int N, int D, int H, int W, int Cin, int Cout,
+                              WgradParams& p, bool& swap, cudaStream_t stream) {
+  B2_REQUIRE(x && dy && workspace, "b2_conv3d_wgrad: null pointer");
   B2_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "b2_conv3d_wgrad: bad shape");
   B2_REQUIRE(Cin % 32 == 0 && Cin >= 32, "b2_conv3d_wgrad: Cin=%d must be a multiple of 32", Cin);
   B2_REQUIRE(Cout % 64 == 0 && Cout >= 64, "b2_conv3d_wgrad: Cout=%d must be a multiple of 64", Cout);
   B2_REQUIRE(ldx % 8 == 0 && x_coff % 8 == 0 && ldy % 8 == 0 && y_coff % 8 == 0,
              "b2_conv3d_wgrad: channel strides/offsets must be multiples of 8");
-  WgradParams p;
-  const bool swap = wgrad_swap_roles(Cin, Cout);
+  swap = wgrad_swap_roles(Cin, Cout);
   // kernel view: "shifted" operand (slots along M) and "fixed" operand (N); swapped roles shift dY by the flipped tap
   const void* sh_ptr = swap ? dy : x;
   const void* fx_ptr = swap ? x : dy;
@@ -430,6 +513,18 @@ extern "C" int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* d
   dim3 grid((unsigned)(p.n_gchunks * p.n_cout_tiles), (unsigned)p.splits);
   B2_LAUNCH(conv3d_wgrad_kernel, grid, kWgThreads, smem_bytes, stream, tx, ty, p);
   B2_CHECK_CUDA(cudaGetLastError());
+  return B2_OK;
+}
+
+extern "C" int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* dy, int ldy, int y_coff, float* dw,
+                               void* workspace, long long workspace_bytes, int N, int D, int H, int W, int Cin,
+                               int Cout, cudaStream_t stream) {
+  B2_REQUIRE(dw, "b2_conv3d_wgrad: null pointer");
+  WgradParams p;
+  bool swap = false;
+  int rc = wgrad_partial_impl(x, ldx, x_coff, dy, ldy, y_coff, workspace, workspace_bytes, N, D, H, W, Cin, Cout, p,
+                              swap, stream);
+  if (rc) return rc;
   const long long total = 27LL * Cin * Cout;
   if (p.splits >= 32 && !swap) {
     // few elements, many splits (enc0.conv2 148, enc1.conv1 / dec2.conv2 74, enc1.conv2 37): split-parallel reduce
@@ -442,5 +537,54 @@ extern "C" int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* d
     B2_LAUNCH(wgrad_reduce_simple_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, p.ws, dw, p.splits, Cin, Cout);
   }
   B2_CHECK_CUDA(cudaGetLastError());
+  return B2_OK;
+}
+
+// The tensor-core half of b2_conv3d_wgrad only: the split partials stay in `workspace` (which must then be private to
+// this layer until b2_wgrad_reduce_multi has run); *splits_out / *swapped_out describe their layout for the reduce.
+extern "C" int b2_conv3d_wgrad_partial(const void* x, int ldx, int x_coff, const void* dy, int ldy, int y_coff,
+                                       void* workspace, long long workspace_bytes, int N, int D, int H, int W, int Cin,
+                                       int Cout, int* splits_out, int* swapped_out, cudaStream_t stream) {
+  B2_REQUIRE(splits_out && swapped_out, "b2_conv3d_wgrad_partial: null pointer");
+  WgradParams p;
+  bool swap = false;
+  int rc = wgrad_partial_impl(x, ldx, x_coff, dy, ldy, y_coff, workspace, workspace_bytes, N, D, H, W, Cin, Cout, p,
+                              swap, stream);
+  if (rc) return rc;
+  *splits_out = p.splits;
+  *swapped_out = swap ? 1 : 0;
+  return B2_OK;
+}
+
+// One launch reduces the split partials of `count` layers (HOST arrays of `count` entries) into dW[co][ci][3][3][3].
+extern "C" int b2_wgrad_reduce_multi(const float* const* ws, float* const* dw, const int* splits, const int* cin,
+                                     const int* cout, const int* swapped, int count, cudaStream_t stream) {
+  B2_REQUIRE(ws && dw && splits && cin && cout && swapped && count >= 0, "b2_wgrad_reduce_multi: null pointer");
+  int done = 0;
+  while (done < count) {
+    WgReduceArgs a;
+    int k = 0;
+    long long blocks = 0;
+    while (done + k < count && k < kMaxReduceLayers) {
+      const int i = done + k;
+      B2_REQUIRE(ws[i] && dw[i] && splits[i] > 0 && cin[i] % 8 == 0 && cout[i] % 32 == 0,
+                 "b2_wgrad_reduce_multi: bad layer %d", i);
+      a.ws[k] = ws[i]; a.dw[k] = dw[i];
+      a.splits[k] = splits[i]; a.cin[k] = cin[i]; a.cout[k] = cout[i]; a.swapped[k] = swapped[i];
+      a.mode[k] = (swapped[i] || splits[i] > 10) ? 1 : 0;
+      a.first_block[k] = (int)blocks;
+      const long long total = 27LL * cin[i] * cout[i];
+      blocks += a.mode[k] == 0 ? (long long)(cout[i] / 32) * (cin[i] / 8) : (total + 31) / 32;
+      B2_REQUIRE(blocks < (1LL << 31), "b2_wgrad_reduce_multi: too many blocks");
+      ++k;
+    }
+    a.first_block[k] = (int)blocks;
+    a.count = k;
+    if (blocks > 0) {
+      B2_LAUNCH(wgrad_reduce_multi_kernel, (unsigned)blocks, 256, 0, stream, a);
+      B2_CHECK_CUDA(cudaGetLastError());
+    }
+    done += k;
+  }
   return B2_OK;
 }

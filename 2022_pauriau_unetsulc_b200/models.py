@@ -11,6 +11,8 @@ The module holds ordinary fp32 ``nn.Parameter`` s under the upstream names (so `
 ``nn.Conv3d`` / ``nn.GroupNorm``: they read the parameters and enqueue the hand-written sm_100a kernels of
 ``libunetsulc_b200.so`` (NDHWC bf16 activations, fp32 accumulation and statistics).  There is no CPU fallback.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -18,7 +20,14 @@ from . import ops
 from .ops import ActView
 
 GN_EPS = 1e-5
-
+# Weight-gradient split reduction: 13 short, latency-bound launches per step = 0.23 ms on the critical path (A/B with the
+# reductions skipped, round 2, 1 x B200).  Three placements were measured on the same box (40-step graph replays):
+#   "inline" (default): on the main stream right after each wgrad kernel ............................ 6.74 ms/step
+#   "defer"  (B2_WGRAD_REDUCE=defer): ONE launch per step / per data-parallel bucket ................. 6.74-6.84 ms/step
+#            (13 private workspaces = 455 MB go through HBM; the inline reduce finds its ~35 MB of partials in L2)
+#   side stream, overlapping the following dgrad / GroupNorm kernels ................................ 6.91 ms/step
+#            (its blocks delay CTAs of the persistent 148-CTA convolution grids; removed)
+_WGRAD_REDUCE = os.environ.get("B2_WGRAD_REDUCE", "inline")
 
 def _double_conv(in_ch, out_ch, encoder, order, num_groups):
     if encoder:
@@ -112,6 +121,9 @@ class UNet3D(nn.Module):
         # data-parallel hook: called as hook(name_prefix, [grad tensors]) when a level's gradients are ready
         self.grad_ready_hook = None
         self.post_head_hook = None
+        # data parallel: layer indices after which the pending weight-gradient reductions must be flushed (set by
+        # BucketedGradReducer.begin(): the layers that close a gradient bucket); None = after every layer
+        self.grad_flush_at = None
         # CUDA-graph capture: re-pack the bf16 weights of every trainable layer even when the packs are fresh, so that
         # the recorded step always contains the re-pack its replays need after each SGD update
         self.force_repack = False
@@ -315,6 +327,19 @@ class UNet3D(nn.Module):
             outs = [None] * 42
 
         B = save.x.shape[0]
+        # Weight gradients: the split reductions of the layers are deferred and run as ONE launch (b2_wgrad_reduce_multi)
+        # at the end of backward — or, data parallel, whenever a gradient bucket closes (grad_flush_at, set by the
+        # reducer), right before the layers' grad-ready hooks fire.
+        pending, waiting = [], []
+        flush_at = self.__dict__.get("grad_flush_at")
+
+        def flush():
+            ops.wgrad_reduce_multi(pending)
+            del pending[:]
+            if hook is not None:
+                for j in waiting:
+                    hook(j, [g for g in grads[3 * j:3 * j + 3] if g is not None])
+            del waiting[:]
 
         def layer_bwd(i, dy, dy_stats=None):
             """dy: gradient w.r.t. the GN output of layer i (dy_stats: GroupNorm-backward statistics of dy when the
@@ -336,10 +361,15 @@ class UNet3D(nn.Module):
             if needs[3 * i]:
                 if layer.cin == 1:
                     grads[3 * i] = ops.conv3d_first_wgrad(rc["x"], dr, layer.cout, outs[3 * i])
-                else:
+                elif _WGRAD_REDUCE == "inline":
                     grads[3 * i] = ops.conv3d_wgrad(rc["x"], dr, layer.cin, layer.cout, outs[3 * i])
-            if hook is not None:
-                hook(i, [g for g in grads[3 * i:3 * i + 3] if g is not None])
+                else:   # "defer"
+                    desc = ops.conv3d_wgrad_partial(rc["x"], dr, layer.cin, layer.cout, i, outs[3 * i])
+                    grads[3 * i] = desc["dw"]
+                    pending.append(desc)
+            waiting.append(i)
+            if hook is not None and (flush_at is None or i in flush_at):
+                flush()
             if i <= first_needed or layer.cin == 1:
                 return None
             xin = rc["x"]
@@ -363,15 +393,20 @@ class UNet3D(nn.Module):
         # statistics (batch 1): the upsample adjoint for layers 11, 9, 7, the pooling adjoint for layers 5, 3, 1.
         fuse = (B == 1)
         st_next = dfeat_stats    # layer 13: accumulated by the head kernel when it produced dfeat
+
+        def done():
+            flush()
+            return grads
+
         for lvl in (0, 1, 2):
             dy, st = split(layer_bwd(li, dy, st_next))
             li -= 1
             if dy is None:
-                return grads
+                return done()
             dc = layer_bwd(li, dy, st)
             li -= 1
             if dc is None:
-                return grads
+                return done()
             dcat[lvl] = dc
             if fuse and 2048 % up_c[lvl] == 0:
                 dy, st_next = ops.upcat_bwd(dc.window(skip_c[lvl], up_c[lvl]), *dims[lvl + 1], stat_r=rec[li]["r"],
@@ -390,12 +425,12 @@ class UNet3D(nn.Module):
             dy, st = split(layer_bwd(li, dy, st_next))
             li -= 1
             if dy is None:
-                return grads
+                return done()
             dy = layer_bwd(li, dy, st)
             li -= 1
             if dy is None:
-                return grads
-        return grads
+                return done()
+        return done()
 
     # ------------------------------------------------------------------------------------------ public API
     def forward(self, x):

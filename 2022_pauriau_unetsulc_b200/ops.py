@@ -245,6 +245,39 @@ def conv3d_wgrad(x, dy, cin, cout, out=None):
     return dw
 
 
+def conv3d_wgrad_partial(x, dy, cin, cout, slot, out=None):
+    """The tensor-core half of conv3d_wgrad: split partials stay in the workspace of `slot` (one per layer) until
+    wgrad_reduce_multi() runs.  Returns the descriptor to hand to it; desc["dw"] is the (not yet valid) gradient."""
+    lib = _lib.load()
+    _need_cuda(x.buf, dy.buf)
+    need = lib.b2_conv3d_wgrad_workspace_bytes(x.N, x.D, x.H, x.W, cin, cout)
+    if need < 0:
+        raise RuntimeError("b2_conv3d_wgrad: unsupported shape Cin=%d Cout=%d" % (cin, cout))
+    ws = Workspace.get(need, x.buf.device, "wgrad_p%s" % slot)
+    dw = out if out is not None else torch.empty((cout, cin, 3, 3, 3), dtype=torch.float32, device=x.buf.device)
+    splits, swapped = C.c_int(0), C.c_int(0)
+    with _Prof("conv3d_wgrad", 2.0 * x.N * x.V * 27 * cin * cout):
+        _lib.check(lib.b2_conv3d_wgrad_partial(_p(x.buf), x.ld, x.coff, _p(dy.buf), dy.ld, dy.coff, _p(ws), ws.numel(),
+                                               x.N, x.D, x.H, x.W, cin, cout, C.byref(splits), C.byref(swapped), _s()),
+                   "b2_conv3d_wgrad_partial")
+    _count(1)
+    return dict(ws=ws, dw=dw, splits=splits.value, swapped=swapped.value, cin=cin, cout=cout)
+
+
+def wgrad_reduce_multi(descs):
+    """one launch: dW of every pending layer (descriptors of conv3d_wgrad_partial) from its split partials"""
+    n = len(descs)
+    if n == 0:
+        return
+    lib = _lib.load()
+    vp, ia = C.c_void_p * n, C.c_int * n
+    _lib.check(lib.b2_wgrad_reduce_multi(vp(*[d["ws"].data_ptr() for d in descs]), vp(*[d["dw"].data_ptr() for d in descs]),
+                                         ia(*[d["splits"] for d in descs]), ia(*[d["cin"] for d in descs]),
+                                         ia(*[d["cout"] for d in descs]), ia(*[d["swapped"] for d in descs]), n, _s()),
+               "b2_wgrad_reduce_multi")
+    _count((n + 15) // 16)
+
+
 def conv3d_first_fwd(x, w, y, relu=True):
     """x fp32 [N, 1, D, H, W] contiguous; w fp32 [cout, 1, 3, 3, 3]; y ActView"""
     lib = _lib.load()

@@ -80,6 +80,7 @@ class BucketedGradReducer(object):
             layers = [l for l in active_layers if _BUCKET_OF_LAYER[l] == b]
             if layers:
                 self._close_at[min(layers)] = b    # backward visits layers in decreasing order
+        self.model.grad_flush_at = set(self._close_at)   # deferred weight-gradient reductions flush where buckets close
         # gradients of frozen parameters are not produced: keep their slots at zero
         for v, n in zip(self.views, needs):
             if not n:

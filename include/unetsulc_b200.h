@@ -69,6 +69,16 @@ int b2_conv3d_wgrad(const void* x, int ldx, int x_coff, const void* dy, int ldy,
                     void* workspace, long long workspace_bytes, int N, int D, int H, int W, int Cin, int Cout,
                     cudaStream_t stream);
 
+/* The same in two halves, so that the split reductions of SEVERAL layers run as one launch (13 short latency-bound
+ * launches per step otherwise): b2_conv3d_wgrad_partial runs the tensor-core kernel and leaves the split partials in
+ * `workspace` (private to that layer until reduced; *splits_out / *swapped_out describe their layout);
+ * b2_wgrad_reduce_multi reduces `count` layers (HOST arrays of `count` entries) into their dW tensors.            */
+int b2_conv3d_wgrad_partial(const void* x, int ldx, int x_coff, const void* dy, int ldy, int y_coff, void* workspace,
+                            long long workspace_bytes, int N, int D, int H, int W, int Cin, int Cout,
+                            int* splits_out, int* swapped_out, cudaStream_t stream);
+int b2_wgrad_reduce_multi(const float* const* ws, float* const* dw, const int* splits, const int* cin,
+                          const int* cout, const int* swapped, int count, cudaStream_t stream);
+
 /* encoders.0.conv1 (Cin = 1): direct convolution on the fp32 [N,D,H,W] skeleton volume (dataset.py:78-80)        */
 int b2_conv3d_first_fwd(const float* x, const float* w, void* y, int ldy, int y_coff, int N, int D, int H, int W,
                         int Cout, int relu, cudaStream_t stream);

@@ -293,3 +293,18 @@ def test_num_conv_chain_head_matches_sequential_reference():
     torch.cuda.synchronize()
     for b, p, g in zip(before, ours.head_parameters(), grads[42:]):
         assert torch.allclose(p.detach(), b - 1e-2 * g, rtol=1e-5, atol=1e-7)
+
+
+def test_deferred_weight_gradient_reduction_is_bit_identical(monkeypatch):
+    """B2_WGRAD_REDUCE=defer (b2_conv3d_wgrad_partial + one b2_wgrad_reduce_multi launch) == the inline reduction."""
+    from unetsulc_b200 import models
+    ref, ours = _pair()
+    x, labels = _data()
+    ours.train()
+    monkeypatch.setattr(models, "_WGRAD_REDUCE", "inline")
+    _, _, _, g_inline = ours.forward_backward(x, labels)
+    monkeypatch.setattr(models, "_WGRAD_REDUCE", "defer")
+    _, _, _, g_defer = ours.forward_backward(x, labels)
+    torch.cuda.synchronize()
+    for (n, _), a, b in zip(ours.named_parameters(), g_inline, g_defer):
+        assert rel_l2(b, a) < 1e-6, n
