@@ -295,7 +295,7 @@ def test_num_conv_chain_head_matches_sequential_reference():
         assert torch.allclose(p.detach(), b - 1e-2 * g, rtol=1e-5, atol=1e-7)
 
 
-def test_deferred_weight_gradient_reduction_is_bit_identical(monkeypatch):
+def test_deferred_weight_gradient_reduction_matches_inline(monkeypatch):
     """B2_WGRAD_REDUCE=defer (b2_conv3d_wgrad_partial + one b2_wgrad_reduce_multi launch) == the inline reduction."""
     from unetsulc_b200 import models
     ref, ours = _pair()
