@@ -165,6 +165,17 @@ class UnetPatternSulciLabelling(object):
             c = cache[gfile] = (bck2, names, pts - np.min(pts, axis=0), ids)
         return c[2], c[3]
 
+    def _name_ids(self, names):
+        """int32 class ids of a list of sulcus names (-2 for names outside sulci_side_list); converted once per list
+        object — 30 k dictionary look-ups per graph otherwise"""
+        cache = self.__dict__.setdefault("_name_id_cache", {})
+        c = cache.get(id(names))
+        if c is None or c[0] is not names:
+            if len(cache) > 256:
+                cache.clear()
+            c = cache[id(names)] = (names, np.asarray([self.dict_sulci.get(nm, -2) for nm in names], dtype=np.int32))
+        return c[1]
+
     def _labeling_device(self, gfile, bck2=None, names=None, imgsize=None, exact=None):
         """The device half of labeling(): eval forward + Softmax scores gathered at the skeleton points.
         Returns (scores fp32 [n, C], preds int32 [n], ytrue int64 [n]) as DEVICE tensors."""
@@ -248,8 +259,7 @@ class UnetPatternSulciLabelling(object):
             fold = ops.match_voxels(torch.from_numpy(nbck).to(dev), torch.from_numpy(nbck_nc).to(dev),
                                     torch.from_numpy(vert_nc.astype(np.int32)).to(dev))
             cut = ops.fold_vote(scores, fold, n_folds, [int(t) for t in threshold_range])     # int32 [T, n]
-            true_ids = torch.as_tensor([self.dict_sulci.get(nm, -2) for nm in data['names']], dtype=torch.int32,
-                                       device=dev)
+            true_ids = torch.from_numpy(self._name_ids(data['names'])).to(dev)
             counts = torch.zeros((len(threshold_range), 3, n_classes), dtype=torch.int64, device=dev)
             for t in range(len(threshold_range)):
                 ops.esi_counts(true_ids, cut[t], n_classes, counts[t])
