@@ -65,7 +65,7 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w /
     }
     if (relu) {
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) acc[c] = fmaxf(acc[c], 0.f);
+      for (int c = 0; c < COUT; ++c) acc[c] = relu_nan(acc[c]);
     }
     if (active) {
       uint4* dst = reinterpret_cast<uint4*>(y + v * ldy + y_coff);

@@ -212,7 +212,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             float f = __uint_as_float(v[e]);
-            if (p.relu) f = fmaxf(f, 0.f);
+            if (p.relu) f = relu_nan(f);
             f = valid ? __bfloat162float(__float2bfloat16_rn(f)) : 0.f;   // statistics of what is stored
             xs[e] = f;
             xq[e] = f * f;
@@ -247,7 +247,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               o.z = __uint_as_float(v[4 * j + 2]);
               o.w = __uint_as_float(v[4 * j + 3]);
               if (p.relu) {
-                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                o.x = relu_nan(o.x); o.y = relu_nan(o.y); o.z = relu_nan(o.z); o.w = relu_nan(o.w);
               }
               dst[j] = o;
             }
@@ -259,7 +259,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 f[e] = __uint_as_float(v[8 * j + e]);
-                if (p.relu) f[e] = fmaxf(f[e], 0.f);
+                if (p.relu) f[e] = relu_nan(f[e]);
               }
               uint4 o;
               o.x = pack_bf16x2(f[0], f[1]);
@@ -456,7 +456,7 @@ conv3d_igemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             float f = __uint_as_float(v[e]);
-            if (p.relu) f = fmaxf(f, 0.f);
+            if (p.relu) f = relu_nan(f);
             f = valid ? __bfloat162float(__float2bfloat16_rn(f)) : 0.f;
             xs[e] = f;
             xq[e] = f * f;
@@ -488,7 +488,7 @@ conv3d_igemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               f[e] = __uint_as_float(v[8 * j + e]);
-              if (p.relu) f[e] = fmaxf(f[e], 0.f);
+              if (p.relu) f[e] = relu_nan(f[e]);
             }
             uint4 o;
             o.x = pack_bf16x2(f[0], f[1]);
@@ -541,7 +541,7 @@ conv_splitk_reduce_kernel(const float* __restrict__ partial, int splits, long lo
       const float4 t = *reinterpret_cast<const float4*>(partial + s * split_stride + v * C + c);
       a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
     }
-    if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    if (relu) { a.x = relu_nan(a.x); a.y = relu_nan(a.y); a.z = relu_nan(a.z); a.w = relu_nan(a.w); }
     uint2 o;
     o.x = pack_bf16x2(a.x, a.y);
     o.y = pack_bf16x2(a.z, a.w);

@@ -238,7 +238,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               float f = __uint_as_float(v[e]);
-              if (p.relu) f = fmaxf(f, 0.f);
+              if (p.relu) f = relu_nan(f);
               f = valid ? __bfloat162float(__float2bfloat16_rn(f)) : 0.f;
               xs[e] = f;
               xq[e] = f * f;
@@ -270,7 +270,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 f[e] = __uint_as_float(v[8 * j + e]);
-                if (p.relu) f[e] = fmaxf(f[e], 0.f);
+                if (p.relu) f[e] = relu_nan(f[e]);
               }
               uint4 ov;
               ov.x = pack_bf16x2(f[0], f[1]);

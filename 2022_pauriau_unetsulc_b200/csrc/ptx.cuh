@@ -276,6 +276,9 @@ __device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane) {
   }
 }
 
+// ReLU that propagates NaN like torch.relu does (fmaxf(NaN, 0) would return 0 and silently "heal" a diverged run)
+__device__ __forceinline__ float relu_nan(float f) { return f < 0.f ? 0.f : f; }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);

@@ -328,3 +328,41 @@ def test_step_metrics_equal_host_esi_and_loss():
     want = esi_score_ref(labels[m].tolist() * 2, preds[m].tolist() * 2, list(range(9)))
     assert abs(stats.esi_from_counts(counts, list(range(9))) - want) < 1e-12
     assert acc.tolist() == [3.0, 4.0]
+
+
+def test_learning_batch_size_2_pads_to_prescanned_size(tmp_path):
+    """batch_size > 1 (training.py:119-136): every volume is padded to the largest box seen over num_epochs augmented
+    passes (found without building volumes: SulciDataset.item_size), generators re-seeded; the padded size is recorded in
+    the results like the reference does; the run is deterministic."""
+    from unetsulc_b200.training import UnetTrainingSulciLabelling
+    bck2, names, sslist = harness.synthetic_cohort(n_subjects=5, shape=(14, 16, 12), n_classes=6, seed=2)
+    files = sorted(bck2)
+    runs = []
+    for rep in range(2):
+        random.seed(1); np.random.seed(1); torch.manual_seed(1)
+        with _quiet():
+            m = UnetTrainingSulciLabelling(files, 'L', cuda=0, working_path=str(tmp_path), dict_model={'name': 'b2'},
+                                           dict_names=names, dict_bck2=bck2, sulci_side_list=sslist)
+            m.learning(1e-2, 0.9, 2, files[:4], files[4:], batch_size=2)
+        r = m.results
+        assert len(r['train_image_size']) == 3 and len(r['val_image_size']) == 3
+        assert all(a >= b for a, b in zip(r['train_image_size'], (14, 16, 12)))
+        assert len(r['epoch_loss_train'][0]) == 2 and np.isfinite(r['epoch_loss_train'][0]).all()
+        assert [t["steps"] for t in m.timings["train"]] == [2, 2]
+        runs.append((r['epoch_loss_train'], r['epoch_loss_val'], r['train_image_size']))
+    assert runs[0] == runs[1]
+
+
+def test_diverged_weights_give_nan_not_finite_garbage():
+    """non-finite partial sums used to be converted to integers in the fixed-point statistics accumulators
+    (undefined behaviour, finite-looking GroupNorm statistics).  They now poison the accumulator: the loss is NaN, as
+    with a floating-point reduction."""
+    import unetsulc_b200
+    from oracle.synth import synth_volume
+    torch.manual_seed(0)
+    model = unetsulc_b200.UNet3D(1, 8).cuda().train()
+    with torch.no_grad():
+        model.decoders[2].double_conv.conv1.weight[3, 5, 1, 1, 1] = float("inf")
+    x, labels = synth_volume((16, 24, 32), 8, 5, occupancy=0.06)
+    loss, _, _, grads = model.forward_backward(x.unsqueeze(0).cuda(), labels.unsqueeze(0).cuda())
+    assert not torch.isfinite(loss[0])
