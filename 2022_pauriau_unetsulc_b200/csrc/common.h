@@ -78,9 +78,19 @@ __device__ __forceinline__ double stat_read(const long long* slot) {
   return (double)__ldcg(slot) + (double)lo * (1.0 / 4294967296.0);
 }
 
+// pdl_wait: nothing of the preceding grid is read or written before it.  pdl_trigger: the NEXT kernel may be staged.
+// Round 1 triggered at the very start of every block: the dependent grid was scheduled (and sat waiting on SM slots)
+// for the whole duration of the primary — measured slower.  Round 2 triggers late: generic kernels only from the blocks
+// of (roughly) their LAST resident wave (earlier blocks count as triggered when they exit), the persistent convolution
+// kernels when a CTA's producers have issued their last load.  MEASURED (round 2, 1 x B200, two A/B pairs of 40-step
+// graph replays): 6.80 / 6.82 ms with the attribute against 6.68 / 6.70 ms without — still a loss, so B2_PDL stays
+// opt-in.  No-ops unless the launch carries the PDL attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  pdl_wait();
+  const unsigned lin = blockIdx.x + blockIdx.y * gridDim.x, total = gridDim.x * gridDim.y;
+  if (lin + 592u >= total) pdl_trigger();   // 592 = 148 SMs x 4 resident blocks: the last wave of a multi-wave grid
 }
 
 template <typename... KArgs, typename... Args>

@@ -73,7 +73,7 @@ template <int KC>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const IgemmParams p) {
-  pdl_prologue();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kABytes = 128 * KC * 2;
@@ -139,6 +139,7 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
     }
+    if (warp == 1) pdl_trigger();   // this CTA has issued its last loads: the next kernel may be staged
   } else if (warp == 0) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN, 0, 0);

@@ -51,7 +51,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                    const SlabParams p) {
   constexpr int kTH = 128 / kTW;
   constexpr int kPlaneRows = kTW * (kTH + 2);
-  pdl_prologue();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kRowBytes = KC * 2;
@@ -121,6 +121,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             __syncwarp();
           }
     }
+    if (warp == 1) pdl_trigger();   // last plane loads issued: the next kernel may be staged
   } else if (warp >= 4 && warp <= 6) {
     // ---------------------------------------------------------------- weight producers (one d-tap row each)
     const int ddi = warp - 4;   // dd + 1

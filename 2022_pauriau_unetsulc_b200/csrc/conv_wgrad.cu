@@ -42,7 +42,7 @@ static constexpr int kWgThreads = 32 * (1 + kWgProducers + 1 + 4);
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                     const WgradParams p) {
-  pdl_prologue();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem;                                   // 2 x dY tile
@@ -120,6 +120,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         __syncwarp();
       }
     }
+    if (warp == 1) pdl_trigger();   // last slot loads issued: the next kernel may be staged
   } else if (warp == kWgProducers + 1) {
     // ---------------------------------------------------------------- producer of the dY tiles
     int sb = 0;
