@@ -16,7 +16,7 @@
 // (tcgen05.st) after reading it.
 //
 // Warp roles: 0 MMA issuer (+TMEM), 1-3 plane producers (ring stage s owned by producer s mod 3), 4-6 weight
-// producers (one d-tap row each), 7 idle, 8-11 epilogue.  Whole-warp uniform loops, elected-lane issue.
+// producers (one d-tap row each), 7 idle, 8-15 epilogue (two warps per TMEM lane quarter).  Whole-warp uniform loops, elected-lane issue.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -39,7 +39,7 @@ struct SlabParams {
   long long total_tiles;
 };
 
-static constexpr int kSlabThreads = 32 * 12;
+static constexpr int kSlabThreads = 32 * 16;
 static constexpr int kTD = 4;
 
 // kTW x kTH x kTD output tile with kTW * kTH = 128 voxels per plane: 32 x 4 (round 1) or 16 x 8 — the second shape cuts
@@ -84,7 +84,7 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_init(&b_full[s], 3);
       mbar_init(&b_empty[s], 1);
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], 256);
     }
     fence_mbar_init();
   }
@@ -199,13 +199,26 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
   } else if (warp >= 8) {
-    // ---------------------------------------------------------------- epilogue
+    // ---------------------------------------------------------------- epilogue: 8 warps
+    // Warp (q, half): TMEM lane quarter q = warp & 3; with BN = 64 the two halves take the two 32-column chunks of every
+    // output plane, with BN = 32 they take the output planes {0, 1} / {2, 3}.  The GroupNorm statistics are accumulated
+    // PER THREAD (its row, 32 columns, 2 x 32 fp32 registers) over all tiles of the CTA and reduced across lanes ONCE at
+    // the end.  Round 1 ran a 2 x 31-shuffle transposing reduction per chunk, plane and tile in four warps: for the
+    // short-K layers (encoders.0.conv2, decoders.2.conv2, every dgrad with fused backward statistics) that epilogue was
+    // as long as the main loop — the same launches ran 15-45 us faster without statistics.
     const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = (warp - 8) >> 2;
     const int row = q * 32 + lane;    // accumulator row == voxel within the output plane: (h-line, w)
     const int lw = row % kTW, lh = row / kTW;
-    float st_s[2] = {0.f, 0.f}, st_q[2] = {0.f, 0.f};
+    const int n_chunks_n = BN / 32;   // 1 or 2
+    const int c0 = (n_chunks_n == 2) ? 32 * half : 0;
+    const int o_begin = (n_chunks_n == 2) ? 0 : 2 * half, o_end = (n_chunks_n == 2) ? kTD : 2 * half + 2;
+    float acc_s[32], acc_q[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) { acc_s[e] = 0.f; acc_q[e] = 0.f; }
     // every MMA accumulates: clear both accumulator sets once, then hand them to the MMA issuer
-    for (uint32_t c = 0; c < 512; c += 32) tmem_st32_zero(tmem_base + ((uint32_t)(q * 32) << 16) + c);
+    for (uint32_t c = 256u * half; c < 256u * half + 256u; c += 32)
+      tmem_st32_zero(tmem_base + ((uint32_t)(q * 32) << 16) + c);
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(&tmem_empty[0]);
@@ -221,64 +234,51 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const int w = w0 + lw, h = h0 + lh;
       mbar_wait(&tmem_full[acc], (it >> 1) & 1u);
       tc_fence_after();
-      for (int o = 0; o < kTD; ++o) {
+      for (int o = o_begin; o < o_end; ++o) {
         const int d = d0 + o;
         const bool valid = (w < p.W) && (h < p.H) && (d < p.D);
         const size_t vox = (((size_t)n * p.D + d) * p.H + h) * p.W + w;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(o * BN);
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)(o * BN + c0);
+        uint32_t v[32];
+        tmem_ld32(t_addr, v);
+        tmem_ld_wait();
+        tmem_st32_zero(t_addr);   // ready for the next tile's always-accumulating MMAs
+        uint32_t pk[16];
 #pragma unroll
-        for (int chunk = 0; chunk < 2; ++chunk) {
-          const int c0 = chunk * 32;
-          if (c0 >= BN) break;
-          uint32_t v[32];
-          tmem_ld32(t_addr + c0, v);
-          tmem_ld_wait();
-          tmem_st32_zero(t_addr + c0);   // ready for the next tile's always-accumulating MMAs
-          if (p.stat_acc != nullptr) {
-            float xs[32], xq[32];
+        for (int e = 0; e < 16; ++e) {
+          float f0 = __uint_as_float(v[2 * e]), f1 = __uint_as_float(v[2 * e + 1]);
+          if (p.relu) { f0 = relu_nan(f0); f1 = relu_nan(f1); }
+          pk[e] = pack_bf16x2(f0, f1);
+        }
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(p.y + vox * p.ldy + p.y_coff + c0);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              float f = __uint_as_float(v[e]);
-              if (p.relu) f = relu_nan(f);
-              f = valid ? __bfloat162float(__float2bfloat16_rn(f)) : 0.f;
-              xs[e] = f;
-              xq[e] = f * f;
-            }
-            if (p.stat_r != nullptr) {
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          if (p.stat_acc != nullptr) {   // statistics of what is STORED (bf16-rounded), this thread's row
+            if (p.stat_r != nullptr) {   // backward: sum dy, sum dy * r
               const uint4* rp = reinterpret_cast<const uint4*>(p.stat_r + vox * BN + c0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                uint4 u = make_uint4(0, 0, 0, 0);
-                if (valid) u = __ldg(rp + j);
+                const uint4 u = __ldg(rp + j);
                 const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  xq[8 * j + 2 * e] = xs[8 * j + 2 * e] * __uint_as_float(wds[e] << 16);
-                  xq[8 * j + 2 * e + 1] = xs[8 * j + 2 * e + 1] * __uint_as_float(wds[e] & 0xffff0000u);
+                  const float g0 = __uint_as_float(pk[4 * j + e] << 16), g1 = __uint_as_float(pk[4 * j + e] & 0xffff0000u);
+                  acc_s[8 * j + 2 * e] += g0;
+                  acc_s[8 * j + 2 * e + 1] += g1;
+                  acc_q[8 * j + 2 * e] = fmaf(g0, __uint_as_float(wds[e] << 16), acc_q[8 * j + 2 * e]);
+                  acc_q[8 * j + 2 * e + 1] = fmaf(g1, __uint_as_float(wds[e] & 0xffff0000u), acc_q[8 * j + 2 * e + 1]);
                 }
               }
-            }
-            warp_column_sums(xs, lane);
-            warp_column_sums(xq, lane);
-            st_s[chunk] += xs[0];
-            st_q[chunk] += xq[0];
-          }
-          if (valid) {
-            uint4* dst = reinterpret_cast<uint4*>(p.y + vox * p.ldy + p.y_coff + c0);
+            } else {                     // forward: sum r, sum r^2
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float f[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                f[e] = __uint_as_float(v[8 * j + e]);
-                if (p.relu) f[e] = relu_nan(f[e]);
+              for (int e = 0; e < 16; ++e) {
+                const float g0 = __uint_as_float(pk[e] << 16), g1 = __uint_as_float(pk[e] & 0xffff0000u);
+                acc_s[2 * e] += g0;
+                acc_s[2 * e + 1] += g1;
+                acc_q[2 * e] = fmaf(g0, g0, acc_q[2 * e]);
+                acc_q[2 * e + 1] = fmaf(g1, g1, acc_q[2 * e + 1]);
               }
-              uint4 ov;
-              ov.x = pack_bf16x2(f[0], f[1]);
-              ov.y = pack_bf16x2(f[2], f[3]);
-              ov.z = pack_bf16x2(f[4], f[5]);
-              ov.w = pack_bf16x2(f[6], f[7]);
-              dst[j] = ov;
             }
           }
         }
@@ -288,15 +288,25 @@ conv3d_slab_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_arrive(&tmem_empty[acc]);
     }
     if (p.stat_acc != nullptr) {
-      float2* sbuf = reinterpret_cast<float2*>(smem_p);   // [4][Cout] in the (now idle) plane ring
-#pragma unroll
-      for (int chunk = 0; chunk < 2; ++chunk)
-        if (chunk * 32 < BN) sbuf[q * BN + chunk * 32 + lane] = make_float2(st_s[chunk], st_q[chunk]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = q * 32 + lane; c < BN; c += 128) {
-        const float2 a = sbuf[c], b = sbuf[BN + c], cc = sbuf[2 * BN + c], d = sbuf[3 * BN + c];
-        stat_atomic_add(p.stat_acc + 4 * c, (a.x + b.x) + (cc.x + d.x));
-        stat_atomic_add(p.stat_acc + 4 * c + 2, (a.y + b.y) + (cc.y + d.y));
+      // one transposing reduction per thread-array: afterwards lane L holds the sums of column c0 + L over this warp's rows
+      warp_column_sums(acc_s, lane);
+      warp_column_sums(acc_q, lane);
+      float2* sbuf = reinterpret_cast<float2*>(smem_p);   // [8 warps][32] in the (now idle) plane ring
+      sbuf[(warp - 8) * 32 + lane] = make_float2(acc_s[0], acc_q[0]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 8 || (warp == 12 && n_chunks_n == 2)) {
+        // BN = 64: the four warps of a half cover one 32-column chunk; BN = 32: all eight warps cover the same 32 columns
+        const int wb = (n_chunks_n == 2) ? 4 * half : 0;
+        float2 a = sbuf[(wb + 0) * 32 + lane], b = sbuf[(wb + 1) * 32 + lane];
+        float2 cc = sbuf[(wb + 2) * 32 + lane], d = sbuf[(wb + 3) * 32 + lane];
+        float ssum = (a.x + b.x) + (cc.x + d.x), qsum = (a.y + b.y) + (cc.y + d.y);
+        if (n_chunks_n == 1) {
+          a = sbuf[4 * 32 + lane]; b = sbuf[5 * 32 + lane]; cc = sbuf[6 * 32 + lane]; d = sbuf[7 * 32 + lane];
+          ssum += (a.x + b.x) + (cc.x + d.x);
+          qsum += (a.y + b.y) + (cc.y + d.y);
+        }
+        stat_atomic_add(p.stat_acc + 4 * (c0 + lane), ssum);
+        stat_atomic_add(p.stat_acc + 4 * (c0 + lane) + 2, qsum);
       }
     }
   }
