@@ -421,9 +421,11 @@ def run_ours(args):
         "frac_vs_burst": achieved / burst if burst else None,
         "frac_vs_sustained": achieved / sustained if sustained else None,
         "launches_per_step": len(ig) / max(prof_steps, 1), "avg_launch_ms": ig_ms / max(len(ig), 1),
-        "share_of_step": ig_ms * 1e-3 / prof_secs if prof_secs > 0 else None,
+        # share of the TIMED (graph-replayed) step: kernel time per step from the eager event profile / replayed step time
+        # (the profiled eager steps themselves are slower: two events per conv launch keep the host busy)
+        "share_of_step": (ig_ms / max(prof_steps, 1)) / (secs / args.steps * 1e3) if secs > 0 else None,
         "wgrad_kernel_tflops": wg_tf, "wgrad_frac": (wg_tf / peak) if (wg_tf and peak) else None,
-        "wgrad_share_of_step": wg_ms * 1e-3 / prof_secs if prof_secs > 0 else None,
+        "wgrad_share_of_step": (wg_ms / max(prof_steps, 1)) / (secs / args.steps * 1e3) if secs > 0 else None,
         "profiled": "%d eager steps (%.3f ms/step) with CUDA events around every conv launch; the timed region "
                     "replays the same step as a CUDA graph" % (prof_steps, prof_secs / prof_steps * 1e3),
         "step_tflops": step_tf, "step_frac_vs_burst": step_tf / burst if burst else None,
