@@ -627,13 +627,18 @@ class UnetPatternSulciLabelling(object):
         bs = loader.batch_size or 1
         n = len(ds)
         n_batches = (n + bs - 1) // bs
+        # ownership and step count come from parallel.shard_subjects: batch b -> rank b % world, every rank the same
+        # number of steps (weight 0 = padding step)
+        plan = parallel.shard_subjects(range(n_batches), rank, world)
+        owned = {b for b, wgt in plan if wgt > 0}
         last = None
-        for step in range((n_batches + world - 1) // world):
+        for step in range(len(plan)):
             mine = None
             for r in range(world):
                 b = step * world + r
                 idx = range(b * bs, min((b + 1) * bs, n)) if b < n_batches else ()
                 if r == rank and len(idx):
+                    assert b in owned
                     items = [ds[i] for i in idx]
                     mine = (torch.stack([it[0] for it in items]), torch.stack([it[1] for it in items]))
                 elif hasattr(ds, "consume_draws"):
