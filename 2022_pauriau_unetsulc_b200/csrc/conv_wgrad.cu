@@ -12,6 +12,7 @@
 // deterministically into PyTorch's [co][ci][kd][kh][kw] layout.
 #include "common.h"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace b2 {
 
@@ -30,6 +31,7 @@ struct WgradParams {
   long long ksteps_total;
   int stages_a, n_prod;   // ring depth (a multiple of n_prod) and number of active slot-group producers
   int a_bytes, b_bytes, slot_bytes;
+  int halo;      // "dY-halo" mode (fixed operand 64 channels wide, one-plane tile boxes): see plan_wgrad
   float* ws;
 };
 
@@ -112,7 +114,11 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             int s = g * p.SPG + j;
             if (s >= p.total_slots) s = p.total_slots - 1;  // padding slot: result discarded
             const int tap = s / p.n_cchunks, cc = s % p.n_cchunks;
-            const int dd = tap / 9 - 1, dh = (tap / 3) % 3 - 1, dw = tap % 3 - 1;
+            // halo mode: a slot is a (d, w) shift of the shifted operand only (9 per chunk); the three h taps come
+            // from the h-halo of the FIXED operand's tile (three N atoms of one MMA)
+            const int dd = p.halo ? tap / 3 - 1 : tap / 9 - 1;
+            const int dh = p.halo ? 0 : (tap / 3) % 3 - 1;
+            const int dw = tap % 3 - 1;
             tma_load_5d(smem_a + (size_t)sa * p.a_bytes + (size_t)j * p.slot_bytes, &tmap_x, &full_a[sa],
                         cc * p.SWC, w0 + dw, h0 + dh, d0 + dd, n);
           }
@@ -136,19 +142,27 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       mbar_wait(&empty_b[sb], pb ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&full_b[sb], (uint32_t)p.b_bytes);
-        for (int j = 0; j < p.BN / 64; ++j)
-          tma_load_5d(smem_b + (size_t)sb * p.b_bytes + (size_t)j * 16384, &tmap_dy, &full_b[sb], n0 + j * 64, w0, h0,
-                      d0, n);
+        if (p.halo) {   // one box with an h-halo: (bh + 2) lines of bw voxels x 64 channels, zero-filled outside
+          tma_load_5d(smem_b + (size_t)sb * p.b_bytes, &tmap_dy, &full_b[sb], n0, w0, h0 - 1, d0, n);
+        } else {
+          for (int j = 0; j < p.BN / 64; ++j)
+            tma_load_5d(smem_b + (size_t)sb * p.b_bytes + (size_t)j * 16384, &tmap_dy, &full_b[sb], n0 + j * 64, w0,
+                        h0, d0, n);
+        }
       }
       __syncwarp();
       if (++sb == 2) { sb = 0; pb ^= 1; }
     }
   } else if (warp == 0) {
-    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)p.BN, 1, 1);
+    // halo mode: N = 3 x 64 — the three N atoms are the SAME dY tile shifted by -1 / 0 / +1 h-lines (atom stride = one
+    // h-line of bw voxel rows), i.e. one MMA accumulates the three h taps of the slot pair: 6 taps per instruction,
+    // 10 KB of shared-memory reads for 96 tensor-cycles instead of 6 KB for 32
+    const uint32_t acc_cols = p.halo ? 192u : (uint32_t)p.BN;
+    const uint32_t idesc = make_idesc_bf16(128, acc_cols, 1, 1);
     const uint32_t layout_a = (p.SWC == 64) ? SWZ_128B : SWZ_64B;
     const uint32_t row_a = (uint32_t)p.SWC * 2u;
     const uint64_t a_hi = make_smem_desc(0, (uint32_t)p.slot_bytes, 8 * row_a, layout_a);
-    const uint64_t b_hi = make_smem_desc(0, 16384, 1024, SWZ_128B);
+    const uint64_t b_hi = make_smem_desc(0, p.halo ? (uint32_t)p.bw * 128u : 16384u, 1024, SWZ_128B);
     const uint32_t a0 = smem_u32(smem_a) >> 4, b0 = smem_u32(smem_b) >> 4;
     const uint32_t a_kstep = (16 * row_a) >> 4, b_kstep = (16 * 128) >> 4;   // encoded advance per K16 (16 voxels)
     int sa = 0, sb = 0;
@@ -162,7 +176,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         tc_fence_after();
         if (elect_one()) {
           const uint64_t adesc = a_hi | (uint64_t)(a0 + (uint32_t)sa * ((uint32_t)p.a_bytes >> 4));
-          const uint32_t d_tmem = tmem_base + (uint32_t)(g - g_begin) * p.BN;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(g - g_begin) * acc_cols;
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // 128 voxels = 8 x K16
             umma_bf16(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc, (t != t_begin || k > 0) ? 1u : 0u);
@@ -187,6 +201,25 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       const bool valid = (s < p.total_slots) && (t_end > t_begin);
       const int tap = s / p.n_cchunks;
       const int ci = (s % p.n_cchunks) * p.SWC + row % p.SWC;
+      if (p.halo) {
+        // accumulator columns [64 j, 64 j + 64): h tap dh = 1 - j of the slot's (dd, dw) shift
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g - g_begin) * 192u;
+        for (int c0 = 0; c0 < 192; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            const int full_tap = (tap / 3) * 9 + (2 - c0 / 64) * 3 + tap % 3;
+            float4* d4 = reinterpret_cast<float4*>(p.ws + (((size_t)split * 27 + full_tap) * p.Cin + ci) * p.Cout + n0 +
+                                                   (c0 & 63));
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                  __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          }
+        }
+        continue;
+      }
       float* dst = p.ws + (((size_t)split * 27 + tap) * p.Cin + ci) * p.Cout + n0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g - g_begin) * p.BN;
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
@@ -435,7 +468,7 @@ static void choose_box_w(int W, int H, int D, int& bw, int& bh, int& bd) {
     }
 }
 
-static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int Cout) {
+static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int Cout, bool allow_halo) {
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   choose_box_w(W, H, D, p.bw, p.bh, p.bd);
   p.tiles_w = ceil_div(W, p.bw);
@@ -443,12 +476,19 @@ static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int C
   p.tiles_d = ceil_div(D, p.bd);
   p.SWC = (Cin % 64 == 0) ? 64 : 32;
   p.n_cchunks = Cin / p.SWC;
-  p.total_slots = 27 * p.n_cchunks;
-  p.SPG = 128 / p.SWC;
-  p.G = ceil_div(p.total_slots, p.SPG);
   p.BN = (Cout % 256 == 0) ? 256 : (Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : 64));
   p.n_cout_tiles = Cout / p.BN;
-  const int P = 512 / p.BN;
+  // "dY-halo" mode for the 64-wide fixed operand (decoders.2.conv2, encoders.1.conv1, encoders.0.conv2: round 1 ran them
+  // at 640-790 TFLOP/s, bound by re-loading the shifted operand 27 times per K-step and by the 128 x 64 MMA's
+  // shared-memory read rate).  dW[tap] = sum_u X[u + s] dY[u + t] with tap = s - t: the (d, w) part of the tap shifts X
+  // (9 slots per chunk instead of 27), the h part shifts dY — whose tile is loaded ONCE with an h-halo and read by the MMA
+  // as three N atoms one h-line apart (N = 192).  Needs one-plane tile boxes (an h-line = bw consecutive voxel rows).
+  static const bool no_halo = getenv("B2_NO_WGRAD_HALO") != nullptr;
+  p.halo = (allow_halo && !no_halo && Cout == 64 && p.bd == 1 && p.bw % 8 == 0) ? 1 : 0;
+  p.total_slots = (p.halo ? 9 : 27) * p.n_cchunks;
+  p.SPG = 128 / p.SWC;
+  p.G = ceil_div(p.total_slots, p.SPG);
+  const int P = p.halo ? 2 : 512 / p.BN;
   p.n_gchunks = ceil_div(p.G, P);
   p.gpc = ceil_div(p.G, p.n_gchunks);
   p.n_gchunks = ceil_div(p.G, p.gpc);
@@ -460,7 +500,7 @@ static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int C
   p.splits = splits;
   p.slot_bytes = 128 * p.SWC * 2;
   p.a_bytes = 128 * 128 * 2;
-  p.b_bytes = 128 * p.BN * 2;
+  p.b_bytes = p.halo ? (p.bh + 2) * p.bw * 128 : 128 * p.BN * 2;
   const int budget = 227 * 1024 - 1024 - 512;
   p.stages_a = (budget - 2 * p.b_bytes) / p.a_bytes;
   if (p.stages_a > 4) p.stages_a = 4;
@@ -478,7 +518,7 @@ extern "C" long long b2_conv3d_wgrad_workspace_bytes(int N, int D, int H, int W,
   if (Cin % 32 != 0 || Cout % 64 != 0 || N <= 0 || D <= 0 || H <= 0 || W <= 0) return -1;
   WgradParams p;
   const bool swap = wgrad_swap_roles(Cin, Cout);
-  if (plan_wgrad(p, N, D, H, W, swap ? Cout : Cin, swap ? Cin : Cout) != 0) return -1;
+  if (plan_wgrad(p, N, D, H, W, swap ? Cout : Cin, swap ? Cin : Cout, !swap) != 0) return -1;
   return (long long)p.splits * 27 * Cin * Cout * (long long)sizeof(float);
 }
 
@@ -498,7 +538,7 @@ static int wgrad_partial_impl(const void* x, int ldx, int x_coff, const void* dy
   const int sh_c = swap ? Cout : Cin, fx_c = swap ? Cin : Cout;
   const int sh_ld = swap ? ldy : ldx, sh_off = swap ? y_coff : x_coff;
   const int fx_ld = swap ? ldx : ldy, fx_off = swap ? x_coff : y_coff;
-  B2_REQUIRE(plan_wgrad(p, N, D, H, W, sh_c, fx_c) == 0, "b2_conv3d_wgrad: tile does not fit shared memory");
+  B2_REQUIRE(plan_wgrad(p, N, D, H, W, sh_c, fx_c, !swap) == 0, "b2_conv3d_wgrad: tile does not fit shared memory");
   const long long need = (long long)p.splits * 27 * Cin * Cout * (long long)sizeof(float);
   B2_REQUIRE(workspace_bytes >= need, "b2_conv3d_wgrad: workspace %lld < %lld bytes", workspace_bytes, need);
   p.ws = reinterpret_cast<float*>(workspace);
@@ -506,7 +546,7 @@ static int wgrad_partial_impl(const void* x, int ldx, int x_coff, const void* dy
   CUtensorMap tx, ty;
   int rc = make_act_tmap(&tx, sh_ptr, N, D, H, W, sh_c, sh_ld, sh_off, p.SWC, p.bw, p.bh, p.bd);
   if (rc) return rc;
-  rc = make_act_tmap(&ty, fx_ptr, N, D, H, W, fx_c, fx_ld, fx_off, 64, p.bw, p.bh, p.bd);
+  rc = make_act_tmap(&ty, fx_ptr, N, D, H, W, fx_c, fx_ld, fx_off, 64, p.bw, p.halo ? p.bh + 2 : p.bh, p.bd);
   if (rc) return rc;
 
   const size_t smem_bytes = 2 * (size_t)p.b_bytes + (size_t)p.stages_a * p.a_bytes + 1024 + 512;

@@ -236,6 +236,11 @@ WGRAD_SHAPES = [
     (1, 256, 512, 3, 4, 5),
     (2, 64, 128, 5, 7, 9),
     (1, 384, 128, 4, 6, 8),
+    # 64-wide fixed operand with one-plane tile boxes: the "dY-halo" mode (three h taps per MMA)
+    (1, 32, 64, 5, 12, 32),
+    (2, 64, 64, 3, 9, 16),       # ragged h tiles: the halo lines of the last tile are out of range
+    (1, 96, 64, 3, 8, 16),       # three 32-channel chunks
+    (1, 64, 64, 2, 3, 128),      # one-line tiles (bh = 1): the halo is two thirds of the box
 ]
 
 
