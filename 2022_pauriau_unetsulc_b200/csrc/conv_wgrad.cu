@@ -32,6 +32,8 @@ struct WgradParams {
   int stages_a, n_prod;   // ring depth (a multiple of n_prod) and number of active slot-group producers
   int a_bytes, b_bytes, slot_bytes;
   int halo;      // "dY-halo" mode (fixed operand 64 channels wide, one-plane tile boxes): see plan_wgrad
+  int stages_b;    // depth of the fixed-operand ring (2-4)
+  int merge_last;  // a CTA of the LAST group chunk (fewer groups than the others) covers this many consecutive splits
   float* ws;
 };
 
@@ -47,27 +49,42 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_b = smem;                                   // 2 x dY tile
-  uint8_t* smem_a = smem + 2 * (size_t)p.b_bytes;           // stages_a x slot group
+  uint8_t* smem_b = smem;                                          // stages_b x dY tile
+  uint8_t* smem_a = smem + (size_t)p.stages_b * p.b_bytes;         // stages_a x slot group
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages_a * p.a_bytes);
   uint64_t* full_a = bars;
   uint64_t* empty_a = bars + p.stages_a;
   uint64_t* full_b = bars + 2 * p.stages_a;
-  uint64_t* empty_b = full_b + 2;
-  uint64_t* acc_full = empty_b + 2;
+  uint64_t* empty_b = full_b + p.stages_b;
+  uint64_t* acc_full = empty_b + p.stages_b;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
 
-  const int gchunk = blockIdx.x % p.n_gchunks;
-  const int nt = blockIdx.x / p.n_gchunks;
-  const int split = blockIdx.y;
+  // 1-D grid: first the CTAs of the full group chunks (one per chunk x cout tile x split), then those of the last
+  // chunk, each covering `merge_last` consecutive splits (so a chunk with half the groups gets half the CTAs and every
+  // CTA issues about the same number of MMAs); its partial lands in the first of those split slices, zeros in the rest
+  const int full_x = (p.n_gchunks - 1) * p.n_cout_tiles;
+  const int n_full = full_x * p.splits;
+  int gchunk, nt, split, split_hi;
+  if ((int)blockIdx.x < n_full) {
+    gchunk = (int)blockIdx.x % full_x % (p.n_gchunks - 1);
+    nt = (int)blockIdx.x % full_x / (p.n_gchunks - 1);
+    split = (int)blockIdx.x / full_x;
+    split_hi = split + 1;
+  } else {
+    const int j = (int)blockIdx.x - n_full;
+    gchunk = p.n_gchunks - 1;
+    nt = j % p.n_cout_tiles;
+    split = (j / p.n_cout_tiles) * p.merge_last;
+    split_hi = min(split + p.merge_last, p.splits);
+  }
   const int g_begin = gchunk * p.gpc;
   const int g_end = min(g_begin + p.gpc, p.G);
   const int n0 = nt * p.BN;
   const long long t_begin = p.ksteps_total * split / p.splits;
-  const long long t_end = p.ksteps_total * (split + 1) / p.splits;
+  const long long t_end = p.ksteps_total * split_hi / p.splits;
 
   if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -76,7 +93,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       mbar_init(&full_a[s], 1);
       mbar_init(&empty_a[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < p.stages_b; ++s) {
       mbar_init(&full_b[s], 1);
       mbar_init(&empty_b[s], 1);
     }
@@ -151,7 +168,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         }
       }
       __syncwarp();
-      if (++sb == 2) { sb = 0; pb ^= 1; }
+      if (++sb == p.stages_b) { sb = 0; pb ^= 1; }
     }
   } else if (warp == 0) {
     // halo mode: N = 3 x 64 — the three N atoms are the SAME dY tile shifted by -1 / 0 / +1 h-lines (atom stride = one
@@ -189,11 +206,12 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         __syncwarp();
         if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
       }
-      if (++sb == 2) { sb = 0; pb ^= 1; }
+      if (++sb == p.stages_b) { sb = 0; pb ^= 1; }
     }
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const size_t slice4 = (size_t)27 * p.Cin * p.Cout / 4;   // one split slice of the workspace, in float4
     mbar_wait(acc_full, 0);
     tc_fence_after();
     for (int g = g_begin; g < g_end; ++g) {
@@ -216,6 +234,11 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             for (int j = 0; j < 8; ++j)
               d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            for (int e = split + 1; e < split_hi; ++e) {
+              d4 += slice4;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) d4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
         }
         continue;
@@ -232,6 +255,11 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           for (int j = 0; j < 8; ++j)
             d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          for (int e = split + 1; e < split_hi; ++e) {
+            d4 += slice4;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
       }
     }
@@ -468,6 +496,10 @@ static void choose_box_w(int W, int H, int D, int& bw, int& bh, int& bd) {
     }
 }
 
+static int wgrad_ctas(const WgradParams& p, int splits) {
+  return ((p.n_gchunks - 1) * splits + ceil_div(splits, p.merge_last)) * p.n_cout_tiles;
+}
+
 static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int Cout, bool allow_halo) {
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   choose_box_w(W, H, D, p.bw, p.bh, p.bd);
@@ -493,9 +525,21 @@ static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int C
   p.gpc = ceil_div(p.G, p.n_gchunks);
   p.n_gchunks = ceil_div(p.G, p.gpc);
   p.ksteps_total = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
-  const int base_ctas = p.n_gchunks * p.n_cout_tiles;
-  int splits = num_sms() / base_ctas;
-  if (splits < 1) splits = 1;
+  // the last chunk may hold fewer groups than the others (halo mode: 5 groups as 2 + 2 + 1): its CTAs then cover
+  // merge_last splits each, and the freed SMs go to a finer split
+  // (a merged CTA runs twice the K-steps at half the MMAs per step, which only pays if the split gets >= 10 % finer:
+  // measured, 384 -> 128 with one group of four merged x4 went from 280 to 435 us, bound by its per-step loads)
+  const int g_last = p.G - (p.n_gchunks - 1) * p.gpc;
+  p.merge_last = 1;
+  int splits = 1;
+  while (wgrad_ctas(p, splits + 1) <= num_sms()) ++splits;
+  static const bool no_merge = getenv("B2_NO_WGRAD_MERGE") != nullptr;
+  if (p.n_gchunks > 1 && 2 * g_last <= p.gpc && !no_merge) {
+    p.merge_last = 2;
+    int s2 = 1;
+    while (wgrad_ctas(p, s2 + 1) <= num_sms()) ++s2;
+    if (s2 * 10 >= splits * 11) splits = s2; else p.merge_last = 1;
+  }
   if ((long long)splits > p.ksteps_total) splits = (int)p.ksteps_total;
   p.splits = splits;
   p.slot_bytes = 128 * p.SWC * 2;
@@ -507,7 +551,12 @@ static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int C
   // a producer must never be two ring phases ahead of the consumer: give every stage a fixed owner
   p.n_prod = p.stages_a < kWgProducers ? p.stages_a : kWgProducers;
   p.stages_a = (p.stages_a / p.n_prod) * p.n_prod;
-  return p.stages_a >= 2 ? 0 : -1;
+  if (p.stages_a < 2) return -1;
+  // what is left deepens the fixed-operand ring (few groups per K-step = short steps: two stages do not cover the
+  // load latency)
+  p.stages_b = (budget - p.stages_a * p.a_bytes) / p.b_bytes;
+  if (p.stages_b > 4) p.stages_b = 4;
+  return 0;
 }
 
 }  // namespace b2
@@ -549,9 +598,9 @@ static int wgrad_partial_impl(const void* x, int ldx, int x_coff, const void* dy
   rc = make_act_tmap(&ty, fx_ptr, N, D, H, W, fx_c, fx_ld, fx_off, 64, p.bw, p.halo ? p.bh + 2 : p.bh, p.bd);
   if (rc) return rc;
 
-  const size_t smem_bytes = 2 * (size_t)p.b_bytes + (size_t)p.stages_a * p.a_bytes + 1024 + 512;
+  const size_t smem_bytes = (size_t)p.stages_b * p.b_bytes + (size_t)p.stages_a * p.a_bytes + 1024 + 512;
   B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  dim3 grid((unsigned)(p.n_gchunks * p.n_cout_tiles), (unsigned)p.splits);
+  dim3 grid((unsigned)wgrad_ctas(p, p.splits));
   B2_LAUNCH(conv3d_wgrad_kernel, grid, kWgThreads, smem_bytes, stream, tx, ty, p);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;
