@@ -32,6 +32,7 @@ struct WgradParams {
   int stages_a, n_prod;   // ring depth (a multiple of n_prod) and number of active slot-group producers
   int a_bytes, b_bytes, slot_bytes;
   int halo;      // "dY-halo" mode (fixed operand 64 channels wide, one-plane tile boxes): see plan_wgrad
+  int d_fast;      // K-step order (w, d, h) instead of (w, h, d): see wgrad_tile
   int stages_b;    // depth of the fixed-operand ring (2-4)
   int merge_last;  // a CTA of the LAST group chunk (fewer groups than the others) covers this many consecutive splits
   float* ws;
@@ -42,6 +43,27 @@ struct WgradParams {
 // B200, ops of different warps run in parallel: tools/micro/tma_bench2.cu.)
 static constexpr int kWgProducers = 4;
 static constexpr int kWgThreads = 32 * (1 + kWgProducers + 1 + 4);
+
+// K-step -> tile origin.  A split owns a contiguous range of K-steps, i.e. a slab of the volume, and re-reads the
+// neighbouring planes / lines its shifted boxes touch.  Default order (w, h, d): slabs of whole planes.  Halo mode
+// shifts X only in (d, w), so with the order (w, d, h) a split is a band of h-lines through ALL planes: the d +- 1
+// planes of one tile are the next tiles of the same CTA (L2 hits) and no X line is fetched by two splits (measured:
+// decoders.2.conv2 read 691 MB from DRAM with 59 plane-slabs of 1.6 planes each, 264 MB being the operands).
+__device__ __forceinline__ void wgrad_tile(long long t, const WgradParams& p, int& n, int& d0, int& h0, int& w0) {
+  w0 = (int)(t % p.tiles_w) * p.bw;
+  t /= p.tiles_w;
+  if (p.d_fast) {
+    d0 = (int)(t % p.tiles_d) * p.bd;
+    t /= p.tiles_d;
+    h0 = (int)(t % p.tiles_h) * p.bh;
+    n = (int)(t / p.tiles_h);
+  } else {
+    h0 = (int)(t % p.tiles_h) * p.bh;
+    t /= p.tiles_h;
+    d0 = (int)(t % p.tiles_d) * p.bd;
+    n = (int)(t / p.tiles_d);
+  }
+}
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
@@ -113,13 +135,8 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const int me = warp - 1;
     uint32_t ga = 0;
     for (long long t = t_begin; t < t_end; ++t) {
-      long long mt = t;
-      const int w0 = (int)(mt % p.tiles_w) * p.bw;
-      mt /= p.tiles_w;
-      const int h0 = (int)(mt % p.tiles_h) * p.bh;
-      mt /= p.tiles_h;
-      const int d0 = (int)(mt % p.tiles_d) * p.bd;
-      const int n = (int)(mt / p.tiles_d);
+      int n, d0, h0, w0;
+      wgrad_tile(t, p, n, d0, h0, w0);
       for (int g = g_begin; g < g_end; ++g, ++ga) {
         if ((int)(ga % (uint32_t)p.n_prod) != me) continue;   // stage s is always filled by producer s mod n_prod
         const int sa = (int)(ga % (uint32_t)p.stages_a);
@@ -149,13 +166,8 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     int sb = 0;
     uint32_t pb = 0;
     for (long long t = t_begin; t < t_end; ++t) {
-      long long mt = t;
-      const int w0 = (int)(mt % p.tiles_w) * p.bw;
-      mt /= p.tiles_w;
-      const int h0 = (int)(mt % p.tiles_h) * p.bh;
-      mt /= p.tiles_h;
-      const int d0 = (int)(mt % p.tiles_d) * p.bd;
-      const int n = (int)(mt / p.tiles_d);
+      int n, d0, h0, w0;
+      wgrad_tile(t, p, n, d0, h0, w0);
       mbar_wait(&empty_b[sb], pb ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&full_b[sb], (uint32_t)p.b_bytes);
@@ -517,6 +529,8 @@ static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int C
   // as three N atoms one h-line apart (N = 192).  Needs one-plane tile boxes (an h-line = bw consecutive voxel rows).
   static const bool no_halo = getenv("B2_NO_WGRAD_HALO") != nullptr;
   p.halo = (allow_halo && !no_halo && Cout == 64 && p.bd == 1 && p.bw % 8 == 0) ? 1 : 0;
+  static const bool plane_order = getenv("B2_WGRAD_PLANE_ORDER") != nullptr;
+  p.d_fast = (p.halo && !plane_order) ? 1 : 0;
   p.total_slots = (p.halo ? 9 : 27) * p.n_cchunks;
   p.SPG = 128 / p.SWC;
   p.G = ceil_div(p.total_slots, p.SPG);
