@@ -34,6 +34,8 @@ struct WgradParams {
   int halo;      // "dY-halo" mode (fixed operand 64 channels wide, one-plane tile boxes): see plan_wgrad
   int d_fast;      // K-step order (w, d, h) instead of (w, h, d): see wgrad_tile
   int stages_b;    // depth of the fixed-operand ring (2-4)
+  int grid;        // CTAs launched
+  int streamk;     // CTAs own equal runs of the column-major (column, K-step) plane: see wgrad_segment
   int merge_last;  // a CTA of the LAST group chunk (fewer groups than the others) covers this many consecutive splits
   float* ws;
 };
@@ -65,6 +67,58 @@ __device__ __forceinline__ void wgrad_tile(long long t, const WgradParams& p, in
   }
 }
 
+// One unit of work of a CTA: the K-steps [t0, t1) of the group chunk `gchunk` x cout tile `nt`; the partial goes to
+// split slice `layer`, zeros to the slices (layer, zero_to).
+struct WgSegment {
+  int gchunk, nt, layer, zero_to;
+  long long t0, t1;
+};
+
+// Three ways a 1-D grid covers the (chunk x cout tile) columns x K-steps plane:
+//  * uniform splits: CTA = (column, split), every column cut into p.splits equal K ranges;
+//  * ... with the LAST chunk's CTAs covering `merge_last` consecutive splits (a chunk with half the groups gets half
+//    the CTAs; its partial lands in the first of those split slices, zeros in the rest);
+//  * stream-K (p.streamk; columns > SMs / 2, where a uniform split would leave SMs idle — decoders.0.conv1: 81 columns):
+//    the plane is linearised column-major and cut into gridDim.x equal runs; a run touches at most two columns
+//    (= two segments, run one after the other), a column collects 2-3 partials in slice order of arrival; the last
+//    contributor zero-fills the slices its column does not use.
+__device__ __forceinline__ bool wgrad_segment(const WgradParams& p, int sg, WgSegment& s) {
+  if (p.streamk) {
+    const long long K = p.ksteps_total, total = K * p.n_gchunks * p.n_cout_tiles;
+    const long long a = total * blockIdx.x / gridDim.x, b = total * (blockIdx.x + 1) / gridDim.x;
+    const long long col0 = a / K, col1 = (b - 1) / K;
+    if (sg > (int)(col1 - col0)) return false;
+    const long long col = col0 + sg;
+    s.t0 = (sg == 0 ? a : col * K) - col * K;
+    s.t1 = (b < (col + 1) * K ? b : (col + 1) * K) - col * K;
+    s.gchunk = (int)(col % p.n_gchunks);
+    s.nt = (int)(col / p.n_gchunks);
+    // first CTA whose run holds K-step col*K: the largest j with floor(j * total / grid) <= col * K
+    const long long first = ((col * K + 1) * gridDim.x - 1) / total;
+    s.layer = (int)(blockIdx.x - first);
+    s.zero_to = (b >= (col + 1) * K) ? p.splits : s.layer + 1;
+    return true;
+  }
+  if (sg > 0) return false;
+  const int full_x = (p.n_gchunks - 1) * p.n_cout_tiles;
+  const int n_full = full_x * p.splits;
+  if ((int)blockIdx.x < n_full) {
+    s.gchunk = (int)blockIdx.x % full_x % (p.n_gchunks - 1);
+    s.nt = (int)blockIdx.x % full_x / (p.n_gchunks - 1);
+    s.layer = (int)blockIdx.x / full_x;
+    s.zero_to = s.layer + 1;
+  } else {
+    const int j = (int)blockIdx.x - n_full;
+    s.gchunk = p.n_gchunks - 1;
+    s.nt = j % p.n_cout_tiles;
+    s.layer = (j / p.n_cout_tiles) * p.merge_last;
+    s.zero_to = min(s.layer + p.merge_last, p.splits);
+  }
+  s.t0 = p.ksteps_total * s.layer / p.splits;
+  s.t1 = p.ksteps_total * s.zero_to / p.splits;
+  return true;
+}
+
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                     const WgradParams p) {
@@ -79,34 +133,11 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   uint64_t* full_b = bars + 2 * p.stages_a;
   uint64_t* empty_b = full_b + p.stages_b;
   uint64_t* acc_full = empty_b + p.stages_b;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
-
-  // 1-D grid: first the CTAs of the full group chunks (one per chunk x cout tile x split), then those of the last
-  // chunk, each covering `merge_last` consecutive splits (so a chunk with half the groups gets half the CTAs and every
-  // CTA issues about the same number of MMAs); its partial lands in the first of those split slices, zeros in the rest
-  const int full_x = (p.n_gchunks - 1) * p.n_cout_tiles;
-  const int n_full = full_x * p.splits;
-  int gchunk, nt, split, split_hi;
-  if ((int)blockIdx.x < n_full) {
-    gchunk = (int)blockIdx.x % full_x % (p.n_gchunks - 1);
-    nt = (int)blockIdx.x % full_x / (p.n_gchunks - 1);
-    split = (int)blockIdx.x / full_x;
-    split_hi = split + 1;
-  } else {
-    const int j = (int)blockIdx.x - n_full;
-    gchunk = p.n_gchunks - 1;
-    nt = j % p.n_cout_tiles;
-    split = (j / p.n_cout_tiles) * p.merge_last;
-    split_hi = min(split + p.merge_last, p.splits);
-  }
-  const int g_begin = gchunk * p.gpc;
-  const int g_end = min(g_begin + p.gpc, p.G);
-  const int n0 = nt * p.BN;
-  const long long t_begin = p.ksteps_total * split / p.splits;
-  const long long t_end = p.ksteps_total * split_hi / p.splits;
 
   if (warp == 1 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -120,6 +151,7 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       mbar_init(&empty_b[s], 1);
     }
     mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);   // every epilogue thread arrives once it has read its accumulator rows
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -130,34 +162,38 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 
   // Role loops run on the whole warp with warp-uniform control flow; only the TMA / tcgen05 instruction itself is
   // issued by an elected lane (keeps descriptors and addresses in uniform registers, see conv_igemm.cu).
+  WgSegment seg;
   if (warp >= 1 && warp <= kWgProducers) {
     // ---------------------------------------------------------------- producers of the shifted-X slot groups
     const int me = warp - 1;
     uint32_t ga = 0;
-    for (long long t = t_begin; t < t_end; ++t) {
-      int n, d0, h0, w0;
-      wgrad_tile(t, p, n, d0, h0, w0);
-      for (int g = g_begin; g < g_end; ++g, ++ga) {
-        if ((int)(ga % (uint32_t)p.n_prod) != me) continue;   // stage s is always filled by producer s mod n_prod
-        const int sa = (int)(ga % (uint32_t)p.stages_a);
-        const uint32_t pa = (ga / (uint32_t)p.stages_a) & 1u;
-        mbar_wait(&empty_a[sa], pa ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&full_a[sa], (uint32_t)p.a_bytes);
-          for (int j = 0; j < p.SPG; ++j) {
-            int s = g * p.SPG + j;
-            if (s >= p.total_slots) s = p.total_slots - 1;  // padding slot: result discarded
-            const int tap = s / p.n_cchunks, cc = s % p.n_cchunks;
-            // halo mode: a slot is a (d, w) shift of the shifted operand only (9 per chunk); the three h taps come
-            // from the h-halo of the FIXED operand's tile (three N atoms of one MMA)
-            const int dd = p.halo ? tap / 3 - 1 : tap / 9 - 1;
-            const int dh = p.halo ? 0 : (tap / 3) % 3 - 1;
-            const int dw = tap % 3 - 1;
-            tma_load_5d(smem_a + (size_t)sa * p.a_bytes + (size_t)j * p.slot_bytes, &tmap_x, &full_a[sa],
-                        cc * p.SWC, w0 + dw, h0 + dh, d0 + dd, n);
+    for (int sg = 0; wgrad_segment(p, sg, seg); ++sg) {
+      const int g_begin = seg.gchunk * p.gpc, g_end = min(g_begin + p.gpc, p.G);
+      for (long long t = seg.t0; t < seg.t1; ++t) {
+        int n, d0, h0, w0;
+        wgrad_tile(t, p, n, d0, h0, w0);
+        for (int g = g_begin; g < g_end; ++g, ++ga) {
+          if ((int)(ga % (uint32_t)p.n_prod) != me) continue;   // stage s is always filled by producer s mod n_prod
+          const int sa = (int)(ga % (uint32_t)p.stages_a);
+          const uint32_t pa = (ga / (uint32_t)p.stages_a) & 1u;
+          mbar_wait(&empty_a[sa], pa ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_a[sa], (uint32_t)p.a_bytes);
+            for (int j = 0; j < p.SPG; ++j) {
+              int s = g * p.SPG + j;
+              if (s >= p.total_slots) s = p.total_slots - 1;  // padding slot: result discarded
+              const int tap = s / p.n_cchunks, cc = s % p.n_cchunks;
+              // halo mode: a slot is a (d, w) shift of the shifted operand only (9 per chunk); the three h taps come
+              // from the h-halo of the FIXED operand's tile (three N atoms of one MMA)
+              const int dd = p.halo ? tap / 3 - 1 : tap / 9 - 1;
+              const int dh = p.halo ? 0 : (tap / 3) % 3 - 1;
+              const int dw = tap % 3 - 1;
+              tma_load_5d(smem_a + (size_t)sa * p.a_bytes + (size_t)j * p.slot_bytes, &tmap_x, &full_a[sa],
+                          cc * p.SWC, w0 + dw, h0 + dh, d0 + dd, n);
+            }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
     if (warp == 1) pdl_trigger();   // last slot loads issued: the next kernel may be staged
@@ -165,22 +201,25 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // ---------------------------------------------------------------- producer of the dY tiles
     int sb = 0;
     uint32_t pb = 0;
-    for (long long t = t_begin; t < t_end; ++t) {
-      int n, d0, h0, w0;
-      wgrad_tile(t, p, n, d0, h0, w0);
-      mbar_wait(&empty_b[sb], pb ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&full_b[sb], (uint32_t)p.b_bytes);
-        if (p.halo) {   // one box with an h-halo: (bh + 2) lines of bw voxels x 64 channels, zero-filled outside
-          tma_load_5d(smem_b + (size_t)sb * p.b_bytes, &tmap_dy, &full_b[sb], n0, w0, h0 - 1, d0, n);
-        } else {
-          for (int j = 0; j < p.BN / 64; ++j)
-            tma_load_5d(smem_b + (size_t)sb * p.b_bytes + (size_t)j * 16384, &tmap_dy, &full_b[sb], n0 + j * 64, w0,
-                        h0, d0, n);
+    for (int sg = 0; wgrad_segment(p, sg, seg); ++sg) {
+      const int n0 = seg.nt * p.BN;
+      for (long long t = seg.t0; t < seg.t1; ++t) {
+        int n, d0, h0, w0;
+        wgrad_tile(t, p, n, d0, h0, w0);
+        mbar_wait(&empty_b[sb], pb ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full_b[sb], (uint32_t)p.b_bytes);
+          if (p.halo) {   // one box with an h-halo: (bh + 2) lines of bw voxels x 64 channels, zero-filled outside
+            tma_load_5d(smem_b + (size_t)sb * p.b_bytes, &tmap_dy, &full_b[sb], n0, w0, h0 - 1, d0, n);
+          } else {
+            for (int j = 0; j < p.BN / 64; ++j)
+              tma_load_5d(smem_b + (size_t)sb * p.b_bytes + (size_t)j * 16384, &tmap_dy, &full_b[sb], n0 + j * 64, w0,
+                          h0, d0, n);
+          }
         }
+        __syncwarp();
+        if (++sb == p.stages_b) { sb = 0; pb ^= 1; }
       }
-      __syncwarp();
-      if (++sb == p.stages_b) { sb = 0; pb ^= 1; }
     }
   } else if (warp == 0) {
     // halo mode: N = 3 x 64 — the three N atoms are the SAME dY tile shifted by -1 / 0 / +1 h-lines (atom stride = one
@@ -196,84 +235,77 @@ conv3d_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const uint32_t a_kstep = (16 * row_a) >> 4, b_kstep = (16 * 128) >> 4;   // encoded advance per K16 (16 voxels)
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    for (long long t = t_begin; t < t_end; ++t) {
-      mbar_wait(&full_b[sb], pb);
-      tc_fence_after();
-      const uint64_t bdesc = b_hi | (uint64_t)(b0 + (uint32_t)sb * ((uint32_t)p.b_bytes >> 4));
-      for (int g = g_begin; g < g_end; ++g) {
-        mbar_wait(&full_a[sa], pa);
+    for (int sg = 0; wgrad_segment(p, sg, seg); ++sg) {
+      const int g_begin = seg.gchunk * p.gpc, g_end = min(g_begin + p.gpc, p.G);
+      if (sg > 0) {   // the accumulators are reused: wait until the epilogue has read the previous segment
+        mbar_wait(acc_empty, (uint32_t)(sg - 1) & 1u);
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t adesc = a_hi | (uint64_t)(a0 + (uint32_t)sa * ((uint32_t)p.a_bytes >> 4));
-          const uint32_t d_tmem = tmem_base + (uint32_t)(g - g_begin) * acc_cols;
-#pragma unroll
-          for (int k = 0; k < 8; ++k)   // 128 voxels = 8 x K16
-            umma_bf16(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc, (t != t_begin || k > 0) ? 1u : 0u);
-          umma_commit(&empty_a[sa]);
-          if (g == g_end - 1) {
-            umma_commit(&empty_b[sb]);
-            if (t == t_end - 1) umma_commit(acc_full);
-          }
-        }
-        __syncwarp();
-        if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
       }
-      if (++sb == p.stages_b) { sb = 0; pb ^= 1; }
+      for (long long t = seg.t0; t < seg.t1; ++t) {
+        mbar_wait(&full_b[sb], pb);
+        tc_fence_after();
+        const uint64_t bdesc = b_hi | (uint64_t)(b0 + (uint32_t)sb * ((uint32_t)p.b_bytes >> 4));
+        for (int g = g_begin; g < g_end; ++g) {
+          mbar_wait(&full_a[sa], pa);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t adesc = a_hi | (uint64_t)(a0 + (uint32_t)sa * ((uint32_t)p.a_bytes >> 4));
+            const uint32_t d_tmem = tmem_base + (uint32_t)(g - g_begin) * acc_cols;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)   // 128 voxels = 8 x K16
+              umma_bf16(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc, (t != seg.t0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_a[sa]);
+            if (g == g_end - 1) {
+              umma_commit(&empty_b[sb]);
+              if (t == seg.t1 - 1) umma_commit(acc_full);
+            }
+          }
+          __syncwarp();
+          if (++sa == p.stages_a) { sa = 0; pa ^= 1; }
+        }
+        if (++sb == p.stages_b) { sb = 0; pb ^= 1; }
+      }
     }
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const size_t slice4 = (size_t)27 * p.Cin * p.Cout / 4;   // one split slice of the workspace, in float4
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    for (int g = g_begin; g < g_end; ++g) {
-      const int s = g * p.SPG + row / p.SWC;
-      const bool valid = (s < p.total_slots) && (t_end > t_begin);
-      const int tap = s / p.n_cchunks;
-      const int ci = (s % p.n_cchunks) * p.SWC + row % p.SWC;
-      if (p.halo) {
-        // accumulator columns [64 j, 64 j + 64): h tap dh = 1 - j of the slot's (dd, dw) shift
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g - g_begin) * 192u;
-        for (int c0 = 0; c0 < 192; c0 += 32) {
+    for (int sg = 0; wgrad_segment(p, sg, seg); ++sg) {
+      const int g_begin = seg.gchunk * p.gpc, g_end = min(g_begin + p.gpc, p.G);
+      const int n0 = seg.nt * p.BN;
+      mbar_wait(acc_full, (uint32_t)sg & 1u);
+      tc_fence_after();
+      for (int g = g_begin; g < g_end; ++g) {
+        const int s = g * p.SPG + row / p.SWC;
+        const bool valid = s < p.total_slots;
+        const int tap = s / p.n_cchunks;
+        const int ci = (s % p.n_cchunks) * p.SWC + row % p.SWC;
+        const uint32_t acc_cols = p.halo ? 192u : (uint32_t)p.BN;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g - g_begin) * acc_cols;
+        for (int c0 = 0; c0 < (int)acc_cols; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(t_addr + c0, v);
           tmem_ld_wait();
           if (valid) {
-            const int full_tap = (tap / 3) * 9 + (2 - c0 / 64) * 3 + tap % 3;
-            float4* d4 = reinterpret_cast<float4*>(p.ws + (((size_t)split * 27 + full_tap) * p.Cin + ci) * p.Cout + n0 +
-                                                   (c0 & 63));
+            // halo mode: accumulator columns [64 j, 64 j + 64) = h tap dh = 1 - j of the slot's (dd, dw) shift
+            const int full_tap = p.halo ? (tap / 3) * 9 + (2 - c0 / 64) * 3 + tap % 3 : tap;
+            const int col = p.halo ? (c0 & 63) : c0;
+            float4* d4 = reinterpret_cast<float4*>(p.ws + (((size_t)seg.layer * 27 + full_tap) * p.Cin + ci) * p.Cout +
+                                                   n0 + col);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            for (int e = split + 1; e < split_hi; ++e) {
+            for (int e = seg.layer + 1; e < seg.zero_to; ++e) {
               d4 += slice4;
 #pragma unroll
               for (int j = 0; j < 8; ++j) d4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
         }
-        continue;
       }
-      float* dst = p.ws + (((size_t)split * 27 + tap) * p.Cin + ci) * p.Cout + n0;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g - g_begin) * p.BN;
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_addr + c0, v);
-        tmem_ld_wait();
-        if (valid) {
-          float4* d4 = reinterpret_cast<float4*>(dst + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-          for (int e = split + 1; e < split_hi; ++e) {
-            d4 += slice4;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) d4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-      }
+      tc_fence_before();
+      mbar_arrive(acc_empty);
     }
   }
 
@@ -556,6 +588,23 @@ static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int C
   }
   if ((long long)splits > p.ksteps_total) splits = (int)p.ksteps_total;
   p.splits = splits;
+  p.grid = wgrad_ctas(p, splits);
+  p.streamk = 0;
+  // more columns than half the SMs (decoders.0.conv1: 81): a uniform split cannot use the idle SMs, equal runs can
+  static const bool no_streamk = getenv("B2_NO_WGRAD_STREAMK") != nullptr;
+  const int columns = p.n_gchunks * p.n_cout_tiles;
+  if (!no_streamk && splits == 1 && columns < num_sms() && p.ksteps_total * columns >= 4LL * num_sms()) {
+    p.streamk = 1;
+    p.merge_last = 1;
+    p.grid = num_sms();
+    const long long K = p.ksteps_total, total = K * columns;
+    int slices = 1;   // the most runs any column intersects (same arithmetic as wgrad_segment)
+    for (long long col = 0; col < columns; ++col) {
+      const long long first = ((col * K + 1) * p.grid - 1) / total, last = (((col + 1) * K) * p.grid - 1) / total;
+      if ((int)(last - first + 1) > slices) slices = (int)(last - first + 1);
+    }
+    p.splits = slices;
+  }
   p.slot_bytes = 128 * p.SWC * 2;
   p.a_bytes = 128 * 128 * 2;
   p.b_bytes = p.halo ? (p.bh + 2) * p.bw * 128 : 128 * p.BN * 2;
@@ -614,7 +663,7 @@ static int wgrad_partial_impl(const void* x, int ldx, int x_coff, const void* dy
 
   const size_t smem_bytes = (size_t)p.stages_b * p.b_bytes + (size_t)p.stages_a * p.a_bytes + 1024 + 512;
   B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  dim3 grid((unsigned)wgrad_ctas(p, p.splits));
+  dim3 grid((unsigned)p.grid);
   B2_LAUNCH(conv3d_wgrad_kernel, grid, kWgThreads, smem_bytes, stream, tx, ty, p);
   B2_CHECK_CUDA(cudaGetLastError());
   return B2_OK;

@@ -241,6 +241,8 @@ WGRAD_SHAPES = [
     (2, 64, 64, 3, 9, 16),       # ragged h tiles: the halo lines of the last tile are out of range
     (1, 96, 64, 3, 8, 16),       # three 32-channel chunks
     (1, 64, 64, 2, 3, 128),      # one-line tiles (bh = 1): the halo is two thirds of the box
+    (1, 768, 256, 4, 8, 32),     # 81 (group chunk) columns > SMs / 2: stream-K runs, two segments per CTA
+    (1, 704, 256, 5, 9, 24),     # ... ragged tiles, last chunk with one group
 ]
 
 
