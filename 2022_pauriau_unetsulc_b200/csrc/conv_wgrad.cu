@@ -36,7 +36,6 @@ struct WgradParams {
   int stages_b;    // depth of the fixed-operand ring (2-4)
   int grid;        // CTAs launched
   int streamk;     // CTAs own equal runs of the column-major (column, K-step) plane: see wgrad_segment
-  int merge_last;  // a CTA of the LAST group chunk (fewer groups than the others) covers this many consecutive splits
   float* ws;
 };
 
@@ -74,14 +73,14 @@ struct WgSegment {
   long long t0, t1;
 };
 
-// Three ways a 1-D grid covers the (chunk x cout tile) columns x K-steps plane:
+// Two ways a 1-D grid covers the (chunk x cout tile) columns x K-steps plane:
 //  * uniform splits: CTA = (column, split), every column cut into p.splits equal K ranges;
-//  * ... with the LAST chunk's CTAs covering `merge_last` consecutive splits (a chunk with half the groups gets half
-//    the CTAs; its partial lands in the first of those split slices, zeros in the rest);
 //  * stream-K (p.streamk; columns > SMs / 2, where a uniform split would leave SMs idle — decoders.0.conv1: 81 columns):
 //    the plane is linearised column-major and cut into gridDim.x equal runs; a run touches at most two columns
 //    (= two segments, run one after the other), a column collects 2-3 partials in slice order of arrival; the last
 //    contributor zero-fills the slices its column does not use.
+// (Measured and dropped: CTAs of a short last chunk covering two splits each, to even out the MMA count — they then
+// load more bytes per MMA than the others and become the critical path: decoders.2.conv2 245 vs 212 us.)
 __device__ __forceinline__ bool wgrad_segment(const WgradParams& p, int sg, WgSegment& s) {
   if (p.streamk) {
     const long long K = p.ksteps_total, total = K * p.n_gchunks * p.n_cout_tiles;
@@ -100,20 +99,11 @@ __device__ __forceinline__ bool wgrad_segment(const WgradParams& p, int sg, WgSe
     return true;
   }
   if (sg > 0) return false;
-  const int full_x = (p.n_gchunks - 1) * p.n_cout_tiles;
-  const int n_full = full_x * p.splits;
-  if ((int)blockIdx.x < n_full) {
-    s.gchunk = (int)blockIdx.x % full_x % (p.n_gchunks - 1);
-    s.nt = (int)blockIdx.x % full_x / (p.n_gchunks - 1);
-    s.layer = (int)blockIdx.x / full_x;
-    s.zero_to = s.layer + 1;
-  } else {
-    const int j = (int)blockIdx.x - n_full;
-    s.gchunk = p.n_gchunks - 1;
-    s.nt = j % p.n_cout_tiles;
-    s.layer = (j / p.n_cout_tiles) * p.merge_last;
-    s.zero_to = min(s.layer + p.merge_last, p.splits);
-  }
+  const int columns = p.n_gchunks * p.n_cout_tiles;
+  s.gchunk = (int)blockIdx.x % columns % p.n_gchunks;
+  s.nt = (int)blockIdx.x % columns / p.n_gchunks;
+  s.layer = (int)blockIdx.x / columns;
+  s.zero_to = s.layer + 1;
   s.t0 = p.ksteps_total * s.layer / p.splits;
   s.t1 = p.ksteps_total * s.zero_to / p.splits;
   return true;
@@ -540,10 +530,6 @@ static void choose_box_w(int W, int H, int D, int& bw, int& bh, int& bd) {
     }
 }
 
-static int wgrad_ctas(const WgradParams& p, int splits) {
-  return ((p.n_gchunks - 1) * splits + ceil_div(splits, p.merge_last)) * p.n_cout_tiles;
-}
-
 static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int Cout, bool allow_halo) {
   p.N = N; p.D = D; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   choose_box_w(W, H, D, p.bw, p.bh, p.bd);
@@ -554,48 +540,42 @@ static int plan_wgrad(WgradParams& p, int N, int D, int H, int W, int Cin, int C
   p.n_cchunks = Cin / p.SWC;
   p.BN = (Cout % 256 == 0) ? 256 : (Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : 64));
   p.n_cout_tiles = Cout / p.BN;
-  // "dY-halo" mode for the 64-wide fixed operand (decoders.2.conv2, encoders.1.conv1, encoders.0.conv2: round 1 ran them
-  // at 640-790 TFLOP/s, bound by re-loading the shifted operand 27 times per K-step and by the 128 x 64 MMA's
-  // shared-memory read rate).  dW[tap] = sum_u X[u + s] dY[u + t] with tap = s - t: the (d, w) part of the tap shifts X
-  // (9 slots per chunk instead of 27), the h part shifts dY — whose tile is loaded ONCE with an h-halo and read by the MMA
-  // as three N atoms one h-line apart (N = 192).  Needs one-plane tile boxes (an h-line = bw consecutive voxel rows).
+  // "dY-halo" mode for Cout <= 128 at one-plane tile boxes (decoders.2.conv2, encoders.0.conv2, encoders.1.*,
+  // decoders.1.*: round 1 ran the Cout = 64 ones at 640-790 TFLOP/s, bound by re-loading the shifted operand 27 times
+  // per K-step and by the 128 x 64 MMA's shared-memory read rate).  dW[tap] = sum_u X[u + s] dY[u + t] with
+  // tap = s - t: the (d, w) part of the tap shifts X (9 slots per chunk instead of 27), the h part shifts dY — whose
+  // 64-channel tile is loaded ONCE with an h-halo and read by the MMA as three N atoms one h-line apart (N = 192).
+  // Needs an h-line to be bw consecutive, 1024-byte-aligned voxel rows.  Measured (us, incl. reduce): dec2.conv2
+  // 293 -> 212, enc0.conv2 179 -> 143, enc1.conv1 59 -> 48, dec1.conv1 289 -> 257, dec1.conv2 112 -> 99, enc1.conv2
+  // 86 -> 67.
   static const bool no_halo = getenv("B2_NO_WGRAD_HALO") != nullptr;
-  p.halo = (allow_halo && !no_halo && Cout == 64 && p.bd == 1 && p.bw % 8 == 0) ? 1 : 0;
+  static const int halo_max_c = getenv("B2_WGRAD_HALO_MAXC") ? atoi(getenv("B2_WGRAD_HALO_MAXC")) : 128;
+  p.halo = (allow_halo && !no_halo && Cout % 64 == 0 && Cout <= halo_max_c && p.bd == 1 && p.bw % 8 == 0) ? 1 : 0;
+  if (p.halo) {   // 64-channel N tiles, each read as three h-shifted atoms
+    p.BN = 64;
+    p.n_cout_tiles = Cout / 64;
+  }
   static const bool plane_order = getenv("B2_WGRAD_PLANE_ORDER") != nullptr;
   p.d_fast = (p.halo && !plane_order) ? 1 : 0;
   p.total_slots = (p.halo ? 9 : 27) * p.n_cchunks;
   p.SPG = 128 / p.SWC;
   p.G = ceil_div(p.total_slots, p.SPG);
-  const int P = p.halo ? 2 : 512 / p.BN;
+  const int P = p.halo ? 2 : 512 / p.BN;   // accumulators per CTA (one group per CTA measured slower: 237 vs 211 us)
   p.n_gchunks = ceil_div(p.G, P);
   p.gpc = ceil_div(p.G, p.n_gchunks);
   p.n_gchunks = ceil_div(p.G, p.gpc);
   p.ksteps_total = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w;
-  // the last chunk may hold fewer groups than the others (halo mode: 5 groups as 2 + 2 + 1): its CTAs then cover
-  // merge_last splits each, and the freed SMs go to a finer split
-  // (a merged CTA runs twice the K-steps at half the MMAs per step, which only pays if the split gets >= 10 % finer:
-  // measured, 384 -> 128 with one group of four merged x4 went from 280 to 435 us, bound by its per-step loads)
-  const int g_last = p.G - (p.n_gchunks - 1) * p.gpc;
-  p.merge_last = 1;
-  int splits = 1;
-  while (wgrad_ctas(p, splits + 1) <= num_sms()) ++splits;
-  static const bool no_merge = getenv("B2_NO_WGRAD_MERGE") != nullptr;
-  if (p.n_gchunks > 1 && 2 * g_last <= p.gpc && !no_merge) {
-    p.merge_last = 2;
-    int s2 = 1;
-    while (wgrad_ctas(p, s2 + 1) <= num_sms()) ++s2;
-    if (s2 * 10 >= splits * 11) splits = s2; else p.merge_last = 1;
-  }
+  const int columns = p.n_gchunks * p.n_cout_tiles;
+  int splits = num_sms() / columns;
+  if (splits < 1) splits = 1;
   if ((long long)splits > p.ksteps_total) splits = (int)p.ksteps_total;
   p.splits = splits;
-  p.grid = wgrad_ctas(p, splits);
+  p.grid = columns * splits;
   p.streamk = 0;
   // more columns than half the SMs (decoders.0.conv1: 81): a uniform split cannot use the idle SMs, equal runs can
   static const bool no_streamk = getenv("B2_NO_WGRAD_STREAMK") != nullptr;
-  const int columns = p.n_gchunks * p.n_cout_tiles;
   if (!no_streamk && splits == 1 && columns < num_sms() && p.ksteps_total * columns >= 4LL * num_sms()) {
     p.streamk = 1;
-    p.merge_last = 1;
     p.grid = num_sms();
     const long long K = p.ksteps_total, total = K * columns;
     int slices = 1;   // the most runs any column intersects (same arithmetic as wgrad_segment)

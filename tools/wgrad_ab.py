@@ -23,7 +23,8 @@ def timeit(fn, n=20):
 
 for name, cin, cout, dims in (("dec2.conv2", 64, 64, (96, 112, 96)), ("enc0.conv2", 32, 64, (96, 112, 96)),
                               ("enc1.conv1", 64, 64, (48, 56, 48)), ("dec2.conv1", 192, 64, (96, 112, 96)), ("dec0.conv1", 768, 256, (24, 28, 24)),
-                              ("dec0.conv2", 256, 256, (24, 28, 24))):
+                              ("dec0.conv2", 256, 256, (24, 28, 24)), ("dec1.conv1", 384, 128, (48, 56, 48)),
+                              ("dec1.conv2", 128, 128, (48, 56, 48)), ("enc1.conv2", 64, 128, (48, 56, 48))):
     D, H, W = dims
     x = ops.ActView(torch.randn(1, D, H, W, cin, device="cuda").bfloat16(), 1, D, H, W, cin)
     dy = ops.ActView(torch.randn(1, D, H, W, cout, device="cuda").bfloat16(), 1, D, H, W, cout)
