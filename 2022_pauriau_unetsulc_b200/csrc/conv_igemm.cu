@@ -28,6 +28,7 @@ struct IgemmParams {
   int n_tiles_n, BN;
   int KC, n_chunks;
   int stages;
+  int stages_b;        // halo variant: depth of the separate weight-tile ring
   int a_bytes, b_bytes;
   int relu;
   int ldy, y_coff;
@@ -69,20 +70,28 @@ __device__ __forceinline__ void decode_tile(long long tile, const IgemmParams& p
 // loops inside `if (lane == 0)` made every descriptor take the R2UR path into the uniform datapath and cost ~140
 // cycles per tcgen05.mma issue — the issuing thread, not TMA or the tensor pipe, bounded the kernel at ~900 cycles
 // per stage.)
-template <int KC>
+// HALO variant (KC = 64, one-plane tile boxes bw x bh with bw % 8 == 0): the A ring holds tiles with an h-halo —
+// bh + 2 lines of bw voxels, one line = bw / 8 whole 1 024-byte swizzle atoms — loaded once per (d, w) tap pair and
+// channel chunk; the three h taps read the same tile through descriptors that start one line apart.  A loads drop from 27 to 9 per chunk and tile (the
+// plain kernel sits on the L2 -> SM limit: 16 KB of A + BN x 128 B of weights per four MMAs); the weight tiles get a
+// ring of their own (one stage per tap and chunk).
+template <int KC, bool HALO>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const IgemmParams p) {
   pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int kABytes = 128 * KC * 2;
+  const int kABytes = HALO ? p.a_bytes : 128 * KC * 2;   // HALO: (bh + 2) lines of bw voxels (runtime)
+  const int n_bstages = HALO ? p.stages_b : p.stages;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)p.stages * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * p.b_bytes);
-  uint64_t* full = bars;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)n_bstages * p.b_bytes);
+  uint64_t* full = bars;                    // HALO: the A ring's barriers
   uint64_t* empty = bars + p.stages;
-  uint64_t* tmem_full = bars + 2 * p.stages;
+  uint64_t* full_b = bars + 2 * p.stages;   // HALO only: the weight ring's barriers
+  uint64_t* empty_b = full_b + (HALO ? p.stages_b : 0);
+  uint64_t* tmem_full = empty_b + (HALO ? p.stages_b : 0);
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -93,8 +102,14 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full[s], 2);   // A loader + B loader each arrive with their own expect_tx
+      mbar_init(&full[s], HALO ? 1 : 2);   // plain: A loader + B loader each arrive with their own expect_tx
       mbar_init(&empty[s], 1);
+    }
+    if (HALO) {
+      for (int s = 0; s < p.stages_b; ++s) {
+        mbar_init(&full_b[s], 1);
+        mbar_init(&empty_b[s], 1);
+      }
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -113,6 +128,45 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int me = (warp - 1) >> 1;
     const bool loads_a = ((warp - 1) & 1) == 0;
     uint32_t gs = 0;  // global stage counter, identical in every producer and in the MMA issuer
+    if constexpr (HALO) {
+      // item order (shared with the MMA issuer): (dd, dw, chunk) for the A ring, (dd, dw, chunk, dh) for the weights
+      for (long long work = blockIdx.x; work < p.total_tiles; work += gridDim.x) {
+        int n, d0, h0, w0, n0;
+        decode_tile(work, p, n, d0, h0, w0, n0);
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const int dd = t9 / 3 - 1, dw = t9 % 3 - 1;
+          for (int ch = 0; ch < p.n_chunks; ++ch) {
+            if (loads_a) {
+              if ((int)(gs % kProducerPairs) == me) {
+                const int stage = (int)(gs % (uint32_t)p.stages);
+                const uint32_t phase = (gs / (uint32_t)p.stages) & 1u;
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (elect_one()) {
+                  mbar_arrive_expect_tx(&full[stage], (uint32_t)kABytes);
+                  tma_load_5d(smem_a + (size_t)stage * kABytes, &tmap_a, &full[stage], ch * KC, w0 + dw, h0 - 1,
+                              d0 + dd, n);
+                }
+                __syncwarp();
+              }
+              ++gs;
+            } else {
+              for (int j = 0; j < 3; ++j, ++gs) {   // dh = j - 1
+                if ((int)(gs % kProducerPairs) != me) continue;
+                const int stage = (int)(gs % (uint32_t)p.stages_b);
+                const uint32_t phase = (gs / (uint32_t)p.stages_b) & 1u;
+                mbar_wait(&empty_b[stage], phase ^ 1);
+                if (elect_one()) {
+                  mbar_arrive_expect_tx(&full_b[stage], (uint32_t)p.b_bytes);
+                  tma_load_2d(smem_b + (size_t)stage * p.b_bytes, &tmap_b, &full_b[stage], ch * KC,
+                              ((dd + 1) * 9 + j * 3 + (dw + 1)) * p.Cout + n0);
+                }
+                __syncwarp();
+              }
+            }
+          }
+        }
+      }
+    } else
     for (long long work = blockIdx.x; work < p.total_tiles * p.splits; work += gridDim.x) {
       int n, d0, h0, w0, n0;
       decode_tile(work % p.total_tiles, p, n, d0, h0, w0, n0);
@@ -151,6 +205,43 @@ conv3d_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int stage = 0;
     uint32_t phase = 0;
     uint32_t it = 0;
+    if constexpr (HALO) {
+      int sb = 0;
+      uint32_t pb = 0;
+      const int n_items = 9 * p.n_chunks;
+      const uint32_t line_units = (uint32_t)p.bw * 8u;   // one h-line = bw voxels x 128 B, in 16-byte units
+      for (long long work = blockIdx.x; work < p.total_tiles; work += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int i = 0; i < n_items; ++i) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          for (int j = 0; j < 3; ++j) {
+            mbar_wait(&full_b[sb], pb);
+            tc_fence_after();
+            if (elect_one()) {
+              // h tap dh = j - 1: output line l reads tile line l + j
+              const uint64_t adesc = desc_hi | (uint64_t)(a0 + (uint32_t)stage * a_step + (uint32_t)j * line_units);
+              const uint64_t bdesc = desc_hi | (uint64_t)(b0 + (uint32_t)sb * b_step);
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (i | j | k) != 0 ? 1u : 0u);
+              umma_commit(&empty_b[sb]);
+              if (j == 2) {
+                umma_commit(&empty[stage]);
+                if (i == n_items - 1) umma_commit(&tmem_full[acc]);
+              }
+            }
+            __syncwarp();
+            if (++sb == p.stages_b) { sb = 0; pb ^= 1; }
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else
     for (long long work = blockIdx.x; work < p.total_tiles * p.splits; work += gridDim.x, ++it) {
       const int split = (int)(work / p.total_tiles);
       const int n_stage_per_tile = (27 * (split + 1) / p.splits - 27 * split / p.splits) * p.n_chunks;
@@ -704,6 +795,43 @@ static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpa
     B2_CHECK_CUDA(cudaGetLastError());
     return B2_OK;
   }
+  // h-halo variant (see the kernel): 64-channel chunks, no split-K, one-plane tile boxes.  B2_IGEMM_HALO = widest N
+  // tile that takes it (0: never).  Measured (us, plain -> halo): decoders.2.conv1 dgrad 529 -> 472, decoders.1.conv1
+  // fprop 286 -> 275, dgrad 254 -> 247, decoders.1.conv2 105 -> 101, encoders.2.conv2 dgrad 41 -> 36.
+  static const int halo_mode = getenv("B2_IGEMM_HALO") ? atoi(getenv("B2_IGEMM_HALO")) : 256;
+  if (halo_mode > 0 && p.KC == 64 && p.splits == 1 && BN <= halo_mode) {
+    // box with whole swizzle atoms per line (bw % 8 == 0): least padding first, then the smallest halo (largest bh)
+    long long best = -1;
+    int hbw = 8, hbh = 16;
+    for (int cw = 8; cw <= 32; cw *= 2) {
+      const int chh = 128 / cw;
+      const long long cost = (long long)ceil_div(W, cw) * cw * ceil_div(H, chh) * chh * 64 - chh;
+      if (best < 0 || cost < best) { best = cost; hbw = cw; hbh = chh; }
+    }
+    const int a_halo = (hbh + 2) * hbw * 128;
+    int stages_b = (smem_budget - kProducerPairs * a_halo) / p.b_bytes;
+    if (stages_b > 12) stages_b = 12;
+    stages_b = (stages_b / kProducerPairs) * kProducerPairs;
+    if (stages_b >= kProducerPairs) {
+      p.bw = hbw; p.bh = hbh; p.bd = 1;
+      p.tiles_w = ceil_div(W, p.bw);
+      p.tiles_h = ceil_div(H, p.bh);
+      p.tiles_d = D;
+      p.total_tiles = (long long)N * p.tiles_d * p.tiles_h * p.tiles_w * p.n_tiles_n;
+      p.a_bytes = a_halo;
+      p.stages = kProducerPairs;
+      p.stages_b = stages_b;
+      rc = make_act_tmap(&ta, x, N, D, H, W, Cin, ldx, x_coff, p.KC, p.bw, p.bh + 2, p.bd);
+      if (rc) return rc;
+      const size_t smem_h = (size_t)p.stages * p.a_bytes + (size_t)p.stages_b * p.b_bytes + 1024 + 512;
+      const long long grid_h = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+      B2_CHECK_CUDA(cudaFuncSetAttribute((conv3d_igemm_kernel<64, true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024));
+      B2_LAUNCH((conv3d_igemm_kernel<64, true>), (unsigned)grid_h, kThreads, smem_h, stream, ta, tb, p);
+      B2_CHECK_CUDA(cudaGetLastError());
+      return B2_OK;
+    }
+  }
   const size_t smem_bytes = (size_t)p.stages * (p.a_bytes + p.b_bytes) + 1024 + 512;
   if (p.splits > 1) {   // partial tiles: dense fp32 [split][voxel][Cout], no ReLU before the reduction
     p.y = nullptr;
@@ -715,11 +843,13 @@ static int conv3d_igemm_impl(const void* x, int ldx, int x_coff, const void* wpa
   const long long work_items = p.total_tiles * p.splits;
   long long grid = work_items < num_sms() ? work_items : num_sms();
   if (p.KC == 64) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B2_LAUNCH(conv3d_igemm_kernel<64>, (unsigned)grid, kThreads, smem_bytes, stream, ta, tb, p);
+    B2_CHECK_CUDA(cudaFuncSetAttribute((conv3d_igemm_kernel<64, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024));
+    B2_LAUNCH((conv3d_igemm_kernel<64, false>), (unsigned)grid, kThreads, smem_bytes, stream, ta, tb, p);
   } else {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv3d_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B2_LAUNCH(conv3d_igemm_kernel<32>, (unsigned)grid, kThreads, smem_bytes, stream, ta, tb, p);
+    B2_CHECK_CUDA(cudaFuncSetAttribute((conv3d_igemm_kernel<32, false>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024));
+    B2_LAUNCH((conv3d_igemm_kernel<32, false>), (unsigned)grid, kThreads, smem_bytes, stream, ta, tb, p);
   }
   B2_CHECK_CUDA(cudaGetLastError());
   if (p.splits > 1) {
