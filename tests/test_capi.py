@@ -44,3 +44,27 @@ def test_sass_contains_tcgen05_and_tma():
     assert "UTMALDG" in sass          # cp.async.bulk.tensor
     assert "LDTM" in sass             # tcgen05.ld
     assert "HMMA." not in sass.replace("UTCHMMA", "")   # no legacy mma.sync path
+
+
+def test_wgrad_plan_of_the_baseline_layers():
+    """The weight-gradient launch plan, read back on the CPU through the workspace size (= split slices x 27 x Cin x
+    Cout fp32; 148 SMs assumed without a device): halo mode cuts Cout <= 128 layers into 64-channel N tiles with 9
+    shifted slots per chunk, decoders.0.conv1 (81 columns > 74) takes stream-K runs with three partial slices."""
+    from unetsulc_b200 import _lib
+    lib = _lib.load()
+    expect = {
+        # (Cin, Cout, D, H, W): split slices
+        (64, 64, 96, 112, 96): 49,      # halo: 5 groups as 2 + 2 + 1 chunks -> 3 columns
+        (32, 64, 96, 112, 96): 74,      # halo, 32-channel slots: 3 groups as 2 + 1
+        (192, 64, 96, 112, 96): 21,     # roles swapped (dY shifted), N = 192: 7 columns
+        (384, 128, 48, 56, 48): 5,      # halo, two 64-channel N tiles x 14 chunks
+        (128, 128, 48, 56, 48): 14,
+        (64, 128, 48, 56, 48): 24,
+        (768, 256, 24, 28, 24): 3,      # stream-K
+        (256, 256, 24, 28, 24): 5,
+        (256, 512, 12, 14, 12): 2,
+    }
+    for (cin, cout, d, h, w), splits in expect.items():
+        nbytes = lib.b2_conv3d_wgrad_workspace_bytes(1, d, h, w, cin, cout)
+        assert nbytes == splits * 27 * cin * cout * 4, (cin, cout, nbytes // (27 * cin * cout * 4))
+    assert lib.b2_conv3d_wgrad_workspace_bytes(1, 8, 8, 8, 48, 64) == -1   # Cin must be a multiple of 32
