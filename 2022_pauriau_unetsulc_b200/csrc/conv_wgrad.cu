@@ -10,6 +10,10 @@
 // slot group).  Each CTA owns up to 512/BN accumulators (slot groups) in TMEM and a contiguous range of
 // K-steps; partial results go to a fp32 workspace [split][tap][ci][co] and a second kernel reduces the splits
 // deterministically into PyTorch's [co][ci][kd][kh][kw] layout.
+//
+// Round 2 added two planning modes (plan_wgrad): the "dY-halo" mode for Cout <= 128 at one-plane tile boxes — X is
+// shifted only in (d, w), the three h taps are three N atoms of ONE dY tile loaded with an h-halo (N = 192 per MMA) —
+// and stream-K runs when a uniform K split would leave SMs idle (wgrad_segment).
 #include "common.h"
 #include "ptx.cuh"
 #include <stdlib.h>
@@ -31,7 +35,7 @@ struct WgradParams {
   long long ksteps_total;
   int stages_a, n_prod;   // ring depth (a multiple of n_prod) and number of active slot-group producers
   int a_bytes, b_bytes, slot_bytes;
-  int halo;      // "dY-halo" mode (fixed operand 64 channels wide, one-plane tile boxes): see plan_wgrad
+  int halo;        // "dY-halo" mode (64-channel N tiles read as three h-shifted atoms): see plan_wgrad
   int d_fast;      // K-step order (w, d, h) instead of (w, h, d): see wgrad_tile
   int stages_b;    // depth of the fixed-operand ring (2-4)
   int grid;        // CTAs launched
