@@ -14,6 +14,8 @@
 // per ~735 cycles whatever its size (<= 32 KB) and however many are in flight, while ops issued by different warps
 // proceed in parallel (1/2/4 warps: 22/45/89 B/clk/SM).  Stage s of the ring is filled by producer pair (s mod 4):
 // the even warp of the pair loads the A box, the odd warp the weight tile.
+// Round 2: the HALO instantiation (64-channel chunks, one-plane tile boxes) loads each A tile once per (d, w) tap pair
+// with an h-halo and takes the three h taps from it by descriptor offsets; see the comment above the kernel.
 #include "common.h"
 #include "ptx.cuh"
 #include <stdlib.h>
